@@ -1,0 +1,204 @@
+"""Generate tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (imported from /root/reference
+through oracle/ref_shims.py), and check that the oracle restatement reproduces it bit-for-bit on CPU.
+
+Build-container only:   python -m oracle.gen_golden
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Golden files (small, committed):
+  kalman_demo.npz     the reference's only known-answer snippet (deep_sort/sort/kalman_filter.py:259-273)
+  kalman_batch.npz    seeded KalmanFilter.initiate/predict/update/gating_distance in/out
+  assoc_seq.npz       24-frame DeepSort.update sequence with an injected extractor: per-frame inputs
+                      (boxes, features, class ids) and the reference's (K,6) int32 outputs + track tables
+  tiny416.npz         yolov3-tiny 416: head outputs digest, soft_non_max_suppression output, one frame
+  reid.npz            Extractor features for boxes on one frame (crop + cv2.resize + Net)
+"""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+from . import ref_shims
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+CFG_DIR = os.path.join(os.path.dirname(HERE), "config")
+
+
+def _eq(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b):
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64)).max() if a.shape == b.shape else "shape"
+        raise AssertionError(f"oracle != reference for {what}: max diff {d}")
+    print(f"  oracle == reference (bit-exact): {what}")
+
+
+def _close(a, b, tol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.abs(a - b).max()
+    if a.shape != b.shape or d > tol:
+        raise AssertionError(f"oracle != reference for {what}: max diff {d} > {tol}")
+    print(f"  oracle ~= reference (max abs diff {d:.3g} <= {tol}): {what}")
+
+
+def gen_kalman():
+    from deep_sort.sort.kalman_filter import KalmanFilter
+    from . import sort_ref as S
+    kf = KalmanFilter()
+    m, c = kf.initiate(torch.tensor([10, 15, 0.5, 10]))
+    diag0 = torch.diagonal(c[0]).numpy().copy()
+    m, c = kf.predict(m, c)
+    diag1 = torch.diagonal(c[0]).numpy().copy()
+    m, c = kf.update(m, c, torch.tensor([12, 20, 0.6, 11]))
+    m2, c2 = kf.initiate(torch.tensor([12, 13, 0.7, 5]))
+    m2, c2 = kf.predict(m2, c2)
+    m2, c2 = kf.update(m2, c2, torch.tensor([13, 14, 0.7, 8]))
+    meas = torch.tensor([[12, 20, 0.6, 11], [20, 16, 0.4, 18]])
+    maha = kf.gating_distance(torch.cat((m, m2), 0), torch.cat((c, c2), 0), meas)
+    np.savez(os.path.join(GOLD, "kalman_demo.npz"), diag_init=diag0, diag_pred=diag1, mean_upd=m.numpy(),
+             cov_upd=c.numpy(), maha4=maha.numpy())
+    # oracle on the same snippet
+    om, oc = S.kf_initiate(torch.tensor([10, 15, 0.5, 10]))
+    _eq(torch.diagonal(oc[0]), diag0, "kf.initiate")
+    om, oc = S.kf_predict(om, oc)
+    _eq(torch.diagonal(oc[0]), diag1, "kf.predict")
+    om, oc = S.kf_update(om, oc, torch.tensor([12, 20, 0.6, 11]))
+    _eq(om, m, "kf.update mean"); _eq(oc, c, "kf.update cov")
+
+    rng = np.random.default_rng(7)
+    n, mm = 64, 48
+    xyah = np.stack([rng.uniform(0, 600, n), rng.uniform(0, 600, n), rng.uniform(0.3, 0.7, n), rng.uniform(40, 160, n)], 1).astype(np.float32)
+    means, covs = zip(*[kf.initiate(torch.from_numpy(x)) for x in xyah])
+    mean0, cov0 = torch.cat(means, 0), torch.cat(covs, 0)
+    mean1, cov1 = kf.predict(mean0, cov0)
+    z = (xyah + rng.normal(0, [2, 2, 0.01, 2], (n, 4))).astype(np.float32)
+    mean2, cov2 = kf.update(mean1, cov1, torch.from_numpy(z))
+    mean3, cov3 = kf.predict(mean2, cov2)
+    dets = np.concatenate([z[:mm - 8] + rng.normal(0, [4, 4, 0.01, 3], (mm - 8, 4)),
+                           np.stack([rng.uniform(0, 600, 8), rng.uniform(0, 600, 8), rng.uniform(0.3, 0.7, 8), rng.uniform(40, 160, 8)], 1)], 0).astype(np.float32)
+    gate2 = kf.gating_distance(mean3, cov3, torch.from_numpy(dets), only_position=True)
+    np.savez(os.path.join(GOLD, "kalman_batch.npz"), xyah=xyah, mean0=mean0.numpy(), cov0=cov0.numpy(),
+             mean1=mean1.numpy(), cov1=cov1.numpy(), z=z, mean2=mean2.numpy(), cov2=cov2.numpy(),
+             mean3=mean3.numpy(), cov3=cov3.numpy(), dets_xyah=dets, gate2=gate2.numpy())
+    o1 = S.kf_predict(mean0, cov0); _eq(o1[0], mean1, "batch predict mean"); _eq(o1[1], cov1, "batch predict cov")
+    o2 = S.kf_update(mean1, cov1, torch.from_numpy(z)); _eq(o2[0], mean2, "batch update mean"); _eq(o2[1], cov2, "batch update cov")
+    _eq(S.kf_gating_position(mean3, cov3, torch.from_numpy(dets)), gate2, "gating (position only)")
+
+
+def gen_assoc():
+    from deep_sort import DeepSort
+    from . import sort_ref as S
+    from .synth import Scenario
+    sc = Scenario(n=40, seed=3, p_miss=0.08, p_new=0.03, p_leave=0.02)
+    frames = [sc.step() for _ in range(24)]
+    feats_now = {}
+
+    class Inject:                                    # extractor injection point, deep_sort/deep_sort.py:28-31
+        def __call__(self, crops):
+            return torch.from_numpy(feats_now["f"])
+
+    frame_img = np.zeros((608, 608, 3), np.uint8)
+    kw = dict(max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
+    ref = DeepSort(Inject(), min_confidence=1, use_cuda=False, **kw)
+    orc = S.DeepSortRef(lambda fr, tl: torch.from_numpy(feats_now["f"]), **kw)
+    out = {}
+    for t, (tl, ft, cl) in enumerate(frames):
+        ft = ft.astype(np.float16).astype(np.float32)      # stored as fp16 in the fixture: keep it lossless
+        feats_now["f"] = ft
+        r = ref.update(torch.from_numpy(tl.copy()), torch.ones(len(tl)), frame_img, torch.from_numpy(cl))
+        o = orc.update(tl.copy(), None, frame_img, torch.from_numpy(cl))
+        r = np.asarray(r, np.int32).reshape(-1, 6)
+        o = np.asarray(o, np.int32).reshape(-1, 6)
+        _eq(o, r, f"DeepSort.update frame {t} ({len(tl)} dets -> {len(r)} rows)")
+        trk = ref.tracker.tracks
+        tab = np.array([[k.track_id, k.hits, k.age, k.time_since_update, k.state] for k in trk], np.int32).reshape(-1, 5)
+        st = orc.tracker.state_arrays()
+        _eq(np.stack([st["ids"], st["hits"], st["age"], st["tsu"], st["state"]], 1).reshape(-1, 5), tab, f"track table frame {t}")
+        if len(trk):
+            _eq(st["mean"], torch.cat([k.mean for k in trk], 0).numpy(), f"track means frame {t}")
+            _eq(st["cov"], torch.cat([k.covariance for k in trk], 0).numpy(), f"track covs frame {t}")
+        out[f"tlwh_{t}"], out[f"feat_{t}"], out[f"cls_{t}"] = tl, ft.astype(np.float16), cl
+        out[f"out_{t}"], out[f"table_{t}"] = r, tab
+        out[f"mean_{t}"] = st["mean"]
+    out["n_frames"] = np.int32(len(frames))
+    out["params"] = np.array([kw["max_dist"], kw["max_iou_distance"], kw["max_age"], kw["n_init"], kw["nn_budget"]], np.float64)
+    np.savez_compressed(os.path.join(GOLD, "assoc_seq.npz"), **out)
+
+
+def gen_tiny():
+    from yolo3.models import Darknet
+    from yolo3.utils.model_build import soft_non_max_suppression
+    from . import darknet_ref as D
+    from .synth import make_frame, darknet_weights, frame_to_input
+    cfg = os.path.join(CFG_DIR, "yolov3-tiny.cfg")
+    blocks = D.parse_cfg(cfg)
+    frames = [make_frame(416, 416, seed=s) for s in (0, 1)]
+    ws, info = darknet_weights(blocks, frames, seed=0, target=50)
+    print("  tiny416 calibration:", info)
+    with tempfile.TemporaryDirectory() as td:
+        wpath = os.path.join(td, "tiny.weights")
+        D.write_weights(wpath, blocks, ws)
+        model = Darknet(cfg, img_size=(416, 416))
+        model.load_darknet_weights(wpath)
+        model.eval()
+        _, ws2 = D.read_weights(wpath, blocks)
+    for a, b in zip(ws, ws2):
+        _eq(a["w"], b["w"], "weights roundtrip") if a is ws[0] else None
+    x = frame_to_input(frames[0])
+    with torch.no_grad():
+        pred = model(x)
+        dets = soft_non_max_suppression(pred.clone(), 0.5, 0.4)[0]
+    op = D.forward(blocks, ws2, x)
+    _eq(op, pred, "Darknet.forward yolov3-tiny 416")
+    od = D.postprocess(op[0].numpy(), 0.5, 0.4)
+    _eq(od, dets.numpy(), f"soft_non_max_suppression ({len(od)} detections)")
+    sel = np.argsort(-pred[0, :, 4].numpy(), kind="stable")[:256]
+    np.savez_compressed(os.path.join(GOLD, "tiny416.npz"), frame_seed=np.int32(0), weight_seed=np.int32(0),
+                        pred_top_idx=sel.astype(np.int32), pred_top=pred[0, sel].numpy(), dets=dets.numpy(),
+                        pred_sha256=np.frombuffer(hashlib.sha256(pred.numpy().tobytes()).digest(), np.uint8))
+
+
+def gen_reid():
+    from deep_sort.deep.feature_extractor import Extractor
+    from . import reid_ref as R
+    from .synth import make_frame, reid_state_dict
+    from .cv_resize_ref import crops_to_batch
+    sd = reid_state_dict(seed=0)
+    frame = make_frame(608, 608, seed=5)
+    rng = np.random.default_rng(11)
+    m = 12
+    tlwh = np.stack([rng.uniform(-5, 540, m), rng.uniform(-5, 470, m), rng.uniform(20, 90, m), rng.uniform(40, 160, m)], 1).astype(np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "ckpt.t7")
+        torch.save({"net_dict": sd}, p)
+        ex = Extractor(p, use_cuda=False)
+    H, W = frame.shape[:2]
+    crops = []
+    for b in torch.from_numpy(tlwh):                  # deep_sort/deep_sort.py:116-122,138-141
+        x, y, w, h = b
+        x1, x2, y1, y2 = max(int(x), 0), min(int(x + w), W - 1), max(int(y), 0), min(int(y + h), H - 1)
+        crops.append(frame[y1:y2, x1:x2])
+    feats = ex(crops)
+    of = R.extract(sd, frame, tlwh)
+    # crop + fixed-point resize + normalisation are bit-exact; the 20-conv fp32 stack is compared with a
+    # tolerance because oneDNN's fp32 conv result depends on buffer placement (observed 2e-7).
+    _eq(crops_to_batch(frame, tlwh), ex._preprocess(crops).numpy(), "Extractor._preprocess (crop + cv2.resize + normalise)")
+    _close(of, feats, 1e-6, "Extractor features (Net forward)")
+    np.savez_compressed(os.path.join(GOLD, "reid.npz"), frame_seed=np.int32(5), weight_seed=np.int32(0), tlwh=tlwh,
+                        feats=feats.numpy())
+
+
+def main():
+    ref_shims.install()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_reid):
+        print(fn.__name__)
+        fn()
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
