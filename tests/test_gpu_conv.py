@@ -1,0 +1,64 @@
+"""Parity of the tcgen05 implicit-GEMM convolution (and the direct first-layer kernel) against a plain PyTorch fp32
+convolution of the same fp16-rounded operands.  Tolerance: the kernel accumulates in fp32 and rounds the result to fp16
+once, so |y - ref| <= 2e-3 * max(1, |ref|) (fp16 has 11 significand bits -> 4.9e-4 relative; the margin covers the
+accumulation-order difference); fp32-output (YOLO head) cases use 1e-3 relative to the output scale."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from util import DEV, conv2d_abi, conv2d_ref
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, N, H, W, cin, cout, k, stride, bn, act, res_mode, out_f32
+    ("1x1_s1_19", 1, 19, 19, 64, 32, 1, 1, True, 1, 0, False),
+    ("3x3_s1_38", 1, 38, 38, 64, 128, 3, 1, True, 1, 0, False),
+    ("3x3_s1_bk32", 1, 40, 24, 32, 64, 3, 1, True, 1, 0, False),
+    ("3x3_s1_bk16", 1, 26, 26, 16, 32, 3, 1, True, 1, 0, False),
+    ("3x3_s2_76", 1, 76, 76, 64, 128, 3, 2, True, 1, 0, False),
+    ("3x3_s2_bk32", 1, 64, 64, 32, 64, 3, 2, True, 2, 0, False),
+    ("3x3_s2_odd_tiles", 2, 38, 38, 128, 256, 3, 2, True, 1, 0, False),
+    ("1x1_s2_batch3", 3, 64, 32, 64, 128, 1, 2, True, 0, 0, False),
+    ("head_255_f32", 1, 19, 19, 1024, 255, 1, 1, False, 0, 0, True),
+    ("res_after_act", 1, 38, 38, 128, 256, 3, 1, True, 1, 1, False),
+    ("res_before_relu_batch5", 5, 32, 16, 128, 128, 3, 1, True, 3, 2, False),
+    ("mish_1x1", 1, 76, 76, 128, 64, 1, 1, True, 2, 0, False),
+    ("deep_k_wide_n", 1, 19, 19, 512, 1024, 3, 1, True, 1, 0, False),
+    ("reid_8x4_batch7", 7, 8, 4, 512, 512, 3, 1, True, 3, 0, False),
+    ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
+    ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
+    ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_parity(case):
+    name, N, H, W, cin, cout, k, stride, use_bn, act, res_mode, out_f32 = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    x = torch.randn(N, H, W, cin, generator=g)
+    x = (x.to(DEV) if cin == 3 else x.half().to(DEV))
+    w = (torch.randn(cout, cin, k, k, generator=g) * float(np.sqrt(2.0 / (cin * k * k)))).numpy()
+    bn = bias = None
+    if use_bn:
+        bn = [(1 + 0.1 * torch.randn(cout, generator=g)).numpy(), (0.1 * torch.randn(cout, generator=g)).numpy(),
+              (0.1 * torch.randn(cout, generator=g)).numpy(), (0.5 + torch.rand(cout, generator=g)).numpy()]
+        if cin == 3:
+            bias = (0.1 * torch.randn(cout, generator=g)).numpy()
+    else:
+        bias = (0.1 * torch.randn(cout, generator=g)).numpy()
+    res = None
+    if res_mode:
+        pad = (k - 1) // 2
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        res = torch.randn(N, Ho, Wo, cout, generator=g).half().to(DEV)
+    y = conv2d_abi(x, w, stride, bn, bias, act, res, res_mode, out_f32).float()
+    ref = conv2d_ref(x, w, stride, bn, bias, act, res, res_mode)
+    assert y.shape == ref.shape
+    err = (y - ref).abs()
+    tol = (1e-3 if out_f32 else 2e-3) * torch.clamp(ref.abs(), min=1.0)
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{name}: {bad} / {err.numel()} elements out of tolerance, max err {err.max().item():.4g}"
+    assert torch.isfinite(y).all()

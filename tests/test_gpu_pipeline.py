@@ -1,0 +1,98 @@
+"""End-to-end: the fused per-frame pipeline (detector -> NMS -> crop -> ReID -> tracker) through the reference-facing
+Python surface against the oracle on config 1 (yolov3-tiny 416 + DeepSort), plus the drop-in VideoDetector on a clip."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from util import DEV
+
+pytestmark = pytest.mark.gpu
+
+
+def build(frames):
+    from oracle.synth import reid_state_dict
+    from test_gpu_detector import make_model
+    from yolo_deepsort_b200 import DeepSort, FramePipeline
+    model, blocks, ws = make_model("yolov3-tiny", (416, 416), frames)
+    sd = reid_state_dict(seed=0)
+    ds = DeepSort(sd, max_dist=0.3, min_confidence=1, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30, use_cuda=True, device=DEV)
+    return model, blocks, ws, sd, ds, FramePipeline(model, ds, thres=0.5, nms_thres=0.4, class_mask=[0, 2, 4])
+
+
+def oracle_run(blocks, ws, sd, clip):
+    from oracle import darknet_ref as D, reid_ref as R, sort_ref as S
+    orc = S.DeepSortRef(lambda fr, tl: R.extract(sd, fr, tl), max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
+    outs, dets_all = [], []
+    for f in clip:
+        det = D.detect(blocks, ws, f, (416, 416), 0.5, 0.4)
+        dets_all.append(det)
+        if det is None:
+            outs.append(None)
+            continue
+        tlwh, conf, cls = D.to_tracker_inputs(det, [0, 2, 4])
+        outs.append(orc.update(tlwh, conf, f, torch.from_numpy(cls)))
+    return outs, dets_all
+
+
+def test_pipeline_matches_oracle_on_clip():
+    """32-frame clip built from three distinct scenes (A x12, B x8, A x6, C x6): tracks confirm, go missing, are
+    re-identified, and new ones spawn.  Track ids / class ids exact, boxes within 1 px (int32 truncation of fp32 boxes that
+    differ by < 1e-3 relative), per-frame detection sets identical."""
+    from oracle.synth import make_frame
+    scenes = [make_frame(416, 416, seed=s) for s in (0, 1, 2)]
+    clip = [scenes[0]] * 12 + [scenes[1]] * 8 + [scenes[0]] * 6 + [scenes[2]] * 6
+    model, blocks, ws, sd, ds, pipe = build(scenes)
+    ref_out, ref_dets = oracle_run(blocks, ws, sd, clip)
+    n_rows = 0
+    for t, f in enumerate(clip):
+        tracks, dets = pipe.step(f)
+        rd = ref_dets[t]
+        assert (rd is None and len(dets) == 0) or dets.shape == rd.shape, f"frame {t}: {len(dets)} detections vs {0 if rd is None else len(rd)}"
+        if rd is not None:
+            np.testing.assert_array_equal(dets[:, 5], rd[:, 5], err_msg=f"frame {t}: classes")
+            np.testing.assert_allclose(dets[:, :4], rd[:, :4], rtol=5e-3, atol=0.5, err_msg=f"frame {t}: boxes")
+        ro = ref_out[t]
+        if ro is None:
+            assert tracks is None
+            continue
+        ro = np.asarray(ro, np.int32).reshape(-1, 6)
+        got = np.asarray(tracks, np.int32).reshape(-1, 6)
+        assert got.shape == ro.shape, f"frame {t}: {got.shape[0]} track rows vs {ro.shape[0]}"
+        np.testing.assert_array_equal(got[:, 4:], ro[:, 4:], err_msg=f"frame {t}: track ids / class ids")
+        assert np.abs(got[:, :4] - ro[:, :4]).max() <= 1, f"frame {t}: boxes differ by more than 1 px"
+        n_rows += len(ro)
+    assert n_rows > 200, "the clip should produce confirmed tracks"
+
+
+def test_drop_in_video_detector(tmp_path):
+    """The reference-shaped driver: VideoDetector(model, names, tracker=DeepSort(...)).detect(path) on a lossless clip."""
+    import cv2
+    from oracle.synth import make_frame
+    from yolo_deepsort_b200 import VideoDetector
+    scenes = [make_frame(416, 416, seed=s) for s in (0, 1)]
+    clip = [scenes[0]] * 5 + [scenes[1]] * 3
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 25, (416, 416))
+    assert wr.isOpened()
+    for f in clip:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    wr.release()
+    model, blocks, ws, sd, ds, _ = build(scenes)
+    names = str(tmp_path / "coco.names")
+    with open(names, "w") as fh:
+        fh.write("\n".join(f"c{i}" for i in range(80)) + "\n")
+    vd = VideoDetector(model, names, thres=0.5, nms_thres=0.4, skip_frames=-1, class_mask=[0, 2, 4], tracker=ds, half=True)
+    ref_out, _ = oracle_run(blocks, ws, sd, clip)
+    n = 0
+    for t, (img, hold, actions) in enumerate(vd.detect(path, show_fps=False)):
+        assert img.shape == (416, 416, 3) and actions == []
+        ro = np.asarray(ref_out[t], np.int32).reshape(-1, 6)
+        got = np.asarray(hold, np.int32).reshape(-1, 6)
+        np.testing.assert_array_equal(got[:, 4:], ro[:, 4:])
+        n += 1
+    assert n == len(clip)
+    with pytest.raises(IOError):
+        next(vd.detect(str(tmp_path / "missing.avi")))

@@ -1,0 +1,94 @@
+"""ReID parity: crop + cv2-exact resize + normalisation bit-exact against the oracle (and therefore cv2), features of the
+20-conv net within tolerance of the fp32 oracle and of the golden written by the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from util import DEV
+from yolo_deepsort_b200 import Extractor
+from yolo_deepsort_b200._lib import YdstError, check, lib, ptr, stream_ptr
+
+pytestmark = pytest.mark.gpu
+
+
+def crop_resize_abi(frame, tlwh):
+    m = len(tlwh)
+    out = torch.empty((m, 128, 64, 3), dtype=torch.float32, device=DEV)
+    f = torch.from_numpy(frame).to(DEV)
+    t = torch.from_numpy(np.asarray(tlwh, np.float32)).to(DEV)
+    check(lib().ydst_crop_resize(ptr(f), frame.shape[0], frame.shape[1], ptr(t), m, ptr(out), stream_ptr()))
+    return out
+
+
+def test_crop_resize_bit_exact():
+    from oracle.cv_resize_ref import crops_to_batch
+    from oracle.synth import make_frame
+    frame = make_frame(608, 608, seed=5)
+    rng = np.random.default_rng(0)
+    m = 200
+    tlwh = np.stack([rng.uniform(-20, 580, m), rng.uniform(-20, 560, m), rng.uniform(3, 200, m), rng.uniform(3, 300, m)], 1).astype(np.float32)
+    # special cases: exact network size (copy path), 2x downscale, box hanging over every border, 1-pixel-wide crop
+    tlwh[0] = [10, 20, 64, 128]; tlwh[1] = [100, 100, 128, 256]; tlwh[2] = [-30, -30, 100, 100]; tlwh[3] = [560, 500, 200, 300]
+    tlwh[4] = [50.9, 60.2, 1.3, 90.0]; tlwh[5] = [300, 300, 2, 2]
+    keep = []
+    for i, b in enumerate(tlwh):      # drop boxes whose crop is empty (the reference raises there)
+        x1, x2 = max(int(b[0]), 0), min(int(np.float32(b[0] + b[2])), 607)
+        y1, y2 = max(int(b[1]), 0), min(int(np.float32(b[1] + b[3])), 607)
+        if x2 > x1 and y2 > y1:
+            keep.append(i)
+    tlwh = tlwh[keep]
+    ref = crops_to_batch(frame, tlwh).transpose(0, 2, 3, 1)
+    got = crop_resize_abi(frame, tlwh).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_empty_crop_is_an_error():
+    from oracle.synth import make_frame
+    frame = make_frame(64, 64, seed=1)
+    with pytest.raises(YdstError):
+        crop_resize_abi(frame, np.array([[70, 70, 10, 10]], np.float32))
+
+
+@pytest.fixture(scope="module")
+def extractor():
+    from oracle.synth import reid_state_dict
+    sd = reid_state_dict(seed=0)
+    return Extractor(sd, use_cuda=True, max_batch=256, device=DEV), sd
+
+
+def test_features_match_golden(extractor):
+    """tests/golden/reid.npz was written by the unmodified reference Extractor (cv2 + torch CPU fp32)."""
+    from oracle.synth import make_frame
+    ex, sd = extractor
+    g = np.load(os.path.join(GOLDEN, "reid.npz"))
+    frame = make_frame(608, 608, seed=int(g["frame_seed"]))
+    feats = ex.extract(torch.from_numpy(frame).to(DEV), torch.from_numpy(g["tlwh"]).to(DEV)).cpu().numpy()
+    ref = g["feats"]
+    np.testing.assert_allclose(np.linalg.norm(feats, axis=1), 1.0, atol=1e-5)
+    rel = np.linalg.norm(feats - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    cos = (feats * ref).sum(1)
+    print("ReID features: max relative L2 error %.3g, min cosine %.6f" % (rel.max(), cos.min()))
+    assert rel.max() < 5e-3 and cos.min() > 0.9999
+
+
+@pytest.mark.parametrize("m", [1, 7, 50, 256])
+def test_features_vs_oracle_batches(extractor, m):
+    from oracle import reid_ref as R
+    from oracle.synth import make_frame
+    ex, sd = extractor
+    frame = make_frame(608, 608, seed=8)
+    rng = np.random.default_rng(m)
+    tlwh = np.stack([rng.uniform(0, 500, m), rng.uniform(0, 440, m), rng.uniform(25, 90, m), rng.uniform(50, 160, m)], 1).astype(np.float32)
+    ref = R.extract(sd, frame, tlwh).numpy()
+    got = ex.extract(torch.from_numpy(frame).to(DEV), torch.from_numpy(tlwh).to(DEV)).cpu().numpy()
+    rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 5e-3, rel.max()
+    # reference-compatible list-of-crops entry gives the same features as the fused entry
+    if m <= 7:
+        from oracle.cv_resize_ref import crop_box
+        crops = [frame[y1:y2, x1:x2] for (x1, y1, x2, y2) in (crop_box(b, 608, 608) for b in tlwh)]
+        got2 = ex(crops).cpu().numpy()
+        np.testing.assert_array_equal(got2, got)

@@ -1,0 +1,412 @@
+// extern "C" surface of libydst (include/ydst.h): argument checking, handle ownership, error strings.
+#include <cstring>
+#include <mutex>
+
+#include "../../include/ydst.h"
+#include "assoc.cuh"
+#include "net.cuh"
+#include "tracker.cuh"
+
+namespace ydst {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace ydst
+
+using namespace ydst;
+
+struct ydst_detector { Detector* impl; };
+struct ydst_reid { Reid* impl; };
+struct ydst_tracker { Tracker* impl; };
+
+struct ydst_pipeline {
+    Detector* det; Reid* reid; Tracker* trk;
+    float conf, iou;
+    int* mask_dev = nullptr; int n_mask = 0;
+    uint8_t* frame_dev = nullptr;
+    float *tlwh = nullptr, *confd = nullptr, *cls = nullptr, *feat = nullptr;
+    int* h_counts = nullptr;      // pinned: [0] m, [1] n_dets, [2] overflow, [3] crop error flag
+    float* h_dets = nullptr;      // pinned 300 x 6
+};
+
+static cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+extern "C" {
+
+const char* ydst_last_error(void) { return g_err.c_str(); }
+int ydst_version(void) { return 100; }
+
+// ---------------- detector ----------------
+int ydst_detector_create(const ydst_layer_desc* layers, int n_layers, const float* weights_host, size_t n_weights, int height,
+                         int width, int batch, ydst_detector** out) {
+    YDST_API_BEGIN
+    YDST_CHECK(layers && n_layers > 0 && weights_host && out, "null argument");
+    auto* h = new ydst_detector{nullptr};
+    try { h->impl = new Detector(layers, n_layers, weights_host, n_weights, height, width, batch); }
+    catch (...) { delete h; throw; }
+    *out = h;
+    YDST_API_END
+}
+int ydst_detector_destroy(ydst_detector* d) {
+    YDST_API_BEGIN
+    if (d) { d->impl->nms_.destroy(); delete d->impl; delete d; }
+    YDST_API_END
+}
+int ydst_detector_shape(const ydst_detector* d, int* rows, int* fields) {
+    YDST_API_BEGIN
+    YDST_CHECK(d, "null handle");
+    if (rows) *rows = d->impl->rows;
+    if (fields) *fields = d->impl->fields;
+    YDST_API_END
+}
+int ydst_detector_forward_nchw(ydst_detector* d, const void* x_dev, int is_half, float* pred_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(d && x_dev, "null argument");
+    d->impl->forward_nchw(x_dev, is_half, pred_dev, S(stream));
+    YDST_API_END
+}
+int ydst_detector_forward_u8(ydst_detector* d, const uint8_t* frame_dev, float* pred_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(d && frame_dev, "null argument");
+    d->impl->forward_u8(frame_dev, pred_dev, S(stream));
+    YDST_API_END
+}
+int ydst_detector_nms(ydst_detector* d, float conf_thres, float iou_thres, float* dets_dev, int* n_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(d, "null handle");
+    d->impl->nms(conf_thres, iou_thres, dets_dev, n_dev, S(stream));
+    YDST_API_END
+}
+double ydst_detector_flops(const ydst_detector* d) { return d ? d->impl->plan.flops : 0.0; }
+int ydst_detector_launches(const ydst_detector* d) { return d ? d->impl->plan.launches + 1 : 0; }
+
+int ydst_nms(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, float* dets_dev, int* n_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(pred_dev && dets_dev && n_host && rows >= 0 && fields > 5, "bad argument");
+    Nms nms;
+    nms.init(4096, 300);
+    try {
+        nms.run(pred_dev, rows, fields, conf_thres, iou_thres, S(stream));
+        int h[4];
+        YDST_CUDA(cudaMemcpyAsync(dets_dev, nms.dets, sizeof(float) * 6 * 300, cudaMemcpyDeviceToDevice, S(stream)));
+        YDST_CUDA(cudaMemcpyAsync(h, nms.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, S(stream)));
+        YDST_CUDA(cudaStreamSynchronize(S(stream)));
+        YDST_CHECK(h[2] == 0, "NMS candidate capacity exceeded (%d candidates > %d)", h[0], nms.cap);
+        *n_host = h[1];
+    } catch (...) { nms.destroy(); throw; }
+    nms.destroy();
+    YDST_API_END
+}
+
+// Stand-alone convolution through the same kernels the networks use (conv_tc / conv_first), for parity tests.
+int ydst_conv2d(const void* x_dev, int N, int H, int W, int cin, const float* w_host, int cout, int k, int stride, const float* bn_host,
+                const float* bias_host, int act, const void* res_dev, int res_mode, void* y_dev, int y_is_f32, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(x_dev && w_host && y_dev && N > 0 && H > 0 && W > 0, "bad argument");
+    DeviceArena arena;
+    const int pad = (k - 1) / 2;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
+    if (bn_host) { g = bn_host; b = bn_host + cout; m = bn_host + 2 * cout; v = bn_host + 3 * cout; }
+    auto cw = pack_conv(arena, w_host, cout, cin, k, g, b, m, v, bias_host, cin == 3);
+    cudaStream_t st = S(stream);
+    if (cin == 3) {
+        YDST_CHECK(!y_is_f32 && !res_dev, "first-layer path: fp16 output, no residual");
+        Act out = make_act(arena, N, Ho, Wo, cout);
+        launch_conv_first((const float*)x_dev, N, H, W, cw->w32, cw->scale, cw->bias, cout, stride, act, out, st);
+        launch_unpack(out, (__half*)y_dev, st);
+    } else {
+        Act in = make_act(arena, N, H, W, cin);
+        launch_pack((const __half*)x_dev, in, st);
+        Act res;
+        if (res_dev) { res = make_act(arena, N, Ho, Wo, cout); launch_pack((const __half*)res_dev, res, st); }
+        ConvTcLaunch L;
+        if (y_is_f32) {
+            float* f32 = (float*)arena.alloc((size_t)N * (Ho + 2) * (Wo + 2) * cw->cout16 * sizeof(float));
+            Act geo; geo.N = N; geo.H = Ho; geo.W = Wo; geo.C = cout; geo.ctot = cw->cout16; geo.coff = 0;
+            conv_tc_plan(L, in, geo, cw->w16, k, k, stride, cw->scale, cw->bias, act, 0, nullptr, f32, cout);
+            conv_tc_run(L, st);
+            launch_unpack_f32(f32, cw->cout16, N, Ho, Wo, cout, (float*)y_dev, st);
+        } else {
+            Act out = make_act(arena, N, Ho, Wo, cout);
+            conv_tc_plan(L, in, out, cw->w16, k, k, stride, cw->scale, cw->bias, act, res_dev ? res_mode : 0, res_dev ? &res : nullptr, nullptr, cout);
+            conv_tc_run(L, st);
+            launch_unpack(out, (__half*)y_dev, st);
+        }
+    }
+    YDST_CUDA(cudaStreamSynchronize(st));
+    YDST_API_END
+}
+
+// ---------------- ReID ----------------
+int ydst_reid_create(const float* weights_host, size_t n_weights, int max_batch, ydst_reid** out) {
+    YDST_API_BEGIN
+    YDST_CHECK(weights_host && out, "null argument");
+    auto* h = new ydst_reid{nullptr};
+    try { h->impl = new Reid(weights_host, n_weights, max_batch); }
+    catch (...) { delete h; throw; }
+    *out = h;
+    YDST_API_END
+}
+int ydst_reid_destroy(ydst_reid* r) {
+    YDST_API_BEGIN
+    if (r) { delete r->impl; delete r; }
+    YDST_API_END
+}
+int ydst_reid_extract(ydst_reid* r, const uint8_t* frame_dev, int height, int width, const float* tlwh_dev, int m, float* feat_dev,
+                      void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(r && frame_dev && (m == 0 || (tlwh_dev && feat_dev)), "null argument");
+    YDST_CUDA(cudaMemsetAsync(r->impl->err_flag, 0, sizeof(int), S(stream)));
+    r->impl->extract(frame_dev, height, width, tlwh_dev, m, feat_dev, S(stream));
+    int flag = 0;
+    YDST_CUDA(cudaMemcpyAsync(&flag, r->impl->err_flag, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    YDST_CUDA(cudaStreamSynchronize(S(stream)));
+    if (flag) { set_error("empty crop: a box has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    YDST_API_END
+}
+int ydst_reid_forward(ydst_reid* r, const float* x_dev, int m, float* feat_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(r && (m == 0 || (x_dev && feat_dev)), "null argument");
+    r->impl->forward(x_dev, m, feat_dev, S(stream));
+    YDST_API_END
+}
+int ydst_crop_resize(const uint8_t* frame_dev, int height, int width, const float* tlwh_dev, int m, float* out_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(frame_dev && (m == 0 || (tlwh_dev && out_dev)), "null argument");
+    int* flag_dev = nullptr;
+    YDST_CUDA(cudaMalloc(&flag_dev, sizeof(int)));
+    int flag = 0;
+    cudaMemsetAsync(flag_dev, 0, sizeof(int), S(stream));
+    try {
+        launch_crop_resize(frame_dev, height, width, tlwh_dev, m, out_dev, flag_dev, S(stream));
+        YDST_CUDA(cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+        YDST_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) { cudaFree(flag_dev); throw; }
+    cudaFree(flag_dev);
+    if (flag) { set_error("empty crop: a box has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    YDST_API_END
+}
+double ydst_reid_flops_per_crop(void) {
+    double f = 2.0 * 128 * 64 * 64 * 27;
+    const int st[4][3] = {{64, 64, 0}, {64, 128, 1}, {128, 256, 1}, {256, 512, 1}};
+    int h = 64, w = 32;
+    for (int s = 0; s < 4; ++s) {
+        if (s > 0) { h /= 2; w /= 2; }
+        const double px = (double)h * w;
+        f += 2.0 * px * st[s][1] * 9 * st[s][0];                // block 0 conv1
+        f += 3 * 2.0 * px * st[s][1] * 9 * st[s][1];            // the other three 3x3 convs
+        if (st[s][2]) f += 2.0 * px * st[s][1] * st[s][0];      // 1x1 downsample
+    }
+    return f;
+}
+
+// ---------------- association stage kernels ----------------
+int ydst_kf_initiate(const float* det_tlwh_dev, int n, float* mean_dev, float* cov_dev, void* stream) {
+    YDST_API_BEGIN
+    launch_kf_initiate(det_tlwh_dev, nullptr, mean_dev, cov_dev, nullptr, n, S(stream));
+    YDST_API_END
+}
+int ydst_kf_predict(float* mean_dev, float* cov_dev, int n, void* stream) {
+    YDST_API_BEGIN
+    launch_kf_predict(mean_dev, cov_dev, nullptr, n, S(stream));
+    YDST_API_END
+}
+int ydst_kf_update(float* mean_dev, float* cov_dev, const float* det_tlwh_dev, int n, void* stream) {
+    YDST_API_BEGIN
+    launch_kf_update(mean_dev, cov_dev, nullptr, det_tlwh_dev, nullptr, n, S(stream));
+    YDST_API_END
+}
+int ydst_gate_position(const float* mean_dev, const float* cov_dev, int n, const float* det_tlwh_dev, int m, float* maha_dev, void* stream) {
+    YDST_API_BEGIN
+    launch_gate_position(mean_dev, cov_dev, nullptr, n, det_tlwh_dev, m, maha_dev, S(stream));
+    YDST_API_END
+}
+int ydst_appearance_cost(const float* gallery_dev, const int* seg_host, int n, const float* det_feat_dev, int m, const float* mean_dev,
+                         const float* cov_dev, const float* det_tlwh_dev, float max_dist, float* cost_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(seg_host && n >= 0 && m >= 0, "bad argument");
+    if (n == 0 || m == 0) return 0;
+    const int G = seg_host[n];
+    std::vector<int> row_ptr(G), row_track(G);
+    for (int t = 0; t < n; ++t)
+        for (int g = seg_host[t]; g < seg_host[t + 1]; ++g) { row_ptr[g] = g; row_track[g] = t; }
+    float *gal_n = nullptr, *det_n = nullptr;
+    int *d_rp = nullptr, *d_rt = nullptr, *enc = nullptr;
+    auto cleanup = [&]() { cudaFree(gal_n); cudaFree(det_n); cudaFree(d_rp); cudaFree(d_rt); cudaFree(enc); };
+    try {
+        YDST_CUDA(cudaMalloc(&gal_n, (size_t)std::max(G, 1) * kFeat * sizeof(float)));
+        YDST_CUDA(cudaMalloc(&det_n, (size_t)m * kFeat * sizeof(float)));
+        YDST_CUDA(cudaMalloc(&d_rp, (size_t)std::max(G, 1) * sizeof(int)));
+        YDST_CUDA(cudaMalloc(&d_rt, (size_t)std::max(G, 1) * sizeof(int)));
+        YDST_CUDA(cudaMalloc(&enc, (size_t)n * m * sizeof(int)));
+        YDST_CUDA(cudaMemcpyAsync(d_rp, row_ptr.data(), G * sizeof(int), cudaMemcpyHostToDevice, S(stream)));
+        YDST_CUDA(cudaMemcpyAsync(d_rt, row_track.data(), G * sizeof(int), cudaMemcpyHostToDevice, S(stream)));
+        launch_normalize_rows(gallery_dev, gal_n, G, S(stream));
+        launch_normalize_rows(det_feat_dev, det_n, m, S(stream));
+        launch_fill_i32(enc, 0x7f800000, (long long)n * m, S(stream));
+        launch_cosine_min(gal_n, d_rp, d_rt, G, det_n, m, enc, S(stream));
+        launch_cost_finalize(enc, mean_dev, cov_dev, nullptr, n, det_tlwh_dev, m, max_dist, cost_dev, S(stream));
+        YDST_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+    YDST_API_END
+}
+int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float* det_tlwh_dev, int m, float max_dist, float* cost_dev,
+                  void* stream) {
+    YDST_API_BEGIN
+    launch_iou_cost(mean_dev, nullptr, tsu_dev, n, det_tlwh_dev, nullptr, m, max_dist, cost_dev, S(stream));
+    YDST_API_END
+}
+int ydst_lsap(const float* cost_dev, int nr, int nc, float max_dist, int* rows_host, int* cols_host, int* over_max_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(nr >= 0 && nc >= 0, "bad shape");
+    if (nr == 0 || nc == 0) return 0;
+    const bool tr = nc < nr;
+    const int R = tr ? nc : nr, C = tr ? nr : nc;
+    float* ct = nullptr; int* res = nullptr; void* work = nullptr;
+    auto cleanup = [&]() { cudaFree(ct); cudaFree(res); cudaFree(work); };
+    try {
+        YDST_CUDA(cudaMalloc(&res, 2 * (size_t)R * sizeof(int)));
+        YDST_CUDA(cudaMalloc(&work, lsap_work_bytes(R, C)));
+        const float* c = cost_dev;
+        if (tr) {
+            YDST_CUDA(cudaMalloc(&ct, (size_t)nr * nc * sizeof(float)));
+            launch_transpose(cost_dev, ct, nr, nc, S(stream));
+            c = ct;
+        }
+        launch_lsap(c, R, C, max_dist, res, res + R, work, S(stream));
+        std::vector<int> h(2 * (size_t)R);
+        YDST_CUDA(cudaMemcpyAsync(h.data(), res, 2 * (size_t)R * sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+        YDST_CUDA(cudaStreamSynchronize(S(stream)));
+        if (!tr) {
+            for (int r = 0; r < R; ++r) { rows_host[r] = r; cols_host[r] = h[r]; if (over_max_host) over_max_host[r] = h[R + r]; }
+        } else {                                   // solver rows are original columns; emit sorted by original row
+            std::vector<int> col_of_row(nr, -1), over(nr, 0);
+            for (int r = 0; r < R; ++r) { col_of_row[h[r]] = r; over[h[r]] = h[R + r]; }
+            int k = 0;
+            for (int orow = 0; orow < nr; ++orow)
+                if (col_of_row[orow] >= 0) { rows_host[k] = orow; cols_host[k] = col_of_row[orow]; if (over_max_host) over_max_host[k] = over[orow]; ++k; }
+        }
+        for (int r = 0; r < R; ++r) YDST_CHECK(h[r] >= 0, "cost matrix is infeasible");
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+    YDST_API_END
+}
+
+// ---------------- tracker ----------------
+int ydst_tracker_create(float max_dist, float max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks, int cap_dets,
+                        ydst_tracker** out) {
+    YDST_API_BEGIN
+    YDST_CHECK(out, "null argument");
+    auto* h = new ydst_tracker{nullptr};
+    try { h->impl = new Tracker(max_dist, max_iou_distance, max_age, n_init, nn_budget, cap_tracks, cap_dets); }
+    catch (...) { delete h; throw; }
+    *out = h;
+    YDST_API_END
+}
+int ydst_tracker_destroy(ydst_tracker* t) {
+    YDST_API_BEGIN
+    if (t) { delete t->impl; delete t; }
+    YDST_API_END
+}
+int ydst_tracker_update(ydst_tracker* t, const float* tlwh_dev, const float* feat_dev, const int* payload_host, int m, int32_t* out_host,
+                        int* k_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(t && out_host && k_host && (m == 0 || (tlwh_dev && feat_dev && payload_host)), "null argument");
+    t->impl->update(tlwh_dev, feat_dev, payload_host, nullptr, m, out_host, k_host, S(stream));
+    YDST_API_END
+}
+int ydst_tracker_update_dev(ydst_tracker* t, const float* tlwh_dev, const float* feat_dev, const float* cls_dev, int m, int32_t* out_host,
+                            int* k_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(t && out_host && k_host && (m == 0 || (tlwh_dev && feat_dev && cls_dev)), "null argument");
+    t->impl->update(tlwh_dev, feat_dev, nullptr, cls_dev, m, out_host, k_host, S(stream));
+    YDST_API_END
+}
+int ydst_tracker_tracks(ydst_tracker* t, int32_t* table_host, float* mean_host, int cap, int* n_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(t && n_host, "null argument");
+    t->impl->snapshot(table_host, mean_host, cap, n_host, S(stream));
+    YDST_API_END
+}
+int ydst_tracker_last_matches(ydst_tracker* t, int32_t* pairs_host, int cap, int* n_host) {
+    YDST_API_BEGIN
+    YDST_CHECK(t && n_host, "null argument");
+    const auto& m = t->impl->last_matches;
+    *n_host = (int)m.size();
+    YDST_CHECK((int)m.size() <= cap, "buffer too small");
+    for (size_t i = 0; i < m.size(); ++i) { pairs_host[2 * i] = m[i].first; pairs_host[2 * i + 1] = m[i].second; }
+    YDST_API_END
+}
+
+// ---------------- fused per-frame pipeline ----------------
+int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk, float conf_thres, float iou_thres,
+                         const int* class_mask_host, int n_mask, ydst_pipeline** out) {
+    YDST_API_BEGIN
+    YDST_CHECK(det && reid && trk && out, "null argument");
+    YDST_CHECK(det->impl->batch == 1, "the per-frame pipeline needs a batch-1 detector");
+    auto* p = new ydst_pipeline();
+    p->det = det->impl; p->reid = reid->impl; p->trk = trk->impl; p->conf = conf_thres; p->iou = iou_thres; p->n_mask = n_mask;
+    const int md = p->det->nms_.max_det;
+    YDST_CUDA(cudaMalloc(&p->frame_dev, (size_t)p->det->H * p->det->W * 3));
+    YDST_CUDA(cudaMalloc(&p->tlwh, sizeof(float) * 4 * md));
+    YDST_CUDA(cudaMalloc(&p->confd, sizeof(float) * md));
+    YDST_CUDA(cudaMalloc(&p->cls, sizeof(float) * md));
+    YDST_CUDA(cudaMalloc(&p->feat, sizeof(float) * 512 * md));
+    YDST_CUDA(cudaMalloc(&p->mask_dev, sizeof(int) * (n_mask > 0 ? n_mask : 1)));
+    if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
+    YDST_CUDA(cudaMallocHost(&p->h_counts, sizeof(int) * 8));
+    YDST_CUDA(cudaMallocHost(&p->h_dets, sizeof(float) * 6 * md));
+    *out = p;
+    YDST_API_END
+}
+int ydst_pipeline_destroy(ydst_pipeline* p) {
+    YDST_API_BEGIN
+    if (p) {
+        cudaFree(p->frame_dev); cudaFree(p->tlwh); cudaFree(p->confd); cudaFree(p->cls); cudaFree(p->feat); cudaFree(p->mask_dev);
+        cudaFreeHost(p->h_counts); cudaFreeHost(p->h_dets);
+        delete p;
+    }
+    YDST_API_END
+}
+static int pipeline_run(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
+                        cudaStream_t st) {
+    Detector& det = *p->det;
+    det.forward_u8(frame_dev, nullptr, st);
+    det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, st);
+    // frame == network size, so resize_boxes' ratios are exactly 1 (yolo3/utils/model_build.py:12-19)
+    det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, p->tlwh, p->confd, p->cls, st);
+    YDST_CUDA(cudaMemcpyAsync(p->h_counts, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    if (dets_host) YDST_CUDA(cudaMemcpyAsync(p->h_dets, det.nms_.dets, sizeof(float) * 6 * det.nms_.max_det, cudaMemcpyDeviceToHost, st));
+    YDST_CUDA(cudaStreamSynchronize(st));
+    YDST_CHECK(p->h_counts[2] == 0, "NMS candidate capacity exceeded (%d candidates)", p->h_counts[0]);
+    const int n_dets = p->h_counts[1], m = p->h_counts[3];
+    if (n_dets_host) *n_dets_host = n_dets;
+    if (dets_host) memcpy(dets_host, p->h_dets, sizeof(float) * 6 * n_dets);
+    if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
+    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), st));
+    p->reid->extract(frame_dev, det.H, det.W, p->tlwh, m, p->feat, st);
+    YDST_CUDA(cudaMemcpyAsync(p->h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    p->trk->update(p->tlwh, p->feat, nullptr, p->cls, m, out_host, k_host, st);
+    if (p->h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    return 0;
+}
+int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
+                       void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && frame_host && out_host && k_host, "null argument");
+    YDST_CUDA(cudaMemcpyAsync(p->frame_dev, frame_host, (size_t)p->det->H * p->det->W * 3, cudaMemcpyHostToDevice, S(stream)));
+    const int rc = pipeline_run(p, p->frame_dev, out_host, k_host, dets_host, n_dets_host, S(stream));
+    if (rc) return rc;
+    YDST_API_END
+}
+int ydst_pipeline_step_dev(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
+                           void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && frame_dev && out_host && k_host, "null argument");
+    const int rc = pipeline_run(p, frame_dev, out_host, k_host, dets_host, n_dets_host, S(stream));
+    if (rc) return rc;
+    YDST_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+// DeepSORT association kernels for sm_100a: batched Kalman filter on struct-of-arrays track state,
+// appearance / IoU cost matrices with fused gating, and an exact on-device linear assignment.
+//
+// Reference stages replaced (deep_sort/sort/): kalman_filter.py:54-256, nn_matching.py:30-100,158-187,
+// linear_assignment.py:51-56,147-203, iou_matching.py:5-91, plus scipy.optimize.linear_sum_assignment.
+// These are HBM/latency-bound fp32 kernels: coalesced 16/32-byte accesses, warp-shuffle data exchange
+// (8 lanes own the 8 rows of one covariance), no tensor cores (costs are compared against 0.3 / 5.9915,
+// so they are kept in full fp32; the LSAP duals are fp64 exactly like scipy's).
+#include "assoc.cuh"
+
+#include <math_constants.h>
+
+namespace ydst {
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ================================================================================================
+// Kalman filter.  Thread layout for predict/update: 8 consecutive lanes per track, lane r owns row r
+// of the 8x8 covariance (two float4) and mean[r]; 4 tracks per warp => 1 KB contiguous per warp access.
+// ================================================================================================
+__device__ __forceinline__ void tlwh_to_xyah(const float* t, float& x, float& y, float& a, float& h) {
+    // Detection.to_xyah / tracker.py:145-146: xy += wh/2 ; a = w/h
+    x = t[0] + t[2] / 2.f;
+    y = t[1] + t[3] / 2.f;
+    a = t[2] / t[3];
+    h = t[3];
+}
+
+__global__ void kf_initiate_kernel(const float* __restrict__ det_tlwh, const int* __restrict__ det_idx, float* __restrict__ mean,
+                                   float* __restrict__ cov, const int* __restrict__ slot_idx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = det_idx ? det_idx[i] : i;
+    const int slot = slot_idx ? slot_idx[i] : i;
+    float x, y, a, h;
+    tlwh_to_xyah(det_tlwh + d * 4, x, y, a, h);
+    float* m = mean + (long long)slot * 8;
+    m[0] = x; m[1] = y; m[2] = a; m[3] = h; m[4] = 0.f; m[5] = 0.f; m[6] = 0.f; m[7] = 0.f;
+    // std = [2*(1/20)*h, .., 1e-2, .., 10*(1/160)*h, .., 1e-5, ..]  (kalman_filter.py:75-84), squared
+    const float sp = 0.1f * h, sv = 0.0625f * h;
+    const float dg[8] = {sp * sp, sp * sp, 1e-2f * 1e-2f, sp * sp, sv * sv, sv * sv, 1e-5f * 1e-5f, sv * sv};
+    float* c = cov + (long long)slot * 64;
+    for (int r = 0; r < 8; ++r)
+        for (int q = 0; q < 8; ++q) c[r * 8 + q] = r == q ? dg[r] : 0.f;
+}
+void launch_kf_initiate(const float* det_tlwh, const int* det_idx, float* mean, float* cov, const int* slot_idx, int n, cudaStream_t st) {
+    if (n == 0) return;
+    kf_initiate_kernel<<<cdiv(n, 128), 128, 0, st>>>(det_tlwh, det_idx, mean, cov, slot_idx, n);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) kf_predict_kernel(float* __restrict__ mean, float* __restrict__ cov, const int* __restrict__ idx, int n) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;     // track
+    const int r = threadIdx.x & 7;
+    const int lane = threadIdx.x & 31, gl = lane & ~7;
+    const bool on = g < n;
+    const int slot = on ? (idx ? idx[g] : g) : 0;
+    float4* crow = reinterpret_cast<float4*>(cov + (long long)slot * 64 + r * 8);
+    float p[8];
+    float m = 0.f;
+    if (on) {
+        const float4 a = crow[0], b = crow[1];
+        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+        m = mean[(long long)slot * 8 + r];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = 0.f;
+    }
+    const float h = __shfl_sync(0xffffffffu, m, gl + 3);            // height BEFORE the motion step (kalman_filter.py:109)
+    // F P : rows 0..3 += rows 4..7
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float o = __shfl_sync(0xffffffffu, p[j], gl + ((r + 4) & 7));
+        if (r < 4) p[j] = p[j] + o;
+    }
+    // (F P) F^T : cols 0..3 += cols 4..7
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = p[j] + p[j + 4];
+    // + Q = diag([.05h,.05h,1e-2,.05h, h/160,h/160,1e-5,h/160]^2)
+    const float sp = h * 0.05f, sv = h * 0.00625f;
+    const float q = r < 4 ? (r == 2 ? 1e-2f * 1e-2f : sp * sp) : (r == 6 ? 1e-5f * 1e-5f : sv * sv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j == r) p[j] = p[j] + q;
+    const float mo = __shfl_sync(0xffffffffu, m, gl + ((r + 4) & 7));
+    if (r < 4) m = m + mo;
+    if (on) {
+        crow[0] = make_float4(p[0], p[1], p[2], p[3]);
+        crow[1] = make_float4(p[4], p[5], p[6], p[7]);
+        mean[(long long)slot * 8 + r] = m;
+    }
+}
+void launch_kf_predict(float* mean, float* cov, const int* idx, int n, cudaStream_t st) {
+    if (n == 0) return;
+    kf_predict_kernel<<<cdiv((long long)n * 8, 256), 256, 0, st>>>(mean, cov, idx, n);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// 4x4 LU with partial pivoting + solve for one right-hand side (LAPACK sgetf2/sgetrs operation order:
+// first-max pivot, multiply the sub-column by the reciprocal pivot, right-looking rank-1 updates).
+__device__ __forceinline__ void lu4_solve(float (&A)[4][4], float (&b)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int pv = j;
+        float mx = fabsf(A[j][j]);
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+            const float v = fabsf(A[i][j]);
+            if (v > mx) { mx = v; pv = i; }
+        }
+        if (pv != j) {
+#pragma unroll
+            for (int i = j + 1; i < 4; ++i)
+                if (i == pv) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float t = A[j][q]; A[j][q] = A[i][q]; A[i][q] = t; }
+                    const float t = b[j]; b[j] = b[i]; b[i] = t;
+                }
+        }
+        const float rcp = 1.f / A[j][j];
+#pragma unroll
+        for (int i = j + 1; i < 4; ++i) {
+            A[i][j] = A[i][j] * rcp;
+#pragma unroll
+            for (int q = j + 1; q < 4; ++q) A[i][q] = A[i][q] - A[i][j] * A[j][q];
+        }
+    }
+    // L y = Pb (unit lower), U x = y
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < i; ++q) b[i] = b[i] - A[i][q] * b[q];
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+#pragma unroll
+        for (int q = i + 1; q < 4; ++q) b[i] = b[i] - A[i][q] * b[q];
+        b[i] = b[i] / A[i][i];
+    }
+}
+
+__global__ void __launch_bounds__(256) kf_update_kernel(float* __restrict__ mean, float* __restrict__ cov, const int* __restrict__ idx,
+                                                        const float* __restrict__ det_tlwh, const int* __restrict__ det_idx, int n) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int r = threadIdx.x & 7;
+    const int lane = threadIdx.x & 31, gl = lane & ~7;
+    const bool on = g < n;
+    const int slot = on ? (idx ? idx[g] : g) : 0;
+    float4* crow = reinterpret_cast<float4*>(cov + (long long)slot * 64 + r * 8);
+    float p[8], m = 0.f, z[4] = {0.f, 0.f, 0.f, 1.f};
+    if (on) {
+        const float4 a = crow[0], b = crow[1];
+        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+        m = mean[(long long)slot * 8 + r];
+        const int d = det_idx ? det_idx[g] : g;
+        tlwh_to_xyah(det_tlwh + d * 4, z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = (j == r) ? 1.f : 0.f;
+    }
+    const float h = __shfl_sync(0xffffffffu, m, gl + 3);
+    // projected covariance S = P[:4,:4] + diag([.05h,.05h,1e-1,.05h]^2)   (kalman_filter.py:143-159)
+    float S[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) S[a][b] = __shfl_sync(0xffffffffu, p[b], gl + a);
+    const float sp = h * 0.05f;
+    S[0][0] = S[0][0] + sp * sp; S[1][1] = S[1][1] + sp * sp; S[2][2] = S[2][2] + 1e-1f * 1e-1f; S[3][3] = S[3][3] + sp * sp;
+    if (!on) { S[0][0] = S[1][1] = S[2][2] = S[3][3] = 1.f; }
+    // Kalman gain row r:  S x = (P H)^T[:, r] = P[r][:4]
+    float LU[4][4], k[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        k[a] = p[a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) LU[a][b] = S[a][b];
+    }
+    lu4_solve(LU, k);
+    // mean += innovation . K^T
+    float innov[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) innov[a] = z[a] - __shfl_sync(0xffffffffu, m, gl + a);
+    float dm = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dm = fmaf(innov[a], k[a], dm);
+    m = m + dm;
+    // cov -= (K S) K^T
+    float ks[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s = fmaf(k[b], S[b][a], s);
+        ks[a] = s;
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        float s = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s = fmaf(ks[a], __shfl_sync(0xffffffffu, k[a], gl + d), s);
+        p[d] = p[d] - s;
+    }
+    if (on) {
+        crow[0] = make_float4(p[0], p[1], p[2], p[3]);
+        crow[1] = make_float4(p[4], p[5], p[6], p[7]);
+        mean[(long long)slot * 8 + r] = m;
+    }
+}
+void launch_kf_update(float* mean, float* cov, const int* idx, const float* det_tlwh, const int* det_idx, int n, cudaStream_t st) {
+    if (n == 0) return;
+    kf_update_kernel<<<cdiv((long long)n * 8, 256), 256, 0, st>>>(mean, cov, idx, det_tlwh, det_idx, n);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// squared Mahalanobis distance in (x, y) only: project, 2x2 LU inverse (getrf + getri order), d S^-1 d^T
+__device__ __forceinline__ float maha_position(const float* __restrict__ mean, const float* __restrict__ cov, float zx, float zy) {
+    const float h = mean[3];
+    const float sp = h * 0.05f;
+    float a = cov[0] + sp * sp, b = cov[1], c = cov[8], d = cov[9] + sp * sp;
+    const bool swap = fabsf(c) > fabsf(a);
+    if (swap) { float t = a; a = c; c = t; t = b; b = d; d = t; }
+    const float l = c * (1.f / a);
+    const float u22 = d - l * b;
+    const float iu00 = 1.f / a, iu11 = 1.f / u22;
+    const float iu01 = (iu00 * b) * (-iu11);
+    float i00 = iu00 - iu01 * l, i10 = 0.f - iu11 * l, i01 = iu01, i11 = iu11;
+    if (swap) { float t = i00; i00 = i01; i01 = t; t = i10; i10 = i11; i11 = t; }
+    const float d0 = -mean[0] + zx, d1 = -mean[1] + zy;
+    const float t0 = fmaf(d1, i10, d0 * i00), t1 = fmaf(d1, i11, d0 * i01);
+    return fmaf(t1, d1, t0 * d0);
+}
+
+__global__ void gate_position_kernel(const float* __restrict__ mean, const float* __restrict__ cov, const int* __restrict__ idx, int n,
+                                     const float* __restrict__ det_tlwh, int m, float* __restrict__ maha) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * m) return;
+    const int i = (int)(e / m), j = (int)(e % m);
+    const int slot = idx ? idx[i] : i;
+    float zx, zy, za, zh;
+    tlwh_to_xyah(det_tlwh + j * 4, zx, zy, za, zh);
+    maha[e] = maha_position(mean + (long long)slot * 8, cov + (long long)slot * 64, zx, zy);
+}
+void launch_gate_position(const float* mean, const float* cov, const int* idx, int n, const float* det_tlwh, int m, float* maha,
+                          cudaStream_t st) {
+    if ((long long)n * m == 0) return;
+    gate_position_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(mean, cov, idx, n, det_tlwh, m, maha);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ================================================================================================
+// Appearance cost
+// ================================================================================================
+__global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int row = blockIdx.x;
+    const float4 v = reinterpret_cast<const float4*>(src + (long long)row * kFeat)[threadIdx.x];
+    float q = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    __shared__ float red[4];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]);
+    reinterpret_cast<float4*>(dst + (long long)row * kFeat)[threadIdx.x] = make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
+}
+void launch_normalize_rows(const float* src, float* dst, int n, cudaStream_t st) {
+    if (n == 0) return;
+    normalize_rows_kernel<<<n, 128, 0, st>>>(src, dst, n);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void fill_i32_kernel(int* p, int v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill_i32(int* p, int v, long long n, cudaStream_t st) {
+    if (n == 0) return;
+    fill_i32_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// order-preserving float <-> int so that a signed atomicMin implements a float min
+__device__ __forceinline__ int f2ord(float f) {
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+static constexpr int kOrdInf = 0x7f800000;
+
+// 64 gallery rows x 64 detections per CTA, K = 512 in steps of 16; each thread owns a 4x4 micro-tile.
+// Epilogue: d = 1 - dot, segmented min over each track's gallery rows through atomicMin (order independent).
+__global__ void __launch_bounds__(256) cosine_min_kernel(const float* __restrict__ gallery, const int* __restrict__ row_ptr,
+                                                         const int* __restrict__ row_track, int G, const float* __restrict__ det, int m,
+                                                         int* __restrict__ cost_enc) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    const int g0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int t = threadIdx.x;
+    const int lr = t >> 2, lk = (t & 3) * 4;
+    const int ga = g0 + lr, jb = j0 + lr;
+    const float* arow = ga < G ? gallery + (long long)row_ptr[ga] * kFeat : nullptr;
+    const float* brow = jb < m ? det + (long long)jb * kFeat : nullptr;
+    const int ty = t >> 4, tx = t & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int k0 = 0; k0 < kFeat; k0 += 16) {
+        const float4 va = arow ? __ldg(reinterpret_cast<const float4*>(arow + k0 + lk)) : make_float4(0, 0, 0, 0);
+        const float4 vb = brow ? __ldg(reinterpret_cast<const float4*>(brow + k0 + lk)) : make_float4(0, 0, 0, 0);
+        As[lk + 0][lr] = va.x; As[lk + 1][lr] = va.y; As[lk + 2][lr] = va.z; As[lk + 3][lr] = va.w;
+        Bs[lk + 0][lr] = vb.x; Bs[lk + 1][lr] = vb.y; Bs[lk + 2][lr] = vb.z; Bs[lk + 3][lr] = vb.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int g = g0 + ty * 4 + a;
+        if (g >= G) continue;
+        const int trk = row_track[g];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + tx * 4 + b;
+            if (j < m) atomicMin(cost_enc + (long long)trk * m + j, f2ord(1.f - acc[a][b]));
+        }
+    }
+}
+void launch_cosine_min(const float* gallery, const int* row_ptr, const int* row_track, int G, const float* det_feat_n, int m,
+                       int* cost_enc, cudaStream_t st) {
+    if (G == 0 || m == 0) return;
+    dim3 grid(cdiv(G, 64), cdiv(m, 64));
+    cosine_min_kernel<<<grid, 256, 0, st>>>(gallery, row_ptr, row_track, G, det_feat_n, m, cost_enc);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// gate (position-only chi^2, strict >) then clamp (cost > max -> max + 1e-5): linear_assignment.py:201-202, :52
+__global__ void cost_finalize_kernel(const int* __restrict__ cost_enc, const float* __restrict__ mean, const float* __restrict__ cov,
+                                     const int* __restrict__ idx, int n, const float* __restrict__ det_tlwh, int m, float max_dist,
+                                     float clamp_val, float* __restrict__ cost) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * m) return;
+    const int i = (int)(e / m), j = (int)(e % m);
+    const int slot = idx ? idx[i] : i;
+    float c = ord2f(cost_enc[e]);
+    float zx, zy, za, zh;
+    tlwh_to_xyah(det_tlwh + j * 4, zx, zy, za, zh);
+    const float g = maha_position(mean + (long long)slot * 8, cov + (long long)slot * 64, zx, zy);
+    if (g > kChi2inv95_2) c = kInftyCost;
+    if (c > max_dist) c = clamp_val;
+    cost[e] = c;
+}
+void launch_cost_finalize(const int* cost_enc, const float* mean, const float* cov, const int* idx, int n, const float* det_tlwh, int m,
+                          float max_dist, float* cost, cudaStream_t st) {
+    if ((long long)n * m == 0) return;
+    const float clamp_val = (float)((double)max_dist + 1e-5);
+    cost_finalize_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(cost_enc, mean, cov, idx, n, det_tlwh, m, max_dist, clamp_val, cost);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void iou_cost_kernel(const float* __restrict__ mean, const int* __restrict__ idx, const int* __restrict__ tsu, int n,
+                                const float* __restrict__ det_tlwh, const int* __restrict__ det_idx, int m, float max_dist,
+                                float clamp_val, float* __restrict__ cost) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * m) return;
+    const int i = (int)(e / m), j = (int)(e % m);
+    const int slot = idx ? idx[i] : i;
+    const float* mu = mean + (long long)slot * 8;
+    // Track.to_tlwh (track.py:81-94): w = a*h ; tl = centre - wh/2
+    const float th = mu[3], tw = mu[2] * th;
+    const float tx = mu[0] - tw / 2.f, ty = mu[1] - th / 2.f;
+    const float* d = det_tlwh + (det_idx ? det_idx[j] : j) * 4;
+    const float dx = d[0], dy = d[1], dw = d[2], dh = d[3];
+    // iou (iou_matching.py:25-41): +1 on the intersection extent only
+    const float iw = fmaxf(fminf(tx + tw, dw + dx) - fmaxf(tx, dx) + 1.f, 0.f);
+    const float ih = fmaxf(fminf(ty + th, dh + dy) - fmaxf(ty, dy) + 1.f, 0.f);
+    const float inter = iw * ih;
+    float c = 1.f - inter / (tw * th + dw * dh - inter);
+    if (tsu && tsu[i] > 1) c = kInftyCost;      // tsu is indexed by cost-matrix row
+    if (c > max_dist) c = clamp_val;
+    cost[e] = c;
+}
+void launch_iou_cost(const float* mean, const int* idx, const int* tsu, int n, const float* det_tlwh, const int* det_idx, int m,
+                     float max_dist, float* cost, cudaStream_t st) {
+    if ((long long)n * m == 0) return;
+    const float clamp_val = (float)((double)max_dist + 1e-5);
+    iou_cost_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(mean, idx, tsu, n, det_tlwh, det_idx, m, max_dist, clamp_val, cost);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += 8)
+        if (x < cols && y0 + k < rows) tile[k][threadIdx.x] = src[(long long)(y0 + k) * cols + x];
+    __syncthreads();
+    const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int k = threadIdx.y; k < 32; k += 8)
+        if (ox < rows && oy0 + k < cols) dst[(long long)(oy0 + k) * rows + ox] = tile[threadIdx.x][k];
+}
+void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
+    if ((long long)rows * cols == 0) return;
+    transpose_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), dim3(32, 8), 0, st>>>(src, dst, rows, cols);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ================================================================================================
+// Linear assignment: Crouse's shortest augmenting path, one CTA, columns scanned in parallel.
+// Same `remaining` permutation, fp64 duals and selection rule as scipy, so ties resolve identically:
+//   among the scanned columns with the lowest path cost pick the LAST unassigned one in array order,
+//   or, if none is unassigned, the FIRST one.
+// ================================================================================================
+struct LsapBest {
+    double val;
+    int it;
+    int una;
+};
+__device__ __forceinline__ bool lsap_better(const LsapBest& a, const LsapBest& b) {
+    if (a.val != b.val) return a.val < b.val;
+    if (a.una != b.una) return a.una != 0;
+    return a.una ? a.it > b.it : a.it < b.it;
+}
+__device__ __forceinline__ LsapBest lsap_shfl(const LsapBest& v, int o) {
+    LsapBest r;
+    r.val = __shfl_xor_sync(0xffffffffu, v.val, o);
+    r.it = __shfl_xor_sync(0xffffffffu, v.it, o);
+    r.una = __shfl_xor_sync(0xffffffffu, v.una, o);
+    return r;
+}
+
+struct LsapWork {
+    double *u, *v, *spc;
+    int *path, *col4row, *row4col, *remaining;
+    unsigned char *SR, *SC;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost, int R, int C, float max_dist, int* __restrict__ col4row_out,
+                                                 int* __restrict__ over_max, LsapWork w) {
+    __shared__ LsapBest s_part[32];
+    __shared__ double s_min;
+    __shared__ int s_i, s_nrem, s_sink;
+    const int tid = threadIdx.x;
+    auto bar = [&]() { if (T == 32) __syncwarp(); else __syncthreads(); };
+
+    for (int i = tid; i < R; i += T) { w.u[i] = 0.0; w.col4row[i] = -1; }
+    for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; w.path[j] = -1; }
+    bar();
+    for (int cur = 0; cur < R; ++cur) {
+        for (int j = tid; j < C; j += T) { w.remaining[j] = C - 1 - j; w.spc[j] = CUDART_INF; w.SC[j] = 0; }
+        for (int i = tid; i < R; i += T) w.SR[i] = 0;
+        if (tid == 0) { s_min = 0.0; s_i = cur; s_nrem = C; s_sink = -1; }
+        bar();
+        while (true) {
+            const int i = s_i, nrem = s_nrem;
+            const double mv = s_min, ui = w.u[i];
+            const float* crow = cost + (long long)i * C;
+            LsapBest best;
+            best.val = CUDART_INF; best.it = 0x7fffffff; best.una = 0;
+            for (int it = tid; it < nrem; it += T) {
+                const int j = w.remaining[it];
+                const double r = mv + (double)__ldg(crow + j) - ui - w.v[j];
+                double s = w.spc[j];
+                if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
+                LsapBest c;
+                c.val = s; c.it = it; c.una = w.row4col[j] == -1;
+                if (lsap_better(c, best)) best = c;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const LsapBest other = lsap_shfl(best, o);
+                if (lsap_better(other, best)) best = other;
+            }
+            if (T > 32) {
+                if ((tid & 31) == 0) s_part[tid >> 5] = best;
+                __syncthreads();
+                if (tid < 32) {
+                    LsapBest b2;
+                    if (tid < T / 32) b2 = s_part[tid];
+                    else { b2.val = CUDART_INF; b2.it = 0x7fffffff; b2.una = 0; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const LsapBest other = lsap_shfl(b2, o);
+                        if (lsap_better(other, b2)) b2 = other;
+                    }
+                    best = b2;
+                }
+            }
+            if (tid == 0) {
+                w.SR[i] = 1;
+                s_min = best.val;
+                if (!(best.val < CUDART_INF)) {
+                    s_sink = -2;                              // infeasible (cannot happen with finite costs)
+                } else {
+                    const int j = w.remaining[best.it];
+                    if (w.row4col[j] == -1) s_sink = j; else s_i = w.row4col[j];
+                    w.SC[j] = 1;
+                    w.remaining[best.it] = w.remaining[nrem - 1];
+                    s_nrem = nrem - 1;
+                }
+            }
+            bar();
+            if (s_sink != -1) break;
+        }
+        const int sink = s_sink;
+        if (sink < 0) {                                        // infeasible: report and stop
+            for (int i = tid; i < R; i += T) { col4row_out[i] = -1; over_max[i] = 1; }
+            return;
+        }
+        const double mv = s_min;
+        for (int i = tid; i < R; i += T)
+            if (w.SR[i] && i != cur) w.u[i] += mv - w.spc[w.col4row[i]];
+        for (int j = tid; j < C; j += T)
+            if (w.SC[j]) w.v[j] -= mv - w.spc[j];
+        bar();
+        if (tid == 0) {
+            w.u[cur] += mv;
+            int j = sink;
+            while (true) {
+                const int i = w.path[j];
+                w.row4col[j] = i;
+                const int t = w.col4row[i];
+                w.col4row[i] = j;
+                j = t;
+                if (i == cur) break;
+            }
+        }
+        bar();
+    }
+    for (int i = tid; i < R; i += T) {
+        const int j = w.col4row[i];
+        col4row_out[i] = j;
+        over_max[i] = cost[(long long)i * C + j] > max_dist ? 1 : 0;
+    }
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+size_t lsap_work_bytes(int R, int C) {
+    return align16(sizeof(double) * R) + 2 * align16(sizeof(double) * C) + 3 * align16(sizeof(int) * C) + align16(sizeof(int) * R) +
+           align16(R) + align16(C) + 64;
+}
+void launch_lsap(const float* cost, int R, int C, float max_dist, int* col4row, int* over_max, void* work, cudaStream_t st) {
+    if (R == 0 || C == 0) return;
+    YDST_CHECK(R <= C, "launch_lsap needs R <= C (transpose first)");
+    unsigned char* p = (unsigned char*)work;
+    LsapWork w;
+    w.u = (double*)p; p += align16(sizeof(double) * R);
+    w.v = (double*)p; p += align16(sizeof(double) * C);
+    w.spc = (double*)p; p += align16(sizeof(double) * C);
+    w.path = (int*)p; p += align16(sizeof(int) * C);
+    w.row4col = (int*)p; p += align16(sizeof(int) * C);
+    w.remaining = (int*)p; p += align16(sizeof(int) * C);
+    w.col4row = (int*)p; p += align16(sizeof(int) * R);
+    w.SR = p; p += align16(R);
+    w.SC = p;
+    if (C <= 96) lsap_kernel<32><<<1, 32, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
+    else if (C <= 1024) lsap_kernel<256><<<1, 256, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
+    else lsap_kernel<1024><<<1, 1024, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
+    YDST_CUDA(cudaGetLastError());
+}
+
+}  // namespace ydst

@@ -1,0 +1,49 @@
+// tcgen05 implicit-GEMM convolution (declarations).  See conv_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ydst {
+
+struct ConvTcParams {
+    // --- GEMM tiling ---
+    int mode;          // 0: flat (stride 1; M tile = 128 consecutive padded pixels)
+                       // 1: patch (stride 2; M tile = TH x TW output pixels of one image)
+    int R, S;          // filter size (1x1 or 3x3)
+    int block_k;       // 16 / 32 / 64 input channels per k-block (row bytes 32 / 64 / 128)
+    int block_n;       // output channels per tile (multiple of 16, <= 256)
+    int cin_blocks;    // Cin / block_k
+    int cin;           // Cin (K offset of a tap in the packed weights = tap * cin)
+    int cout;          // output channels rounded up to 16
+    // --- geometry ---
+    int N, Ho, Wo;     // logical output dims (padded dims are +2)
+    int in_Wp;         // padded input width  (flat mode: == Wo + 2)
+    int in_Hp_half;    // patch mode: padded input height / 2
+    long long P_total; // flat mode: N * (Ho+2) * (Wo+2)
+    int TW, TH, tiles_x, tiles_y;   // patch mode
+    int pad_shift;     // patch mode: 1 - pad  (3x3: 0, 1x1: 1)
+    // --- epilogue ---
+    const float* scale;   // [cout rounded up to block_n]  BN gamma/sqrt(var+eps)   (1 if no BN)
+    const float* bias;    // [..]                         BN beta - mean*scale     (conv bias if no BN)
+    int act;
+    int res_mode;         // 0 none, 1 add after activation (darknet shortcut), 2 add before activation (ReID block)
+    const __half* res; int res_ctot, res_coff;
+    __half* out; int out_ctot, out_coff;
+    float* out_f32;       // when non-null: write fp32 [pixels][cout] instead of fp16 (YOLO head convs)
+};
+
+struct ConvTcLaunch {
+    CUtensorMap tmA[4];   // flat: [0] only.  patch: one per input parity (py*2 + px)
+    CUtensorMap tmB;
+    ConvTcParams p;
+    dim3 grid;
+    int smem_bytes;
+    int stages;
+};
+
+// Host: encode tensor maps + pick tiling.  `w_packed` is fp16 [cout16][R*S*cin] (K-major).
+void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* w_packed, int R, int S, int stride,
+                  const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real);
+void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
+double conv_tc_flops(const ConvTcLaunch& L);   // useful 2*M*N*K (logical, unpadded)
+
+}  // namespace ydst

@@ -1,0 +1,361 @@
+// HBM-bound layer kernels for sm_100a: everything in the detector / ReID graphs that is not a dense
+// contraction.  All activations use the flat-padded NHWC fp16 layout (common.cuh: Act); every kernel
+// moves 16 bytes (8 channels) per thread per access and writes interior pixels only.
+#include "layers.cuh"
+
+namespace ydst {
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(src + i);
+        *reinterpret_cast<float4*>(dst + i) = make_float4(v.x / 255.f, v.y / 255.f, v.z / 255.f, v.w / 255.f);
+    } else {
+        for (long long j = i; j < n; ++j) dst[j] = src[j] / 255.f;
+    }
+}
+void launch_u8_to_f32(const uint8_t* src, float* dst, long long n, cudaStream_t st) {
+    u8_to_f32_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(src, dst, n);
+}
+
+__global__ void nchw_to_nhwc_kernel(const void* __restrict__ src, int is_half, float* __restrict__ dst, int N, int C, int H, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over N*H*W*C (NHWC order)
+    const long long total = (long long)N * C * H * W;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const long long s = (((long long)n * C + c) * H + y) * W + x;
+    dst[i] = is_half ? __half2float(reinterpret_cast<const __half*>(src)[s]) : reinterpret_cast<const float*>(src)[s];
+}
+void launch_nchw_to_nhwc(const void* src, int src_is_half, float* dst, int N, int C, int H, int W, cudaStream_t st) {
+    const long long total = (long long)N * C * H * W;
+    nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, src_is_half, dst, N, C, H, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// First layer: Cin = 3 makes K = 27, far too thin for a tensor-core tile; one thread per output pixel
+// keeps the 27 inputs in registers and streams the (broadcast) weights from shared memory.
+__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ w,
+                                                         const float* __restrict__ scale, const float* __restrict__ bias, int cout,
+                                                         int stride, int act, Act out) {
+    extern __shared__ float sw[];          // [27][cout] then scale[cout], bias[cout]
+    for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) sw[i] = w[i];
+    float* ssc = sw + 27 * cout;
+    float* sbi = ssc + cout;
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) { ssc[i] = scale[i]; sbi[i] = bias[i]; }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * out.H * out.W;
+    if (idx >= total) return;
+    const int xo = (int)(idx % out.W);
+    long long t = idx / out.W;
+    const int yo = (int)(t % out.H);
+    const int n = (int)(t / out.H);
+    float v[27];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int y = yo * stride - 1 + r, x = xo * stride - 1 + s;
+            const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+            const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+        }
+    const long long pix = ((long long)n * out.Hp() + yo + 1) * out.Wp() + xo + 1;
+    __half* op = out.base + pix * out.ctot + out.coff;
+    for (int co = 0; co < cout; co += 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + co);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * cout + co + 4);
+            acc[0] = fmaf(v[k], w0.x, acc[0]); acc[1] = fmaf(v[k], w0.y, acc[1]);
+            acc[2] = fmaf(v[k], w0.z, acc[2]); acc[3] = fmaf(v[k], w0.w, acc[3]);
+            acc[4] = fmaf(v[k], w1.x, acc[4]); acc[5] = fmaf(v[k], w1.y, acc[5]);
+            acc[6] = fmaf(v[k], w1.z, acc[6]); acc[7] = fmaf(v[k], w1.w, acc[7]);
+        }
+        uint4 pk;
+        __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = apply_act(fmaf(acc[2 * q], ssc[co + 2 * q], sbi[co + 2 * q]), act);
+            const float b = apply_act(fmaf(acc[2 * q + 1], ssc[co + 2 * q + 1], sbi[co + 2 * q + 1]), act);
+            h[q] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(op + co) = pk;
+    }
+}
+void launch_conv_first(const float* in, int N, int H, int W, const float* w, const float* scale, const float* bias, int cout,
+                       int stride, int act, const Act& out, cudaStream_t st) {
+    YDST_CHECK(cout % 8 == 0 && cout <= 64, "first-layer conv supports cout in {8..64}, multiple of 8 (got %d)", cout);
+    const long long total = (long long)N * out.H * out.W;
+    const int smem = (27 * cout + 2 * cout) * (int)sizeof(float);
+    conv_first_kernel<<<cdiv(total, 128), 128, smem, st>>>(in, N, H, W, w, scale, bias, cout, stride, act, out);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint4* act_ptr(const Act& a, int n, int y, int x, int c) {
+    return reinterpret_cast<const uint4*>(a.base + (((long long)n * a.Hp() + y + 1) * a.Wp() + x + 1) * a.ctot + a.coff + c);
+}
+__device__ __forceinline__ uint4* act_ptr_w(const Act& a, int n, int y, int x, int c) {
+    return reinterpret_cast<uint4*>(a.base + (((long long)n * a.Hp() + y + 1) * a.Wp() + x + 1) * a.ctot + a.coff + c);
+}
+// decode a linear index over (n, y, x, c8) of `a`
+__device__ __forceinline__ bool decode_idx(const Act& a, long long idx, int& n, int& y, int& x, int& c) {
+    const int cg = a.C >> 3;
+    const long long total = (long long)a.N * a.H * a.W * cg;
+    if (idx >= total) return false;
+    c = (int)(idx % cg) * 8;
+    long long t = idx / cg;
+    x = (int)(t % a.W); t /= a.W;
+    y = (int)(t % a.H);
+    n = (int)(t / a.H);
+    return true;
+}
+
+__global__ void maxpool_kernel(Act in, Act out, int k, int stride, int zero_pad_br) {
+    int n, yo, xo, c;
+    if (!decode_idx(out, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, yo, xo, c)) return;
+    const int pad = zero_pad_br ? 0 : (k - 1) / 2;
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m[4] = {ninf, ninf, ninf, ninf};
+    for (int dy = 0; dy < k; ++dy) {
+        const int y = yo * stride - pad + dy;
+        for (int dx = 0; dx < k; ++dx) {
+            const int x = xo * stride - pad + dx;
+            const bool inside = y >= 0 && y < in.H && x >= 0 && x < in.W;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (inside) v = __ldg(act_ptr(in, n, y, x, c));
+            else if (!zero_pad_br) continue;                 // -inf padding: ignore; zero padding: a real 0
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], h[q]);
+        }
+    }
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ho[q] = m[q];
+    *act_ptr_w(out, n, yo, xo, c) = o;
+}
+void launch_maxpool(const Act& in, const Act& out, int k, int stride, int zero_pad_br, cudaStream_t st) {
+    YDST_CHECK(in.C == out.C && in.C % 8 == 0, "maxpool channel mismatch");
+    const long long total = (long long)out.N * out.H * out.W * (out.C / 8);
+    maxpool_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out, k, stride, zero_pad_br);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void upsample_kernel(Act in, Act out, int s) {
+    int n, y, x, c;
+    if (!decode_idx(out, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, y, x, c)) return;
+    *act_ptr_w(out, n, y, x, c) = __ldg(act_ptr(in, n, y / s, x / s, c));
+}
+void launch_upsample(const Act& in, const Act& out, int s, cudaStream_t st) {
+    YDST_CHECK(in.C == out.C && out.H == in.H * s && out.W == in.W * s, "upsample shape mismatch");
+    const long long total = (long long)out.N * out.H * out.W * (out.C / 8);
+    upsample_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out, s);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void add_kernel(Act a, Act b, Act out) {
+    int n, y, x, c;
+    if (!decode_idx(out, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, y, x, c)) return;
+    const uint4 va = __ldg(act_ptr(a, n, y, x, c)), vb = __ldg(act_ptr(b, n, y, x, c));
+    const __half2* ha = reinterpret_cast<const __half2*>(&va);
+    const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
+        ho[q] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    }
+    *act_ptr_w(out, n, y, x, c) = o;
+}
+void launch_add(const Act& a, const Act& b, const Act& out, cudaStream_t st) {
+    YDST_CHECK(a.C == out.C && b.C == out.C && a.H == out.H && b.H == out.H && a.W == out.W && b.W == out.W, "shortcut shape mismatch");
+    const long long total = (long long)out.N * out.H * out.W * (out.C / 8);
+    add_kernel<<<cdiv(total, 256), 256, 0, st>>>(a, b, out);
+    YDST_CUDA(cudaGetLastError());
+}
+
+__global__ void copy_kernel(Act in, Act out) {
+    int n, y, x, c;
+    if (!decode_idx(out, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, y, x, c)) return;
+    *act_ptr_w(out, n, y, x, c) = __ldg(act_ptr(in, n, y, x, c));
+}
+void launch_copy(const Act& in, const Act& out, cudaStream_t st) {
+    YDST_CHECK(in.C == out.C && in.H == out.H && in.W == out.W && in.N == out.N, "copy shape mismatch");
+    const long long total = (long long)out.N * out.H * out.W * (out.C / 8);
+    copy_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// dense NHWC fp16 <-> flat-padded view (test / boundary helpers)
+__global__ void pack_kernel(const __half* __restrict__ src, Act dst, int to_padded) {
+    int n, y, x, c;
+    if (!decode_idx(dst, (long long)blockIdx.x * blockDim.x + threadIdx.x, n, y, x, c)) return;
+    uint4* dense = reinterpret_cast<uint4*>(const_cast<__half*>(src) + (((long long)n * dst.H + y) * dst.W + x) * dst.C + c);
+    if (to_padded) *act_ptr_w(dst, n, y, x, c) = *dense;
+    else *dense = *act_ptr(dst, n, y, x, c);
+}
+void launch_pack(const __half* dense, const Act& padded, cudaStream_t st) {
+    const long long total = (long long)padded.N * padded.H * padded.W * (padded.C / 8);
+    pack_kernel<<<cdiv(total, 256), 256, 0, st>>>(dense, padded, 1);
+    YDST_CUDA(cudaGetLastError());
+}
+void launch_unpack(const Act& padded, __half* dense, cudaStream_t st) {
+    const long long total = (long long)padded.N * padded.H * padded.W * (padded.C / 8);
+    pack_kernel<<<cdiv(total, 256), 256, 0, st>>>(dense, padded, 0);
+    YDST_CUDA(cudaGetLastError());
+}
+__global__ void unpack_f32_kernel(const float* __restrict__ src, int cstride, int N, int H, int W, int C, float* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * H * W * C) return;
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    dst[i] = src[(((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1) * cstride + c];
+}
+void launch_unpack_f32(const float* padded, int cstride, int N, int H, int W, int C, float* dense, cudaStream_t st) {
+    unpack_f32_kernel<<<cdiv((long long)N * H * W * C, 256), 256, 0, st>>>(padded, cstride, N, H, W, C, dense);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void yolo_decode_kernel(const float* __restrict__ head, int cstride, int N, int gy, int gx, int na, float aw0, float ah0,
+                                   float aw1, float ah1, float aw2, float ah2, int nc, float s0, float s1, float* __restrict__ pred,
+                                   int rows_total, int row0) {
+    const int nf = nc + 5;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * na * gy * gx * nf;
+    if (idx >= total) return;
+    const int k = (int)(idx % nf);
+    long long t = idx / nf;
+    const int x = (int)(t % gx); t /= gx;
+    const int y = (int)(t % gy); t /= gy;
+    const int a = (int)(t % na);
+    const int n = (int)(t / na);
+    const long long pix = ((long long)n * (gy + 2) + y + 1) * (gx + 2) + x + 1;
+    const float v = __ldg(head + pix * cstride + a * nf + k);
+    const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2), ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
+    float o;
+    // (sigmoid(t)+grid) * scale, exp(t) * (anchor/scale) * scale with scale = (H/gy, W/gx, H/gy, W/gx):
+    // x and w use the HEIGHT stride, y and h the WIDTH stride -- the reference's own quirk.
+    if (k == 0) o = (1.f / (1.f + expf(-v)) + (float)x) * s0;
+    else if (k == 1) o = (1.f / (1.f + expf(-v)) + (float)y) * s1;
+    else if (k == 2) o = (expf(v) * (aw / s0)) * s0;
+    else if (k == 3) o = (expf(v) * (ah / s1)) * s1;
+    else o = 1.f / (1.f + expf(-v));
+    const long long row = row0 + ((long long)a * gy + y) * gx + x;
+    pred[((long long)n * rows_total + row) * nf + k] = o;
+}
+void launch_yolo_decode(const float* head, int cstride, int N, int gy, int gx, int na, const float* anchors_wh, int nc, int img_h,
+                        int img_w, float* pred, int rows_total, int row0, cudaStream_t st) {
+    YDST_CHECK(na == 3, "yolo layer with %d anchors (3 supported)", na);
+    const long long total = (long long)N * na * gy * gx * (nc + 5);
+    const float s0 = (float)((double)img_h / gy), s1 = (float)((double)img_w / gx);
+    yolo_decode_kernel<<<cdiv(total, 256), 256, 0, st>>>(head, cstride, N, gy, gx, na, anchors_wh[0], anchors_wh[1], anchors_wh[2],
+                                                        anchors_wh[3], anchors_wh[4], anchors_wh[5], nc, s0, s1, pred, rows_total, row0);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) avgpool_l2_kernel(Act in, float* __restrict__ out) {
+    const int n = blockIdx.x, c = threadIdx.x;       // 512 channels
+    float s = 0.f;
+    for (int y = 0; y < in.H; ++y)
+        for (int x = 0; x < in.W; ++x)
+            s += __half2float(in.base[(((long long)n * in.Hp() + y + 1) * in.Wp() + x + 1) * in.ctot + in.coff + c]);
+    const float v = s / (float)(in.H * in.W);
+    __shared__ float red[16];
+    float q = v * v;
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 16; ++i) tot += red[i];
+    out[(long long)n * 512 + c] = v / sqrtf(tot);
+}
+void launch_avgpool_l2(const Act& in, float* out, cudaStream_t st) {
+    YDST_CHECK(in.C == 512, "ReID tail expects 512 channels");
+    avgpool_l2_kernel<<<in.N, 512, 0, st>>>(in, out);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv2.resize(u8, INTER_LINEAR) fixed-point model, exact (oracle/cv_resize_ref.py).
+__device__ __forceinline__ void axis_coeff(int d, int n_dst, int n_src, bool clamp_frac, int& i0, int& i1, int& w0, int& w1) {
+    const float f = (float)(((double)d + 0.5) * ((double)n_src / (double)n_dst) - 0.5);
+    int i = (int)floorf(f);
+    float fr = f - (float)i;
+    if (clamp_frac) {
+        if (i < 0) { i = 0; fr = 0.f; }
+        if (i >= n_src - 1) { i = n_src - 1; fr = 0.f; }
+        i0 = i; i1 = min(i + 1, n_src - 1);
+    } else {
+        i1 = min(max(i + 1, 0), n_src - 1);
+        i0 = min(max(i, 0), n_src - 1);
+    }
+    w1 = __float2int_rn(fr * 2048.f);
+    w0 = __float2int_rn((1.f - fr) * 2048.f);
+}
+
+__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, const float* __restrict__ tlwh,
+                                                          int m, float* __restrict__ out, int* err_flag) {
+    const int DW = 64, DH = 128;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * DH * DW) return;
+    const int dx = (int)(idx % DW);
+    const int dy = (int)((idx / DW) % DH);
+    const int b = (int)(idx / (DW * DH));
+    const float bx = tlwh[b * 4 + 0], by = tlwh[b * 4 + 1], bw = tlwh[b * 4 + 2], bh = tlwh[b * 4 + 3];
+    // DeepSort._s_tlwh_to_xyxy: int() truncation toward zero; x+w and y+h are fp32 sums; note the -1
+    const int x1 = max((int)bx, 0), x2 = min((int)(bx + bw), W - 1);
+    const int y1 = max((int)by, 0), y2 = min((int)(by + bh), H - 1);
+    const int sw = x2 - x1, sh = y2 - y1;
+    float* o = out + idx * 3;
+    if (sw <= 0 || sh <= 0) {
+        if (dx == 0 && dy == 0) atomicExch(err_flag, 1);
+        o[0] = o[1] = o[2] = 0.f;
+        return;
+    }
+    int v[3];
+    if (sw == DW && sh == DH) {                      // same size: cv2.resize is a copy
+        const uint8_t* s = frame + ((long long)(y1 + dy) * W + x1 + dx) * 3;
+        v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+    } else {
+        int xa, xb, a0, a1, ya, yb, b0, b1;
+        axis_coeff(dx, DW, sw, true, xa, xb, a0, a1);
+        axis_coeff(dy, DH, sh, false, ya, yb, b0, b1);
+        const uint8_t* r0 = frame + ((long long)(y1 + ya) * W + x1) * 3;
+        const uint8_t* r1 = frame + ((long long)(y1 + yb) * W + x1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = (int)r0[xa * 3 + c] * a0 + (int)r0[xb * 3 + c] * a1;
+            const int h1 = (int)r1[xa * 3 + c] * a0 + (int)r1[xb * 3 + c] * a1;
+            int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v[c] = min(max(r, 0), 255);
+        }
+    }
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = ((float)v[c] / 255.f - mean[c]) / stdv[c];
+}
+void launch_crop_resize(const uint8_t* frame, int H, int W, const float* tlwh, int m, float* out, int* err_flag, cudaStream_t st) {
+    if (m == 0) return;
+    crop_resize_kernel<<<cdiv((long long)m * 128 * 64, 256), 256, 0, st>>>(frame, H, W, tlwh, m, out, err_flag);
+    YDST_CUDA(cudaGetLastError());
+}
+
+}  // namespace ydst

@@ -1,0 +1,427 @@
+// Layer-graph planner/executor: turns a Darknet layer list (or the fixed ReID architecture) into a flat
+// list of kernel launches over flat-padded NHWC fp16 buffers.
+//
+// Reference behaviour reproduced here (yolo3/models/models.py): conv padding (k-1)//2 regardless of the cfg
+// `pad` (:39), bias only without BN (:48), BN eps 1e-5 (:52), leaky 0.1 (:54), maxpool k2/s1 preceded by a
+// ZERO pad right/bottom (:61-63), nearest upsample (:132), route = concat of absolute/relative layer
+// outputs with optional channel-group select (:300-303), shortcut = out[-1] + out[from] with its own
+// activation ignored (:304-306), heads concatenated in cfg order (:312).
+//
+// Fusions: BN folded into an fp32 scale/bias epilogue; activation in the conv epilogue; a conv whose only
+// reader is the following shortcut adds the residual in its epilogue; head convs write fp32 for the decode.
+#include "net.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace ydst {
+
+DeviceArena::~DeviceArena() {
+    for (void* p : ptrs_) cudaFree(p);
+}
+void* DeviceArena::alloc(size_t bytes, bool zero) {
+    void* p = nullptr;
+    bytes = (bytes + 255) & ~(size_t)255;
+    YDST_CUDA(cudaMalloc(&p, bytes));
+    if (zero) YDST_CUDA(cudaMemset(p, 0, bytes));
+    ptrs_.push_back(p);
+    total += bytes;
+    return p;
+}
+
+Act make_act(DeviceArena& arena, int N, int H, int W, int C) {
+    Act a;
+    a.N = N; a.H = H; a.W = W; a.C = C; a.ctot = C; a.coff = 0;
+    a.base = (__half*)arena.alloc((size_t)a.pixels() * C * sizeof(__half));
+    return a;
+}
+
+std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w, int cout, int cin, int k, const float* gamma,
+                                       const float* beta, const float* mean, const float* var, const float* conv_bias, bool first_layer) {
+    auto cw = std::make_unique<ConvWeights>();
+    cw->cin = cin; cw->cout = cout; cw->k = k; cw->cout16 = (cout + 15) & ~15;
+    const int taps = k * k;
+    const int npad = (cout + 255) & ~255;
+    std::vector<float> sc(npad, 0.f), bi(npad, 0.f);
+    for (int o = 0; o < cout; ++o) {
+        if (gamma) {
+            const double s = (double)gamma[o] / std::sqrt((double)var[o] + 1e-5);
+            const double b0 = conv_bias ? (double)conv_bias[o] : 0.0;
+            sc[o] = (float)s;
+            bi[o] = (float)((b0 - (double)mean[o]) * s + (double)beta[o]);
+        } else {
+            sc[o] = 1.f;
+            bi[o] = conv_bias ? conv_bias[o] : 0.f;
+        }
+    }
+    cw->scale = (float*)arena.alloc(sizeof(float) * npad);
+    cw->bias = (float*)arena.alloc(sizeof(float) * npad);
+    YDST_CUDA(cudaMemcpy(cw->scale, sc.data(), sizeof(float) * npad, cudaMemcpyHostToDevice));
+    YDST_CUDA(cudaMemcpy(cw->bias, bi.data(), sizeof(float) * npad, cudaMemcpyHostToDevice));
+    if (first_layer) {
+        YDST_CHECK(cin == 3 && k == 3, "first-layer path is 3x3 over 3 channels");
+        std::vector<float> p((size_t)27 * cout);
+        for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r)
+                    for (int s = 0; s < 3; ++s) p[(size_t)((r * 3 + s) * 3 + c) * cout + o] = w[((o * 3 + c) * 3 + r) * 3 + s];
+        cw->w32 = (float*)arena.alloc(p.size() * sizeof(float));
+        YDST_CUDA(cudaMemcpy(cw->w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        const size_t K = (size_t)taps * cin;
+        std::vector<__half> p((size_t)cw->cout16 * K, __float2half(0.f));
+        for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < taps; ++t) p[(size_t)o * K + (size_t)t * cin + c] = __float2half_rn(w[((size_t)o * cin + c) * taps + t]);
+        cw->w16 = (__half*)arena.alloc(p.size() * sizeof(__half));
+        YDST_CUDA(cudaMemcpy(cw->w16, p.data(), p.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
+    return cw;
+}
+
+void run_plan(const Plan& plan, cudaStream_t st) {
+    for (const Op& op : plan.ops) {
+        switch (op.kind) {
+            case OP_CONV_TC: conv_tc_run(op.conv, st); break;
+            case OP_CONV_FIRST:
+                launch_conv_first(op.fsrc, op.out.N, op.i0, op.i1, op.w->w32, op.w->scale, op.w->bias, op.w->cout, op.i2, op.i3, op.out, st);
+                break;
+            case OP_MAXPOOL: launch_maxpool(op.a, op.out, op.i0, op.i1, op.i2, st); break;
+            case OP_UPSAMPLE: launch_upsample(op.a, op.out, op.i0, st); break;
+            case OP_ADD: launch_add(op.a, op.b, op.out, st); break;
+            case OP_COPY: launch_copy(op.a, op.out, st); break;
+            case OP_YOLO:
+                launch_yolo_decode(op.fsrc, op.i0, op.a.N, op.a.H, op.a.W, 3, op.anchors, op.i1, op.i2, op.i3, op.fdst, op.out.N /*rows_total*/,
+                                   op.out.H /*row0*/, st);
+                break;
+            case OP_AVGPOOL_L2: launch_avgpool_l2(op.a, op.fdst, st); break;
+        }
+    }
+}
+
+// ================================================================================================
+// Detector
+// ================================================================================================
+Detector::Detector(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights, int H_, int W_, int batch_)
+    : H(H_), W(W_), batch(batch_) {
+    YDST_CHECK(batch >= 1 && H > 0 && W > 0, "bad detector geometry");
+    build(layers, n, weights, n_weights);
+    nms_.init(4096, 300);
+}
+
+void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size_t n_weights) {
+    in_f32_ = (float*)arena_.alloc((size_t)batch * H * W * 3 * sizeof(float));
+    // readers of each layer's output
+    std::vector<std::vector<int>> readers(n);
+    for (int l = 0; l < n; ++l) {
+        const int t = L[l].type;
+        if (t == YDST_ROUTE) {
+            for (int s = 0; s < L[l].n_src; ++s) {
+                YDST_CHECK(L[l].src[s] >= 0 && L[l].src[s] < l, "route source out of range at layer %d", l);
+                readers[L[l].src[s]].push_back(l);
+            }
+        } else {
+            if (l > 0) readers[l - 1].push_back(l);
+            if (t == YDST_SHORTCUT) {
+                YDST_CHECK(L[l].src[0] >= 0 && L[l].src[0] < l, "shortcut source out of range at layer %d", l);
+                readers[L[l].src[0]].push_back(l);
+            }
+        }
+    }
+    // first pass: YOLO geometry (row offsets) needs every head's grid size, known only after shapes propagate
+    struct Shape { int C, H, W; };
+    std::vector<Shape> shp(n);
+    std::vector<int> yolo_layers;
+    {
+        Shape cur{3, H, W};
+        for (int l = 0; l < n; ++l) {
+            const ydst_layer_desc& d = L[l];
+            switch (d.type) {
+                case YDST_CONV: {
+                    const int pad = (d.size - 1) / 2;
+                    cur = Shape{d.filters, (cur.H + 2 * pad - d.size) / d.stride + 1, (cur.W + 2 * pad - d.size) / d.stride + 1};
+                    break;
+                }
+                case YDST_MAXPOOL: {
+                    if (d.size == 2 && d.stride == 1) break;                       // zero-pad right/bottom keeps the size
+                    const int pad = (d.size - 1) / 2;
+                    cur = Shape{cur.C, (cur.H + 2 * pad - d.size) / d.stride + 1, (cur.W + 2 * pad - d.size) / d.stride + 1};
+                    break;
+                }
+                case YDST_UPSAMPLE: cur = Shape{cur.C, cur.H * d.size, cur.W * d.size}; break;
+                case YDST_ROUTE: {
+                    int c = 0;
+                    for (int s = 0; s < d.n_src; ++s) {
+                        c += shp[d.src[s]].C;
+                        YDST_CHECK(shp[d.src[s]].H == shp[d.src[0]].H && shp[d.src[s]].W == shp[d.src[0]].W, "route spatial mismatch at layer %d", l);
+                    }
+                    if (d.groups > 0) c /= d.groups;
+                    cur = Shape{c, shp[d.src[0]].H, shp[d.src[0]].W};
+                    break;
+                }
+                case YDST_SHORTCUT: cur = shp[d.src[0]]; break;
+                case YDST_YOLO: yolo_layers.push_back(l); break;
+                default: YDST_CHECK(false, "unknown layer type %d at layer %d", d.type, l);
+            }
+            shp[l] = cur;
+        }
+    }
+    YDST_CHECK(!yolo_layers.empty(), "network has no yolo layer");
+    fields = 5 + L[yolo_layers[0]].classes;
+    rows = 0;
+    std::vector<int> row0(n, 0);
+    for (int yl : yolo_layers) {
+        YDST_CHECK(5 + L[yl].classes == fields, "yolo layers disagree on the class count");
+        row0[yl] = rows;
+        rows += 3 * shp[yl].H * shp[yl].W;
+    }
+    pred = (float*)arena_.alloc((size_t)batch * rows * fields * sizeof(float));
+
+    // second pass: buffers + ops
+    std::vector<Act> out(n);
+    std::vector<float*> head_f32(n, nullptr);
+    std::vector<bool> fused_away(n, false);
+    size_t wp = 0;
+    auto take = [&](size_t cnt) {
+        YDST_CHECK(wp + cnt <= n_weights, "weights payload too short: need %zu floats, have %zu", wp + cnt, n_weights);
+        const float* p = weights + wp;
+        wp += cnt;
+        return p;
+    };
+    for (int l = 0; l < n; ++l) {
+        const ydst_layer_desc& d = L[l];
+        Op op;
+        op.layer = l;
+        switch (d.type) {
+            case YDST_CONV: {
+                const int cin = l == 0 ? 3 : shp[l - 1].C;
+                const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr, *cb = nullptr;
+                if (d.batch_normalize) { beta = take(d.filters); gamma = take(d.filters); mean = take(d.filters); var = take(d.filters); }
+                else cb = take(d.filters);
+                const float* w = take((size_t)d.filters * cin * d.size * d.size);
+                const bool first = (l == 0);
+                YDST_CHECK(first || cin % 16 == 0, "layer %d: Cin=%d is not a multiple of 16", l, cin);
+                weights_.push_back(pack_conv(arena_, w, d.filters, cin, d.size, gamma, beta, mean, var, cb, first));
+                const ConvWeights* cw = weights_.back().get();
+                const bool to_yolo = l + 1 < n && L[l + 1].type == YDST_YOLO;
+                const bool fuse_sc = !to_yolo && l + 1 < n && L[l + 1].type == YDST_SHORTCUT && readers[l].size() == 1 &&
+                                     L[l + 1].src[0] != l && !first;
+                if (to_yolo) {
+                    YDST_CHECK(readers[l].size() == 1, "layer %d: a yolo head conv must only feed its yolo layer", l);
+                    head_f32[l] = (float*)arena_.alloc((size_t)batch * (shp[l].H + 2) * (shp[l].W + 2) * cw->cout16 * sizeof(float));
+                    Act geo;                                  // geometry only (fp32 destination)
+                    geo.N = batch; geo.H = shp[l].H; geo.W = shp[l].W; geo.C = d.filters; geo.ctot = cw->cout16; geo.coff = 0;
+                    op.kind = OP_CONV_TC;
+                    conv_tc_plan(op.conv, out[l - 1], geo, cw->w16, d.size, d.size, d.stride, cw->scale, cw->bias, d.activation, 0, nullptr,
+                                 head_f32[l], d.filters);
+                    out[l] = geo;
+                } else {
+                    out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                    if (first) {
+                        op.kind = OP_CONV_FIRST;
+                        op.fsrc = in_f32_; op.out = out[l]; op.w = cw;
+                        op.i0 = H; op.i1 = W; op.i2 = d.stride; op.i3 = d.activation;
+                        YDST_CHECK(d.size == 3, "first layer must be 3x3");
+                    } else {
+                        op.kind = OP_CONV_TC;
+                        const Act* res = nullptr;
+                        if (fuse_sc) { res = &out[L[l + 1].src[0]]; fused_away[l + 1] = true; }
+                        conv_tc_plan(op.conv, out[l - 1], out[l], cw->w16, d.size, d.size, d.stride, cw->scale, cw->bias, d.activation,
+                                     fuse_sc ? 1 : 0, res, nullptr, d.filters);
+                    }
+                }
+                if (op.kind == OP_CONV_TC) plan.flops += conv_tc_flops(op.conv) * ((double)d.filters / op.conv.p.cout);
+                else plan.flops += 2.0 * batch * shp[l].H * shp[l].W * d.filters * 27.0;
+                plan.ops.push_back(op);
+                break;
+            }
+            case YDST_MAXPOOL: {
+                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                op.kind = OP_MAXPOOL; op.a = out[l - 1]; op.out = out[l];
+                op.i0 = d.size; op.i1 = d.stride; op.i2 = (d.size == 2 && d.stride == 1) ? 1 : 0;
+                plan.ops.push_back(op);
+                break;
+            }
+            case YDST_UPSAMPLE: {
+                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                op.kind = OP_UPSAMPLE; op.a = out[l - 1]; op.out = out[l]; op.i0 = d.size;
+                plan.ops.push_back(op);
+                break;
+            }
+            case YDST_ROUTE: {
+                if (d.n_src == 1) {
+                    out[l] = out[d.src[0]];                                   // alias
+                    YDST_CHECK(head_f32[d.src[0]] == nullptr, "route from a yolo head conv is not supported (layer %d)", l);
+                    if (d.groups > 0) {
+                        out[l].C = out[l].C / d.groups;
+                        out[l].coff += d.group_id * out[l].C;
+                    }
+                } else {
+                    YDST_CHECK(d.groups <= 0, "grouped multi-source route is not supported (layer %d)", l);
+                    out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                    int coff = 0;
+                    for (int s = 0; s < d.n_src; ++s) {
+                        Op cp;
+                        cp.layer = l; cp.kind = OP_COPY; cp.a = out[d.src[s]];
+                        cp.out = out[l]; cp.out.C = cp.a.C; cp.out.coff = coff;
+                        coff += cp.a.C;
+                        plan.ops.push_back(cp);
+                    }
+                }
+                break;
+            }
+            case YDST_SHORTCUT: {
+                if (fused_away[l]) { out[l] = out[l - 1]; break; }            // produced by the conv epilogue
+                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                op.kind = OP_ADD; op.a = out[l - 1]; op.b = out[d.src[0]]; op.out = out[l];
+                plan.ops.push_back(op);
+                break;
+            }
+            case YDST_YOLO: {
+                YDST_CHECK(l > 0 && head_f32[l - 1] != nullptr, "yolo layer %d must follow a convolution", l);
+                YDST_CHECK(shp[l - 1].C == 3 * fields, "yolo layer %d: head has %d channels, expected %d", l, shp[l - 1].C, 3 * fields);
+                op.kind = OP_YOLO;
+                op.fsrc = head_f32[l - 1];
+                op.i0 = out[l - 1].ctot;                  // fp32 row stride (cout16)
+                op.a.N = batch; op.a.H = shp[l].H; op.a.W = shp[l].W;
+                op.i1 = d.classes; op.i2 = H; op.i3 = W;
+                op.fdst = pred;
+                op.out.N = rows; op.out.H = row0[l];      // rows_total / row0 (see run_plan)
+                memcpy(op.anchors, d.anchors, sizeof(op.anchors));
+                out[l] = out[l - 1];
+                plan.ops.push_back(op);
+                break;
+            }
+        }
+    }
+    YDST_CHECK(wp == n_weights, "weights payload has %zu floats, network consumes %zu", n_weights, wp);
+    plan.launches = (int)plan.ops.size();
+}
+
+void Detector::forward_u8(const uint8_t* frame_dev, float* pred_out, cudaStream_t st) {
+    launch_u8_to_f32(frame_dev, in_f32_, (long long)batch * H * W * 3, st);
+    run_plan(plan, st);
+    if (pred_out) YDST_CUDA(cudaMemcpyAsync(pred_out, pred, (size_t)batch * rows * fields * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+void Detector::forward_nchw(const void* x_dev, int is_half, float* pred_out, cudaStream_t st) {
+    launch_nchw_to_nhwc(x_dev, is_half, in_f32_, batch, 3, H, W, st);
+    run_plan(plan, st);
+    if (pred_out) YDST_CUDA(cudaMemcpyAsync(pred_out, pred, (size_t)batch * rows * fields * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+void Detector::nms(float conf, float iou, float* dets_out, int* n_out, cudaStream_t st) {
+    nms_.run(pred, rows, fields, conf, iou, st);
+    if (dets_out) YDST_CUDA(cudaMemcpyAsync(dets_out, nms_.dets, sizeof(float) * 6 * nms_.max_det, cudaMemcpyDeviceToDevice, st));
+    if (n_out) YDST_CUDA(cudaMemcpyAsync(n_out, nms_.counters + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+}
+
+// ================================================================================================
+// ReID net (deep_sort/deep/model.py:48-95)
+// ================================================================================================
+static const int kStage[4][3] = {{64, 64, 0}, {64, 128, 1}, {128, 256, 1}, {256, 512, 1}};   // cin, cout, downsample
+
+Reid::Reid(const float* weights, size_t n_weights, int max_batch_) : max_batch(max_batch_) {
+    YDST_CHECK(max_batch >= 1, "max_batch must be >= 1");
+    size_t wp = 0;
+    auto take = [&](size_t cnt) {
+        YDST_CHECK(wp + cnt <= n_weights, "ReID weights too short");
+        const float* p = weights + wp;
+        wp += cnt;
+        return p;
+    };
+    auto conv_bn = [&](int cout, int cin, int k, bool has_bias, bool first) {
+        const float* w = take((size_t)cout * cin * k * k);
+        const float* cb = has_bias ? take(cout) : nullptr;
+        const float* g = take(cout); const float* b = take(cout); const float* m = take(cout); const float* v = take(cout);
+        weights_.push_back(pack_conv(arena_, w, cout, cin, k, g, b, m, v, cb, first));
+    };
+    conv_bn(64, 3, 3, true, true);
+    for (int s = 0; s < 4; ++s)
+        for (int blk = 0; blk < 2; ++blk) {
+            const int cin = blk == 0 ? kStage[s][0] : kStage[s][1], cout = kStage[s][1];
+            conv_bn(cout, cin, 3, false, false);
+            conv_bn(cout, cout, 3, false, false);
+            if (blk == 0 && kStage[s][2]) conv_bn(cout, cin, 1, false, false);
+        }
+    YDST_CHECK(wp == n_weights, "ReID weights: %zu floats given, %zu consumed", n_weights, wp);
+    in_f32_ = (float*)arena_.alloc((size_t)max_batch * 128 * 64 * 3 * sizeof(float));
+    feat_ = (float*)arena_.alloc((size_t)max_batch * 512 * sizeof(float));
+    err_flag = (int*)arena_.alloc(sizeof(int));
+    bufs_.push_back(make_act(arena_, max_batch, 128, 64, 64));          // 0: stem out
+    int h = 64, w = 32;
+    for (int s = 0; s < 4; ++s) {
+        if (s > 0) { h /= 2; w /= 2; }
+        for (int k = 0; k < 4; ++k) bufs_.push_back(make_act(arena_, max_batch, h, w, kStage[s][1]));   // A, B, T, D
+    }
+}
+
+const Plan& Reid::plan_for(int m) {
+    auto it = plans_.find(m);
+    if (it != plans_.end()) return it->second;
+    if (plans_.size() > 256) plans_.clear();
+    Plan plan;
+    auto view = [&](int i) { Act a = bufs_[i]; a.N = m; return a; };
+    size_t wi = 0;
+    {
+        Op op; op.kind = OP_CONV_FIRST; op.fsrc = in_f32_; op.out = view(0); op.w = weights_[wi++].get();
+        op.i0 = 128; op.i1 = 64; op.i2 = 1; op.i3 = ACT_RELU;
+        plan.ops.push_back(op);
+        plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
+    }
+    Act x = view(1);                                                    // stage-1 buffer A
+    {
+        Op op; op.kind = OP_MAXPOOL; op.a = view(0); op.out = x; op.i0 = 3; op.i1 = 2; op.i2 = 0;
+        plan.ops.push_back(op);
+    }
+    for (int s = 0; s < 4; ++s) {
+        const int base = 1 + 4 * s;
+        Act A = view(base), B = view(base + 1), T = view(base + 2), D = view(base + 3);
+        for (int blk = 0; blk < 2; ++blk) {
+            const bool down = blk == 0 && kStage[s][2];
+            const ConvWeights* w1 = weights_[wi++].get();
+            const ConvWeights* w2 = weights_[wi++].get();
+            const ConvWeights* wd = down ? weights_[wi++].get() : nullptr;
+            // the block's output buffer: the stage buffer x is not currently in
+            Act y = (x.base == A.base) ? B : A;
+            if (s > 0 && blk == 0) y = A;                                // x lives in the previous stage's buffers
+            Op c1; c1.kind = OP_CONV_TC;
+            conv_tc_plan(c1.conv, x, T, w1->w16, 3, 3, down ? 2 : 1, w1->scale, w1->bias, ACT_RELU, 0, nullptr, nullptr, w1->cout);
+            plan.ops.push_back(c1); plan.flops += conv_tc_flops(c1.conv);
+            Act res = x;
+            if (down) {
+                Op cd; cd.kind = OP_CONV_TC;
+                conv_tc_plan(cd.conv, x, D, wd->w16, 1, 1, 2, wd->scale, wd->bias, ACT_LINEAR, 0, nullptr, nullptr, wd->cout);
+                plan.ops.push_back(cd); plan.flops += conv_tc_flops(cd.conv);
+                res = D;
+            }
+            Op c2; c2.kind = OP_CONV_TC;
+            conv_tc_plan(c2.conv, T, y, w2->w16, 3, 3, 1, w2->scale, w2->bias, ACT_RELU, 2, &res, nullptr, w2->cout);
+            plan.ops.push_back(c2); plan.flops += conv_tc_flops(c2.conv);
+            x = y;
+        }
+    }
+    {
+        Op op; op.kind = OP_AVGPOOL_L2; op.a = x; op.fdst = feat_;
+        plan.ops.push_back(op);
+    }
+    plan.launches = (int)plan.ops.size();
+    return plans_.emplace(m, std::move(plan)).first->second;
+}
+
+void Reid::forward(const float* x_dev, int m, float* feat_out, cudaStream_t st) {
+    if (m == 0) return;
+    YDST_CHECK(m <= max_batch, "ReID batch %d exceeds max_batch %d", m, max_batch);
+    if (x_dev != in_f32_)
+        YDST_CUDA(cudaMemcpyAsync(in_f32_, x_dev, (size_t)m * 128 * 64 * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    run_plan(plan_for(m), st);
+    if (feat_out && feat_out != feat_)
+        YDST_CUDA(cudaMemcpyAsync(feat_out, feat_, (size_t)m * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+void Reid::extract(const uint8_t* frame_dev, int H, int W, const float* tlwh_dev, int m, float* feat_out, cudaStream_t st) {
+    if (m == 0) return;
+    YDST_CHECK(m <= max_batch, "ReID batch %d exceeds max_batch %d", m, max_batch);
+    launch_crop_resize(frame_dev, H, W, tlwh_dev, m, in_f32_, err_flag, st);
+    forward(in_f32_, m, feat_out, st);
+}
+
+}  // namespace ydst

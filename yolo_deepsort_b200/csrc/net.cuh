@@ -1,0 +1,92 @@
+// Layer-graph planner/executor shared by the detector (Darknet cfg) and the ReID net.  See net.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/ydst.h"
+#include "conv_tc.cuh"
+#include "layers.cuh"
+#include "nms.cuh"
+
+namespace ydst {
+
+struct ConvWeights {
+    int cin = 0, cout = 0, k = 0, cout16 = 0;
+    __half* w16 = nullptr;    // [cout16][k*k*cin]  (tensor-core path)
+    float* w32 = nullptr;     // [27][cout]         (first-layer path)
+    float* scale = nullptr;   // [cout rounded up to 256]
+    float* bias = nullptr;
+};
+
+enum OpKind { OP_CONV_TC, OP_CONV_FIRST, OP_MAXPOOL, OP_UPSAMPLE, OP_ADD, OP_COPY, OP_YOLO, OP_AVGPOOL_L2 };
+
+struct Op {
+    OpKind kind;
+    ConvTcLaunch conv;           // OP_CONV_TC
+    Act a, b, out;               // generic operands
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    const ConvWeights* w = nullptr;
+    const float* fsrc = nullptr; // fp32 source (first-layer input / yolo head)
+    float* fdst = nullptr;       // fp32 destination
+    float anchors[6] = {0, 0, 0, 0, 0, 0};
+    int layer = -1;              // cfg layer index (profiling / debugging)
+};
+
+class DeviceArena {
+public:
+    ~DeviceArena();
+    void* alloc(size_t bytes, bool zero = true);
+    size_t total = 0;
+private:
+    std::vector<void*> ptrs_;
+};
+
+// Owns activation buffers + op list for a fixed batch size.
+struct Plan {
+    std::vector<Op> ops;
+    int launches = 0;
+    double flops = 0;
+};
+void run_plan(const Plan& plan, cudaStream_t st);
+
+class Detector {
+public:
+    Detector(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights, int H, int W, int batch);
+    void forward_u8(const uint8_t* frame_dev, float* pred_out, cudaStream_t st);
+    void forward_nchw(const void* x_dev, int is_half, float* pred_out, cudaStream_t st);
+    void nms(float conf, float iou, float* dets_out, int* n_out, cudaStream_t st);
+    int H, W, batch, rows = 0, fields = 0;
+    float* pred = nullptr;       // [batch][rows][fields]
+    Nms nms_;
+    Plan plan;
+private:
+    void build(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights);
+    DeviceArena arena_;
+    std::vector<std::unique_ptr<ConvWeights>> weights_;
+    float* in_f32_ = nullptr;    // [batch][H][W][3]
+};
+
+class Reid {
+public:
+    Reid(const float* weights, size_t n_weights, int max_batch);
+    void extract(const uint8_t* frame_dev, int H, int W, const float* tlwh_dev, int m, float* feat_out, cudaStream_t st);
+    void forward(const float* x_dev, int m, float* feat_out, cudaStream_t st);
+    int max_batch;
+    int* err_flag = nullptr;     // device
+private:
+    const Plan& plan_for(int m);
+    DeviceArena arena_;
+    std::vector<std::unique_ptr<ConvWeights>> weights_;
+    std::map<int, Plan> plans_;
+    float* in_f32_ = nullptr;    // [max_batch][128][64][3]
+    float* feat_ = nullptr;      // [max_batch][512]
+    std::vector<Act> bufs_;      // activation buffers allocated for max_batch
+};
+
+// Packs one conv's weights (fp32 OIHW + BN/bias) into device buffers.
+std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w_oihw, int cout, int cin, int k, const float* gamma,
+                                       const float* beta, const float* mean, const float* var, const float* conv_bias, bool first_layer);
+Act make_act(DeviceArena& arena, int N, int H, int W, int C);
+
+}  // namespace ydst
