@@ -26,6 +26,15 @@ extern "C" {
 
 const char* ydst_last_error(void);
 int ydst_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long long ydst_launch_count(void);
+/* Per-op timing of the layer graphs (detector + ReID): between _begin and _end every op of a forward is bracketed by
+ * CUDA events on the launching stream.  _end synchronises and returns, per op in launch order: kind (0 = tcgen05 conv,
+ * 1 = first-layer conv, 2 maxpool, 3 upsample, 4 add, 5 copy, 6 yolo decode, 7 avgpool+L2), cfg layer index (-1 for
+ * ReID), useful FLOPs (2*M*N*K, convs only), algorithmic bytes (convs only) and milliseconds.  Measurement aid for
+ * bench.py's roofline object; no reference counterpart (the reference times with time.time(), img_detect.py:84-95). */
+int ydst_profile_begin(void);
+int ydst_profile_end(int cap, int* kind_host, int* layer_host, double* flops_host, double* bytes_host, float* ms_host, int* n_host);
 
 /* ------------------------------------------------------------------------------------------------
  * Detector: Darknet graph + YOLO heads + NMS.
@@ -71,6 +80,12 @@ int ydst_detector_forward_u8(ydst_detector* d, const uint8_t* frame_dev, float* 
  * dets_dev (max_det=300 x 6 float32: x1,y1,x2,y2,conf,cls, score-descending), n_dev (int32 count),
  * both on the device.                                                                               */
 int ydst_detector_nms(ydst_detector* d, float conf_thres, float iou_thres, float* dets_dev, int* n_dev, void* stream);
+/* Parity aid: the output of cfg layer `layer` from the last forward (what Darknet.forward keeps in layer_outputs,
+ * yolo3/models/models.py:296-311), as dense NHWC float16 (N,H,W,C) -- float32 for the linear head convs.  For a
+ * convolution whose following shortcut was fused into its epilogue this is the post-add tensor; a yolo layer aliases
+ * its head conv. */
+int ydst_detector_layer_shape(const ydst_detector* d, int layer, int* n, int* h, int* w, int* c, int* is_f32);
+int ydst_detector_layer_output(const ydst_detector* d, int layer, void* dense_dev, void* stream);
 /* total useful conv FLOPs of one forward (2*M*N*K over conv layers, logical shapes) */
 double ydst_detector_flops(const ydst_detector* d);
 /* number of kernel launches one forward issues */

@@ -16,8 +16,20 @@ from yolo_deepsort_b200._lib import check, lib, ptr, stream_ptr
 pytestmark = pytest.mark.gpu
 
 
+_KEEP = []          # device tensors must outlive the asynchronous kernels that read their raw pointers
+
+
 def dev(a, dtype=torch.float32):
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(DEV).contiguous()
+    t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(DEV).contiguous()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def xyah_to_tlwh(z):
@@ -147,8 +159,9 @@ def test_costs_vs_oracle():
     counts = rng.integers(1, budget + 1, n)
     seg = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     gal = unit_rows(rng, int(seg[-1])) * rng.uniform(0.9, 1.1, (int(seg[-1]), 1)).astype(np.float32)
-    dets = np.concatenate([tl[:m - 10] + rng.normal(0, 3, (m - 10, 4)), np.stack([rng.uniform(0, 500, 10), rng.uniform(0, 500, 10),
-                          rng.uniform(20, 80, 10), rng.uniform(40, 160, 10)], 1)], 0).astype(np.float32)[:m]
+    k = min(n, m - 10)
+    dets = np.concatenate([tl[:k] + rng.normal(0, 3, (k, 4)), np.stack([rng.uniform(0, 500, m - k), rng.uniform(0, 500, m - k),
+                          rng.uniform(20, 80, m - k), rng.uniform(40, 160, m - k)], 1)], 0).astype(np.float32)[:m]
     feats = unit_rows(rng, m)
     feats[:20] = gal[seg[:20]] / np.linalg.norm(gal[seg[:20]], axis=1, keepdims=True) + 0.02 * rng.standard_normal((20, 512)).astype(np.float32)
     # oracle

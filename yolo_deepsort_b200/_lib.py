@@ -33,12 +33,17 @@ _SZ = ctypes.c_size_t
 SIGNATURES = {
     "ydst_last_error": (ctypes.c_char_p, []),
     "ydst_version": (_I, []),
+    "ydst_launch_count": (ctypes.c_longlong, []),
+    "ydst_profile_begin": (_I, []),
+    "ydst_profile_end": (_I, [_I, _P, _P, _P, _P, _P, ctypes.POINTER(_I)]),
     "ydst_detector_create": (_I, [ctypes.POINTER(LayerDesc), _I, _P, _SZ, _I, _I, _I, ctypes.POINTER(_P)]),
     "ydst_detector_destroy": (_I, [_P]),
     "ydst_detector_shape": (_I, [_P, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ydst_detector_forward_nchw": (_I, [_P, _P, _I, _P, _P]),
     "ydst_detector_forward_u8": (_I, [_P, _P, _P, _P]),
     "ydst_detector_nms": (_I, [_P, _F, _F, _P, _P, _P]),
+    "ydst_detector_layer_shape": (_I, [_P, _I] + [ctypes.POINTER(_I)] * 5),
+    "ydst_detector_layer_output": (_I, [_P, _I, _P, _P]),
     "ydst_detector_flops": (ctypes.c_double, [_P]),
     "ydst_detector_launches": (_I, [_P]),
     "ydst_nms": (_I, [_P, _I, _I, _F, _F, _P, ctypes.POINTER(_I), _P]),

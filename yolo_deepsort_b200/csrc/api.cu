@@ -10,6 +10,8 @@
 namespace ydst {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
 }  // namespace ydst
 
 using namespace ydst;
@@ -34,6 +36,36 @@ extern "C" {
 
 const char* ydst_last_error(void) { return g_err.c_str(); }
 int ydst_version(void) { return 100; }
+long long ydst_launch_count(void) { return g_launches; }
+
+int ydst_profile_begin(void) {
+    YDST_API_BEGIN
+    profile_begin();
+    YDST_API_END
+}
+int ydst_profile_end(int cap, int* kind_host, int* layer_host, double* flops_host, double* bytes_host, float* ms_host, int* n_host) {
+    YDST_API_BEGIN
+    YDST_CHECK(n_host, "null argument");
+    YDST_CUDA(cudaDeviceSynchronize());
+    std::vector<OpSample>& v = profile_samples();
+    int n = 0;
+    for (OpSample& s : v) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.e0, s.e1);
+        cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
+        if (n < cap) {
+            if (kind_host) kind_host[n] = s.kind;
+            if (layer_host) layer_host[n] = s.layer;
+            if (flops_host) flops_host[n] = s.flops;
+            if (bytes_host) bytes_host[n] = s.bytes;
+            if (ms_host) ms_host[n] = ms;
+            ++n;
+        }
+    }
+    *n_host = n;
+    v.clear();
+    YDST_API_END
+}
 
 // ---------------- detector ----------------
 int ydst_detector_create(const ydst_layer_desc* layers, int n_layers, const float* weights_host, size_t n_weights, int height,
@@ -74,6 +106,18 @@ int ydst_detector_nms(ydst_detector* d, float conf_thres, float iou_thres, float
     YDST_API_BEGIN
     YDST_CHECK(d, "null handle");
     d->impl->nms(conf_thres, iou_thres, dets_dev, n_dev, S(stream));
+    YDST_API_END
+}
+int ydst_detector_layer_shape(const ydst_detector* d, int layer, int* n, int* h, int* w, int* c, int* is_f32) {
+    YDST_API_BEGIN
+    YDST_CHECK(d, "null handle");
+    d->impl->layer_shape(layer, n, h, w, c, is_f32);
+    YDST_API_END
+}
+int ydst_detector_layer_output(const ydst_detector* d, int layer, void* dense_dev, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(d && dense_dev, "null argument");
+    d->impl->layer_output(layer, dense_dev, S(stream));
     YDST_API_END
 }
 double ydst_detector_flops(const ydst_detector* d) { return d ? d->impl->plan.flops : 0.0; }

@@ -16,6 +16,8 @@ namespace ydst {
 // message retrievable through ydst_last_error().
 // ---------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
+// every kernel launch of this library is counted here (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
 struct Error {
     std::string msg;
 };

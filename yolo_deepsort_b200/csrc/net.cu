@@ -79,8 +79,31 @@ std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w, int c
     return cw;
 }
 
+static bool g_profiling = false;
+static std::vector<OpSample> g_samples;
+void profile_begin() { g_profiling = true; g_samples.clear(); }
+bool profile_active() { return g_profiling; }
+std::vector<OpSample>& profile_samples() { g_profiling = false; return g_samples; }
+
+// algorithmic bytes of one conv: activations in + out (fp16, logical dims) + weights
+static double conv_bytes(const ConvTcLaunch& L) {
+    const ConvTcParams& p = L.p;
+    const double stride2 = p.mode == 1 ? 4.0 : 1.0;
+    const double in_px = (double)p.N * p.Ho * p.Wo * stride2;
+    return 2.0 * (in_px * p.cin + (double)p.N * p.Ho * p.Wo * p.cout * (p.out_f32 ? 2.0 : 1.0) + (double)p.cout * p.R * p.S * p.cin);
+}
+
 void run_plan(const Plan& plan, cudaStream_t st) {
     for (const Op& op : plan.ops) {
+        OpSample smp;
+        if (g_profiling) {
+            smp.kind = op.kind; smp.layer = op.layer;
+            smp.flops = op.kind == OP_CONV_TC ? conv_tc_flops(op.conv) : 0.0;
+            smp.bytes = op.kind == OP_CONV_TC ? conv_bytes(op.conv) : 0.0;
+            cudaEventCreate(&smp.e0); cudaEventCreate(&smp.e1);
+            cudaEventRecord(smp.e0, st);
+        }
+        count_launch();
         switch (op.kind) {
             case OP_CONV_TC: conv_tc_run(op.conv, st); break;
             case OP_CONV_FIRST:
@@ -96,6 +119,7 @@ void run_plan(const Plan& plan, cudaStream_t st) {
                 break;
             case OP_AVGPOOL_L2: launch_avgpool_l2(op.a, op.fdst, st); break;
         }
+        if (g_profiling) { cudaEventRecord(smp.e1, st); g_samples.push_back(smp); }
     }
 }
 
@@ -296,15 +320,35 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
     }
     YDST_CHECK(wp == n_weights, "weights payload has %zu floats, network consumes %zu", n_weights, wp);
     plan.launches = (int)plan.ops.size();
+    out_ = out;
+    head_f32_ = head_f32;
+}
+
+void Detector::layer_shape(int l, int* n, int* h, int* w, int* c, int* is_f32) const {
+    YDST_CHECK(l >= 0 && l < (int)out_.size(), "layer index %d out of range", l);
+    const Act& a = out_[l];
+    if (n) *n = a.N; if (h) *h = a.H; if (w) *w = a.W; if (c) *c = a.C;
+    if (is_f32) *is_f32 = head_f32_[l] != nullptr;
+}
+void Detector::layer_output(int l, void* dense_out, cudaStream_t st) const {
+    YDST_CHECK(l >= 0 && l < (int)out_.size(), "layer index %d out of range", l);
+    const Act& a = out_[l];
+    if (head_f32_[l]) launch_unpack_f32(head_f32_[l], a.ctot, a.N, a.H, a.W, a.C, (float*)dense_out, st);
+    else {
+        YDST_CHECK(a.base != nullptr, "layer %d has no materialised output", l);
+        launch_unpack(a, (__half*)dense_out, st);
+    }
 }
 
 void Detector::forward_u8(const uint8_t* frame_dev, float* pred_out, cudaStream_t st) {
     launch_u8_to_f32(frame_dev, in_f32_, (long long)batch * H * W * 3, st);
+    count_launch();
     run_plan(plan, st);
     if (pred_out) YDST_CUDA(cudaMemcpyAsync(pred_out, pred, (size_t)batch * rows * fields * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
 void Detector::forward_nchw(const void* x_dev, int is_half, float* pred_out, cudaStream_t st) {
     launch_nchw_to_nhwc(x_dev, is_half, in_f32_, batch, 3, H, W, st);
+    count_launch();
     run_plan(plan, st);
     if (pred_out) YDST_CUDA(cudaMemcpyAsync(pred_out, pred, (size_t)batch * rows * fields * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
@@ -421,6 +465,7 @@ void Reid::extract(const uint8_t* frame_dev, int H, int W, const float* tlwh_dev
     if (m == 0) return;
     YDST_CHECK(m <= max_batch, "ReID batch %d exceeds max_batch %d", m, max_batch);
     launch_crop_resize(frame_dev, H, W, tlwh_dev, m, in_f32_, err_flag, st);
+    count_launch();
     forward(in_f32_, m, feat_out, st);
 }
 

@@ -50,6 +50,12 @@ struct Plan {
 };
 void run_plan(const Plan& plan, cudaStream_t st);
 
+// Optional per-op timing (CUDA events recorded on the launching stream around every op of run_plan).
+struct OpSample { int kind; int layer; double flops; double bytes; cudaEvent_t e0, e1; };
+void profile_begin();
+bool profile_active();
+std::vector<OpSample>& profile_samples();
+
 class Detector {
 public:
     Detector(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights, int H, int W, int batch);
@@ -60,7 +66,12 @@ public:
     float* pred = nullptr;       // [batch][rows][fields]
     Nms nms_;
     Plan plan;
+    // debug/parity view: output of cfg layer `l` of the last forward, unpacked to dense NHWC fp16 (N,H,W,C)
+    void layer_shape(int l, int* n, int* h, int* w, int* c, int* is_f32) const;
+    void layer_output(int l, void* dense_out, cudaStream_t st) const;
 private:
+    std::vector<Act> out_;            // per cfg layer (aliases for routes / fused shortcuts)
+    std::vector<float*> head_f32_;    // fp32 buffers of the yolo head convs
     void build(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights);
     DeviceArena arena_;
     std::vector<std::unique_ptr<ConvWeights>> weights_;

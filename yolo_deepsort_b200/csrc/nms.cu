@@ -170,10 +170,12 @@ void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaSt
     nms_mask_kernel<<<cap, 128, 0, st>>>(sorted, counters, cap, iou, mask, words);
     nms_sweep_kernel<<<1, 32, 0, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
     YDST_CUDA(cudaGetLastError());
+    count_launch(4);
 }
 void Nms::to_tracker_inputs(float rw, float rh, const int* class_mask_dev, int n_mask, float* tlwh, float* conf, float* cls, cudaStream_t st) {
     dets_to_tracks_kernel<<<1, 1024, 0, st>>>(dets, counters + 1, rw, rh, class_mask_dev, n_mask, tlwh, conf, cls, counters + 3);
     YDST_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 }  // namespace ydst

@@ -125,6 +125,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         YDST_CHECK(cls_dev != nullptr, "tracker update needs payload_host or cls_dev");
         int* d_cls = over_ + cap_t_;                                // scratch: over_ has cap_t+cap_d ints, LSAP uses <= min(cap_t,cap_d)
         cls_to_int_kernel<<<(m + 127) / 128, 128, 0, st>>>(cls_dev, m, d_cls);
+        count_launch();
         YDST_CUDA(cudaMemcpyAsync(h_cls, d_cls, m * sizeof(int), cudaMemcpyDeviceToHost, st));
         YDST_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < m; ++i) payload[i] = h_cls[i];
@@ -268,6 +269,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         o[0] = (int32_t)cx1; o[1] = (int32_t)cy1; o[2] = (int32_t)x2; o[3] = (int32_t)y2; o[4] = t.id; o[5] = t.payload;
     }
     *k_host = K;
+    count_launch(launches_last);
 }
 
 void Tracker::snapshot(int32_t* table_host, float* mean_host, int cap, int* n_host, cudaStream_t st) {

@@ -169,6 +169,17 @@ class Darknet:
     def flops(self):
         return lib().ydst_detector_flops(self.handle(1))
 
+    def layer_output(self, layer, batch=1):
+        """Parity aid: output of cfg layer `layer` from the last forward as a dense (N,H,W,C) tensor."""
+        h = self.handle(batch)
+        v = [ctypes.c_int() for _ in range(5)]
+        check(lib().ydst_detector_layer_shape(h, int(layer), *[ctypes.byref(x) for x in v]))
+        n, hh, ww, c, f32 = (x.value for x in v)
+        out = torch.empty((n, hh, ww, c), dtype=torch.float32 if f32 else torch.float16, device=self._device)
+        with torch.cuda.device(self._device):
+            check(lib().ydst_detector_layer_output(h, int(layer), ptr(out), stream_ptr()))
+        return out
+
     # ---- forward ----
     def forward(self, x):
         assert x.dim() == 4 and x.shape[1] == 3 and tuple(x.shape[2:]) == tuple(self.img_size), \
