@@ -140,11 +140,12 @@ int ydst_kf_update(float* mean_dev, float* cov_dev, const float* det_tlwh_dev, i
 int ydst_gate_position(const float* mean_dev, const float* cov_dev, int n, const float* det_tlwh_dev, int m, float* maha_dev,
                        void* stream);
 /* gallery_dev (G,512) raw features, seg_host[n+1] row offsets per track; det_feat_dev (m,512); cost_dev (n,m):
- * min cosine distance per track, gated by position Mahalanobis > 5.9915 -> 1e5, clamped > max_dist -> max_dist+1e-5 */
+ * min cosine distance per track, gated by position Mahalanobis > 5.9915 -> 1e5, clamped > max_dist -> max_dist+1e-5.
+ * Thresholds are doubles: the reference compares in float32 but forms max_distance + 1e-5 in double (linear_assignment.py:52). */
 int ydst_appearance_cost(const float* gallery_dev, const int* seg_host, int n, const float* det_feat_dev, int m,
-                         const float* mean_dev, const float* cov_dev, const float* det_tlwh_dev, float max_dist, float* cost_dev,
+                         const float* mean_dev, const float* cov_dev, const float* det_tlwh_dev, double max_dist, float* cost_dev,
                          void* stream);
-int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float* det_tlwh_dev, int m, float max_dist,
+int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float* det_tlwh_dev, int m, double max_dist,
                   float* cost_dev, void* stream);
 /* cost_dev (nr,nc) float32 row-major.  Writes min(nr,nc) pairs sorted by row, exactly as scipy returns them;
  * over_max_host[i] = cost[row,col] > max_dist.  Synchronises.                                        */
@@ -158,7 +159,7 @@ int ydst_lsap(const float* cost_dev, int nr, int nc, float max_dist, int* rows_h
  * lifecycle bookkeeping runs on the host inside this call.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct ydst_tracker ydst_tracker;
-int ydst_tracker_create(float max_dist, float max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks,
+int ydst_tracker_create(double max_dist, double max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks,
                         int cap_dets, ydst_tracker** out);
 int ydst_tracker_destroy(ydst_tracker* t);
 /* One DeepSort.update step after feature extraction: tlwh_dev (m,4), feat_dev (m,512) float32 on the device,

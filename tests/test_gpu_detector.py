@@ -163,6 +163,9 @@ def test_other_cfgs_forward(name, size):
         rows.append((li, b["type"], e))
         worst = max(worst, e)
     top = sorted(rows, key=lambda r: -r[2])[:3]
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", f"layer_err_{name}.txt"), "w") as fh:
+            fh.write("\n".join("%3d %-14s %.3e" % r for r in rows) + "\n")
     print("%s: %d layers, worst relative layer error %.3g at %s" % (name, len(rows), worst, top))
     assert worst < 2e-2
     logit = lambda p_: np.log(np.clip(p_, 1e-7, 1 - 1e-7) / (1 - np.clip(p_, 1e-7, 1 - 1e-7)))

@@ -266,7 +266,7 @@ int ydst_gate_position(const float* mean_dev, const float* cov_dev, int n, const
     YDST_API_END
 }
 int ydst_appearance_cost(const float* gallery_dev, const int* seg_host, int n, const float* det_feat_dev, int m, const float* mean_dev,
-                         const float* cov_dev, const float* det_tlwh_dev, float max_dist, float* cost_dev, void* stream) {
+                         const float* cov_dev, const float* det_tlwh_dev, double max_dist, float* cost_dev, void* stream) {
     YDST_API_BEGIN
     YDST_CHECK(seg_host && n >= 0 && m >= 0, "bad argument");
     if (n == 0 || m == 0) return 0;
@@ -295,7 +295,7 @@ int ydst_appearance_cost(const float* gallery_dev, const int* seg_host, int n, c
     cleanup();
     YDST_API_END
 }
-int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float* det_tlwh_dev, int m, float max_dist, float* cost_dev,
+int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float* det_tlwh_dev, int m, double max_dist, float* cost_dev,
                   void* stream) {
     YDST_API_BEGIN
     launch_iou_cost(mean_dev, nullptr, tsu_dev, n, det_tlwh_dev, nullptr, m, max_dist, cost_dev, S(stream));
@@ -338,7 +338,7 @@ int ydst_lsap(const float* cost_dev, int nr, int nc, float max_dist, int* rows_h
 }
 
 // ---------------- tracker ----------------
-int ydst_tracker_create(float max_dist, float max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks, int cap_dets,
+int ydst_tracker_create(double max_dist, double max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks, int cap_dets,
                         ydst_tracker** out) {
     YDST_API_BEGIN
     YDST_CHECK(out, "null argument");

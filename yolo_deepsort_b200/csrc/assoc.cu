@@ -359,10 +359,11 @@ __global__ void cost_finalize_kernel(const int* __restrict__ cost_enc, const flo
     cost[e] = c;
 }
 void launch_cost_finalize(const int* cost_enc, const float* mean, const float* cov, const int* idx, int n, const float* det_tlwh, int m,
-                          float max_dist, float* cost, cudaStream_t st) {
+                          double max_dist, float* cost, cudaStream_t st) {
     if ((long long)n * m == 0) return;
-    const float clamp_val = (float)((double)max_dist + 1e-5);
-    cost_finalize_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(cost_enc, mean, cov, idx, n, det_tlwh, m, max_dist, clamp_val, cost);
+    // the reference compares in fp32 but forms the replacement value in double: max_distance + 1e-5 (linear_assignment.py:52)
+    const float clamp_val = (float)(max_dist + 1e-5);
+    cost_finalize_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(cost_enc, mean, cov, idx, n, det_tlwh, m, (float)max_dist, clamp_val, cost);
     YDST_CUDA(cudaGetLastError());
 }
 
@@ -389,10 +390,10 @@ __global__ void iou_cost_kernel(const float* __restrict__ mean, const int* __res
     cost[e] = c;
 }
 void launch_iou_cost(const float* mean, const int* idx, const int* tsu, int n, const float* det_tlwh, const int* det_idx, int m,
-                     float max_dist, float* cost, cudaStream_t st) {
+                     double max_dist, float* cost, cudaStream_t st) {
     if ((long long)n * m == 0) return;
-    const float clamp_val = (float)((double)max_dist + 1e-5);
-    iou_cost_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(mean, idx, tsu, n, det_tlwh, det_idx, m, max_dist, clamp_val, cost);
+    const float clamp_val = (float)(max_dist + 1e-5);
+    iou_cost_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(mean, idx, tsu, n, det_tlwh, det_idx, m, (float)max_dist, clamp_val, cost);
     YDST_CUDA(cudaGetLastError());
 }
 

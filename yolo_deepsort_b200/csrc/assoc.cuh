@@ -27,10 +27,10 @@ void launch_fill_i32(int* p, int v, long long n, cudaStream_t st);
 void launch_cosine_min(const float* gallery, const int* row_ptr, const int* row_track, int G, const float* det_feat_n, int m,
                        int* cost_enc, cudaStream_t st);
 void launch_cost_finalize(const int* cost_enc, const float* mean, const float* cov, const int* idx, int n, const float* det_tlwh,
-                          int m, float max_dist, float* cost, cudaStream_t st);
+                          int m, double max_dist, float* cost, cudaStream_t st);
 // IoU cost (iou_matching.py:5-91) between tracks idx[0..n) and detections det_idx[0..m), clamped at max_dist (+1e-5)
 void launch_iou_cost(const float* mean, const int* idx, const int* tsu, int n, const float* det_tlwh, const int* det_idx, int m,
-                     float max_dist, float* cost, cudaStream_t st);
+                     double max_dist, float* cost, cudaStream_t st);
 void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 
 // Exact rectangular LSAP with scipy's tie-breaking.  cost: [R][C] row-major with R <= C.

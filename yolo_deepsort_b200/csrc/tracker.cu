@@ -34,7 +34,7 @@ __global__ void cls_to_int_kernel(const float* __restrict__ cls, int m, int* __r
     if (i < m) out[i] = (int)cls[i];
 }
 
-Tracker::Tracker(float max_dist, float max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets)
+Tracker::Tracker(double max_dist, double max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets)
     : max_dist_(max_dist), max_iou_(max_iou), max_age_(max_age), n_init_(n_init), budget_(budget), cap_t_(cap_tracks), cap_d_(cap_dets) {
     YDST_CHECK(budget >= 1 && cap_tracks >= 1 && cap_dets >= 1, "bad tracker capacities");
     const size_t nt = cap_t_, nd = cap_d_;
@@ -167,7 +167,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         launch_cosine_min(gallery_, d_rp, d_rt, G, det_n_, m, cost_enc_, st);
         launch_cost_finalize(cost_enc_, mean_, cov_, d_slots, na, tlwh, m, max_dist_, cost_, st);
         launches_last += 3;
-        A = solve(cost_, confirmed, all_dets, max_dist_, st);
+        A = solve(cost_, confirmed, all_dets, (float)max_dist_, st);
     }
     std::vector<int> iou_cand = unconfirmed, um_t_a;
     for (int k : A.um_t) (tracks[k].tsu == 1 ? iou_cand : um_t_a).push_back(k);
@@ -183,7 +183,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         int* d_dets = upload(A.um_d, st);
         launch_iou_cost(mean_, d_slots, d_tsu, nb, tlwh, d_dets, mb, max_iou_, cost_, st);
         ++launches_last;
-        B = solve(cost_, iou_cand, A.um_d, max_iou_, st);
+        B = solve(cost_, iou_cand, A.um_d, (float)max_iou_, st);
     }
     std::vector<std::pair<int, int>> matches = A.matches;
     matches.insert(matches.end(), B.matches.begin(), B.matches.end());

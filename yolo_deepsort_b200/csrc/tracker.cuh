@@ -17,7 +17,7 @@ struct TrackHost {
 
 class Tracker {
 public:
-    Tracker(float max_dist, float max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets);
+    Tracker(double max_dist, double max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets);
     ~Tracker();
     // payload_host may be null when cls_dev (float class ids on the device) is given
     void update(const float* tlwh_dev, const float* feat_dev, const int* payload_host, const float* cls_dev, int m, int32_t* out_host,
@@ -33,7 +33,7 @@ private:
     // solves the LSAP for the device cost matrix [nt][nd] and applies linear_assignment.py:58-72
     Assign solve(const float* cost, const std::vector<int>& track_indices, const std::vector<int>& det_indices, float max_dist, cudaStream_t st);
     int* upload(const std::vector<int>& v, cudaStream_t st);
-    float max_dist_, max_iou_;
+    double max_dist_, max_iou_;    // kept in double: the clamp value max_distance + 1e-5 is formed in double by the reference
     int max_age_, n_init_, budget_, cap_t_, cap_d_;
     // device state
     float *mean_ = nullptr, *cov_ = nullptr, *gallery_ = nullptr, *det_n_ = nullptr;
