@@ -256,6 +256,14 @@ def run_ours(args):
     # ---------------- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), untimed pass ----------------
     kind, layer, flops, nbytes, ms, nprof = profile_ops(pipe, dev, t)
     t += nprof
+    if args.dump_ops and rank == 0:
+        per = len(kind) // nprof                                        # ops per step (same op list every step)
+        with open(args.dump_ops, "w") as fh:
+            fh.write("op,kind,layer,gflop,mbytes,us_avg,tflops\n")
+            for i in range(per):
+                us = float(np.mean(ms[i::per][:nprof])) * 1e3 if len(kind) == per * nprof else float(ms[i]) * 1e3
+                fh.write("%d,%d,%d,%.4f,%.3f,%.2f,%.1f\n" % (i, kind[i], layer[i], flops[i] / 1e9, nbytes[i] / 1e6, us,
+                                                            flops[i] / max(us, 1e-3) / 1e6))
     conv = kind == 0
     peaks, peak_src = measured_peaks()
     conv_ms = float(ms[conv].sum()) / nprof
@@ -366,6 +374,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames timed by the cpu_baseline leg (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event timings of the layer graphs to this CSV")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 24 if args.steps is None else args.steps             # one step = one frame, ~0.7 s on 8 host cores

@@ -106,6 +106,12 @@ int ydst_conv2d(const void* x_dev, int N, int H, int W, int cin, const float* w_
                 const float* bn_host, const float* bias_host, int act, const void* res_dev, int res_mode, void* y_dev,
                 int y_is_f32, void* stream);
 
+/* The tiling the planner picks for a stride-1 convolution (k = 1 or 3, cin % 64 == 0) on the halo kernel: N tile, K split,
+ * resident CTAs per SM, CTAs launched and the cost model's estimate.  Pure host function (no CUDA call): lets the CPU test
+ * tier pin the planner's choices for the BASELINE layer shapes.  No reference counterpart (cuDNN picks its own algorithms). */
+int ydst_conv_tiling(int N, int H, int W, int cin, int cout, int k, int* block_n, int* ksplit, int* occupancy, int* ctas,
+                     double* model_us);
+
 /* ------------------------------------------------------------------------------------------------
  * ReID extractor: crop + cv2-exact resize + normalise + Net(reid=True).
  * Replaces DeepSort._get_features (deep_sort/deep_sort.py:133-146), Extractor.__call__

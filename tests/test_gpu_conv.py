@@ -28,6 +28,10 @@ CASES = [
     ("mish_1x1", 1, 76, 76, 128, 64, 1, 1, True, 2, 0, False),
     ("deep_k_wide_n", 1, 19, 19, 512, 1024, 3, 1, True, 1, 0, False),
     ("reid_8x4_batch7", 7, 8, 4, 512, 512, 3, 1, True, 3, 0, False),
+    ("3x3_s1_76_two_boxes", 1, 76, 76, 128, 256, 3, 1, True, 1, 1, False),
+    ("3x3_s1_152_wide_halo", 1, 152, 152, 64, 128, 3, 1, True, 1, 0, False),
+    ("1x1_s1_768_concat_k", 1, 38, 38, 768, 256, 1, 1, True, 1, 0, False),
+    ("reid_64x32_batch3", 3, 64, 32, 64, 64, 3, 1, True, 3, 2, False),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),
@@ -62,3 +66,20 @@ def test_conv_parity(case):
     bad = (err > tol).sum().item()
     assert bad == 0, f"{name}: {bad} / {err.numel()} elements out of tolerance, max err {err.max().item():.4g}"
     assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("cps", [1, 2, 3])
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("deep_k_wide_n", "res_after_act", "1x1_s1_768_concat_k", "head_255_f32")],
+                         ids=lambda c: c[0])
+def test_conv_split_k(case, cps, monkeypatch):
+    """The same convolutions with the K split forced (YDST_FORCE_CPS channel blocks per split): partial sums meet in the
+    workspace and are added in split order, so the result must stay within the same tolerance AND be run-to-run identical."""
+    monkeypatch.setenv("YDST_FORCE_CPS", str(cps))
+    test_conv_parity(case)
+    name, N, H, W, cin, cout, k, stride, use_bn, act, res_mode, out_f32 = case
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, H, W, cin, generator=g).half().to(DEV)
+    w = (torch.randn(cout, cin, k, k, generator=g) * float(np.sqrt(2.0 / (cin * k * k)))).numpy()
+    b = (0.1 * torch.randn(cout, generator=g)).numpy()
+    ys = [conv2d_abi(x, w, stride, None, b, act, None, 0, out_f32) for _ in range(3)]
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2]), "split-K reduction must be deterministic"

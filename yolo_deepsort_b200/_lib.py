@@ -48,6 +48,7 @@ SIGNATURES = {
     "ydst_detector_launches": (_I, [_P]),
     "ydst_nms": (_I, [_P, _I, _I, _F, _F, _P, ctypes.POINTER(_I), _P]),
     "ydst_conv2d": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P]),
+    "ydst_conv_tiling": (_I, [_I, _I, _I, _I, _I, _I] + [ctypes.POINTER(_I)] * 4 + [ctypes.POINTER(ctypes.c_double)]),
     "ydst_reid_create": (_I, [_P, _SZ, _I, ctypes.POINTER(_P)]),
     "ydst_reid_destroy": (_I, [_P]),
     "ydst_reid_extract": (_I, [_P, _P, _I, _I, _P, _I, _P, _P]),

@@ -164,20 +164,40 @@ int ydst_conv2d(const void* x_dev, int N, int H, int W, int cin, const float* w_
         Act res;
         if (res_dev) { res = make_act(arena, N, Ho, Wo, cout); launch_pack((const __half*)res_dev, res, st); }
         ConvTcLaunch L;
+        ConvWorkspace ws = make_conv_workspace(arena);
         if (y_is_f32) {
             float* f32 = (float*)arena.alloc((size_t)N * (Ho + 2) * (Wo + 2) * cw->cout16 * sizeof(float));
             Act geo; geo.N = N; geo.H = Ho; geo.W = Wo; geo.C = cout; geo.ctot = cw->cout16; geo.coff = 0;
-            conv_tc_plan(L, in, geo, cw->w16, k, k, stride, cw->scale, cw->bias, act, 0, nullptr, f32, cout);
+            conv_tc_plan(L, in, geo, cw->w16, k, k, stride, cw->scale, cw->bias, act, 0, nullptr, f32, cout, &ws);
             conv_tc_run(L, st);
             launch_unpack_f32(f32, cw->cout16, N, Ho, Wo, cout, (float*)y_dev, st);
         } else {
             Act out = make_act(arena, N, Ho, Wo, cout);
-            conv_tc_plan(L, in, out, cw->w16, k, k, stride, cw->scale, cw->bias, act, res_dev ? res_mode : 0, res_dev ? &res : nullptr, nullptr, cout);
+            conv_tc_plan(L, in, out, cw->w16, k, k, stride, cw->scale, cw->bias, act, res_dev ? res_mode : 0, res_dev ? &res : nullptr, nullptr, cout, &ws);
             conv_tc_run(L, st);
             launch_unpack(out, (__half*)y_dev, st);
         }
     }
     YDST_CUDA(cudaStreamSynchronize(st));
+    YDST_API_END
+}
+
+int ydst_conv_tiling(int N, int H, int W, int cin, int cout, int k, int* block_n, int* ksplit, int* occupancy, int* ctas, double* model_us) {
+    YDST_API_BEGIN
+    YDST_CHECK(N > 0 && H > 0 && W > 0 && cin > 0 && cin % 64 == 0 && cout > 0 && (k == 1 || k == 3), "bad argument");
+    const long long P = (long long)N * (H + 2) * (W + 2);
+    const int m_tiles = (int)((P + 127) / 128);
+    const int halo = k == 3 ? W + 3 : 0;
+    int a_rows = 128 + 2 * halo;
+    const int boxes = (a_rows + 255) / 256;
+    a_rows = ((a_rows + boxes - 1) / boxes) * boxes;
+    const int cout16 = (cout + 15) & ~15;
+    const ConvTiling t = conv_tc_choose_tiling(m_tiles, cout16, k * k, cin / 64, a_rows, (size_t)48 << 20, 8192);
+    if (block_n) *block_n = t.bn;
+    if (ksplit) *ksplit = t.ksplit;
+    if (occupancy) *occupancy = t.occupancy;
+    if (ctas) *ctas = m_tiles * ((cout16 + t.bn - 1) / t.bn) * t.ksplit;
+    if (model_us) *model_us = t.model_us;
     YDST_API_END
 }
 

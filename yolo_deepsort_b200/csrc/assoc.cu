@@ -376,15 +376,17 @@ __global__ void iou_cost_kernel(const float* __restrict__ mean, const int* __res
     const int slot = idx ? idx[i] : i;
     const float* mu = mean + (long long)slot * 8;
     // Track.to_tlwh (track.py:81-94): w = a*h ; tl = centre - wh/2
-    const float th = mu[3], tw = mu[2] * th;
-    const float tx = mu[0] - tw / 2.f, ty = mu[1] - th / 2.f;
+    // every product/sum below is a separately rounded fp32 operation in the reference (torch elementwise ops), so the
+    // intrinsics keep nvcc from contracting them into FMAs: the IoU cost is bit-exact, not merely close
+    const float th = mu[3], tw = __fmul_rn(mu[2], th);
+    const float tx = __fsub_rn(mu[0], tw / 2.f), ty = __fsub_rn(mu[1], th / 2.f);
     const float* d = det_tlwh + (det_idx ? det_idx[j] : j) * 4;
     const float dx = d[0], dy = d[1], dw = d[2], dh = d[3];
     // iou (iou_matching.py:25-41): +1 on the intersection extent only
-    const float iw = fmaxf(fminf(tx + tw, dw + dx) - fmaxf(tx, dx) + 1.f, 0.f);
-    const float ih = fmaxf(fminf(ty + th, dh + dy) - fmaxf(ty, dy) + 1.f, 0.f);
-    const float inter = iw * ih;
-    float c = 1.f - inter / (tw * th + dw * dh - inter);
+    const float iw = fmaxf(__fadd_rn(__fsub_rn(fminf(__fadd_rn(tx, tw), __fadd_rn(dw, dx)), fmaxf(tx, dx)), 1.f), 0.f);
+    const float ih = fmaxf(__fadd_rn(__fsub_rn(fminf(__fadd_rn(ty, th), __fadd_rn(dh, dy)), fmaxf(ty, dy)), 1.f), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    float c = __fsub_rn(1.f, __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(tw, th), __fmul_rn(dw, dh)), inter)));
     if (tsu && tsu[i] > 1) c = kInftyCost;      // tsu is indexed by cost-matrix row
     if (c > max_dist) c = clamp_val;
     cost[e] = c;

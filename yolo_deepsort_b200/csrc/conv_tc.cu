@@ -21,6 +21,8 @@
 #include "conv_tc.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 namespace ydst {
 
@@ -32,6 +34,177 @@ struct ConvTcMaps {
     CUtensorMap b;
 };
 
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// The single MMA-issuing thread is the critical path of a batch-1 convolution (hundreds of short k-steps per CTA), so the
+// descriptors are not rebuilt per instruction: the high word (SBO, version, swizzle mode) is loop-invariant and the low word
+// (start address >> 4 | LBO) advances by plain integer adds.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t row_bytes) {
+    const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// lean wait for the hot loops (the one in common.cuh carries a printf and is kept for the epilogue)
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 28)) __trap();          // a protocol bug must abort the launch, never hang the GPU
+}
+
+__device__ __forceinline__ void trace_mark(const ConvTcParams& p, int slot) {
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        p.trace[slot] = (unsigned long long)clock64();
+        if (slot == 0 || slot == 7) {
+            unsigned long long g;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+            p.trace[8 + (slot == 7)] = g;
+        }
+    }
+    if (p.trace && slot == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.trace[10] = g;                                  // when the LAST CTA of the grid started
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue shared by both kernels.  Warps 0..3 own TMEM lanes 32w..32w+31 = output rows; a thread handles one output pixel.
+// Columns are processed in groups of up to 64: four tcgen05.ld issued back to back, one wait, then y = acc*scale + bias
+// (BN folded in fp32; scale/bias staged in shared memory), residual add before or after the activation, and one contiguous
+// 128-byte fp16 store per pixel and group (fp32 for the YOLO heads).  The residual of group g+1 is fetched while group g is
+// computed, and group 0's before the accumulator is even complete.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void act16_mish(float (&o)[16]) {
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) o[j] = apply_act(o[j], ACT_MISH);
+}
+
+// activation over 16 values with the (warp-uniform) kind test hoisted out of the element loop
+__device__ __forceinline__ void act16(float (&o)[16], int act) {
+    if (act == ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : 0.1f * o[j];
+    } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (act == ACT_MISH) {
+        act16_mish(o);
+    }
+}
+
+__device__ __forceinline__ void finish16(const ConvTcParams& p, const float (&acc)[16], int c, const float* s_scale, const float* s_bias,
+                                         const uint4& r0, const uint4& r1, long long pix) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j], s_scale[j], s_bias[j]);
+    if (p.res_mode) {
+        float rs[16];
+        const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+        const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
+            rs[2 * q] = f0.x; rs[2 * q + 1] = f0.y;
+            rs[8 + 2 * q] = f1.x; rs[8 + 2 * q + 1] = f1.y;
+        }
+        if (p.res_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += rs[j];
+        }
+        act16(o, p.act);
+        if (p.res_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += rs[j];
+        }
+    } else {
+        act16(o, p.act);
+    }
+    if (p.out_f32) {
+        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    } else {
+        uint4 w0, w1;
+        __half2* g0 = reinterpret_cast<__half2*>(&w0);
+        __half2* g1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            g0[q] = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+            g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ctot + p.out_coff + c);
+        op[0] = w0;
+        op[1] = w1;
+    }
+}
+
+__device__ __forceinline__ void load_res_group(const ConvTcParams& p, long long pix, int c0, int gw, bool valid, uint4 (&r)[8]) {
+    if (!p.res_mode || !valid) return;
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_ctot + p.res_coff + c0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q * 8 < gw && c0 + q * 8 < p.cout) r[q] = __ldg(rp + q);
+}
+
+// stage this CTA's scale/bias columns in shared memory: s_sb[0..bn) = scale, s_sb[bn..2bn) = bias (epilogue threads only)
+__device__ __forceinline__ void stage_scale_bias(const ConvTcParams& p, int n0, float* s_sb) {
+    for (int i = threadIdx.x; i < 2 * p.block_n; i += 128)
+        s_sb[i] = i < p.block_n ? __ldg(p.scale + n0 + i) : __ldg(p.bias + n0 + i - p.block_n);
+    epi_bar_sync();
+}
+
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int warp, int n0, long long pix, bool valid,
+                                              const float* s_sb, uint32_t bar_tmem) {
+    const int gw = p.block_n < 64 ? p.block_n : 64;
+    const int ngroups = p.block_n / gw;
+    uint4 rcur[8], rnext[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rcur[q] = rnext[q] = make_uint4(0, 0, 0, 0);
+    load_res_group(p, pix, n0, gw, valid, rcur);
+    mbar_wait(bar_tmem, 0);
+    tcgen05_fence_after();
+    for (int g = 0; g < ngroups; ++g) {
+        const int c0 = n0 + g * gw;
+        if (c0 >= p.cout) break;                                   // warp-uniform
+        __syncwarp();                                              // reconverge before the .sync.aligned loads
+        uint32_t v[4][16];
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub)
+            if (sub * 16 < gw && c0 + sub * 16 < p.cout)
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * gw + sub * 16), v[sub]);
+        if (g + 1 < ngroups && c0 + gw < p.cout) load_res_group(p, pix, c0 + gw, gw, valid, rnext);
+        tcgen05_wait_ld();
+        if (valid) {
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub)
+                if (sub * 16 < gw && c0 + sub * 16 < p.cout) {
+                    float acc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[sub][j]);
+                    const int cl = g * gw + sub * 16;
+                    finish16(p, acc, c0 + sub * 16, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], pix);
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tap-per-stage kernel: stride-2 convolutions (parity sub-lattice tensor maps) and channel blocks narrower than 64.
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -42,9 +215,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
     const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + (uint32_t)stages * stage_bytes;
-    // barriers: full[s] at +8s, empty[s] at +8(stages+s), tmem_full at +16*stages, tmem ptr after it
+    // barriers: full[s] at +8s, empty[s] at +8(stages+s), tmem_full at +16*stages, tmem ptr after it, then scale/bias
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * stages, bar_tmem = bar_base + 16u * stages;
     const uint32_t tmem_slot = bar_tmem + 8u;
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (bar_tmem + 16u - smem_u32(smem_raw)));
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
 
@@ -68,6 +242,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    grid_dep_launch();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -85,16 +260,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int num_kb = p.R * p.S * p.cin_blocks;
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ================= TMA producer =================
+            grid_dep_wait();
+            int s = 0, cb = 0, r = 0, sx = 0;
+            uint32_t ph = 1;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                mbar_wait_hot(bar_empty + 8u * s, ph);
                 const uint32_t full = bar_full + 8u * s;
                 mbar_arrive_expect_tx(full, a_bytes + b_bytes);
-                const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-                const int r = tap / p.S, sx = tap - r * p.S;
                 const int c0 = cb * p.block_k;
                 const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
                 if (p.mode == 0) {
@@ -105,32 +279,36 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                     tma_load_3d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1),
                                 img * p.in_Hp_half + yo0 + (Y >> 1));
                 }
-                tma_load_2d(a_dst + a_bytes, &maps.b, full, tap * p.cin + c0, n0);
+                tma_load_2d(a_dst + a_bytes, &maps.b, full, (r * p.S + sx) * p.cin + c0, n0);
+                if (++cb == p.cin_blocks) { cb = 0; if (++sx == p.S) { sx = 0; ++r; } }
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
+            const uint32_t hi = desc_hi(row_bytes);
+            const int ksteps = p.block_k >> 4;
+            int s = 0;
+            uint32_t ph = 0, acc = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(bar_full + 8u * s, ph);
+                mbar_wait_hot(bar_full + 8u * s, ph);
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-                const uint32_t b_addr = a_addr + a_bytes;
-                const int ksteps = p.block_k >> 4;
+                const uint32_t a_lo = desc_lo(smem_base + (uint32_t)s * stage_bytes);
+                const uint32_t b_lo = a_lo + (a_bytes >> 4);
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + 32u * k, row_bytes);
-                    const uint64_t db = make_smem_desc(b_addr + 32u * k, row_bytes);
-                    umma_f16(tmem_base, da, db, idesc, (uint32_t)((kb | k) != 0));
+                    umma_f16_lh(tmem_base, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
+                    acc = 1;
                 }
                 umma_commit(bar_empty + 8u * s);     // frees the smem stage once these MMAs retire
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(bar_tmem);                   // accumulator complete
         }
     } else {
-        // ================= epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31) =================
+        // ================= epilogue =================
+        stage_scale_bias(p, n0, s_sb);
         const int row = warp * 32 + lane;
         long long pix = 0;
         bool valid;
@@ -147,65 +325,215 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             valid = yo < p.Ho && xo < p.Wo;
             pix = ((long long)img * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
         }
-        mbar_wait(bar_tmem, 0);
-        tcgen05_fence_after();
-        const int nchunks = p.block_n >> 4;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int c = n0 + ch * 16;
-            if (c >= p.cout) break;                                   // warp-uniform
-            __syncwarp();                                             // reconverge before the .sync.aligned load
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), v);
-            tcgen05_wait_ld();
-            if (!valid) continue;
-            float o[16];
-            const float4* sc4 = reinterpret_cast<const float4*>(p.scale + c);
-            const float4* bi4 = reinterpret_cast<const float4*>(p.bias + c);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 sc = __ldg(sc4 + q), bi = __ldg(bi4 + q);
-                o[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, bi.x);
-                o[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, bi.y);
-                o[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, bi.z);
-                o[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, bi.w);
-            }
-            float rs[16];
-            if (p.res_mode) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_ctot + p.res_coff + c);
-                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
-                    rs[2 * q] = f0.x; rs[2 * q + 1] = f0.y;
-                    rs[8 + 2 * q] = f1.x; rs[8 + 2 * q + 1] = f1.y;
+        grid_dep_wait();
+        epilogue_tile(p, tmem_base, warp, n0, pix, valid, s_sb, bar_tmem);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo kernel (stride 1, 64-channel blocks).
+//   * the activation chunk of one channel block -- the tile's 128 padded-pixel rows plus (Wp + 1) halo rows on each
+//     side -- is fetched ONCE and all nine taps read it through row-shifted UMMA descriptors (tap (r,s) starts
+//     r*Wp + s rows into the chunk), so A traffic drops from 9x to (128 + 2Wp + 2)/128 x;
+//   * weights stream through their own ring of [block_n x 64] tiles, one per (tap, channel block);
+//   * small-M layers fill the SMs by splitting K over channel blocks (grid.z) instead of shrinking the N tile; the
+//     fp32 partials meet in a workspace and the last-arriving CTA of each tile sums them IN SPLIT ORDER (deterministic)
+//     and runs the epilogue;
+//   * griddepcontrol lets the next conv's prologue (barrier init, TMEM alloc, descriptor prefetch) overlap this one's
+//     tail when launched with programmatic stream serialization.
+// Row-shifted operand starts: measured on B200 (tests/test_gpu_conv.py under YDST_BO_MODE=0/1), the 128B-swizzle XOR is taken
+// from the absolute shared-memory address bits -- exactly what TMA used when it wrote the chunk -- so a descriptor may start on
+// any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
+// (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) trace_mark(p, 0);
+
+    const uint32_t a_stage_bytes = ((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u;
+    const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
+    const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
+    const uint32_t bar_fullA = bar_base, bar_emptyA = bar_fullA + 8u * p.a_stages;
+    const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
+    const uint32_t bar_tmem = bar_emptyB + 8u * p.b_stages;
+    const uint32_t tmem_slot = bar_tmem + 8u, flag_slot = tmem_slot + 4u;
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (bar_tmem + 16u - smem_u32(smem_raw)));
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_fullA + 8u * s, 1); mbar_init(bar_emptyA + 8u * s, 1); }
+        for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (threadIdx.x == 0) trace_mark(p, 1);
+    grid_dep_launch();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n0 = blockIdx.y * p.block_n;
+    const int p0 = blockIdx.x * kBlockM;
+    const int cb0 = blockIdx.z * p.cbs_per_split;
+    const int ncb = min(p.cbs_per_split, p.cin_blocks - cb0);
+
+    if (warp == 4) {
+        if (elect_one()) {
+            // ================= TMA producer =================
+            grid_dep_wait();                                   // the input is the previous kernel's output
+            trace_mark(p, 2);
+            const uint32_t a_tx = (uint32_t)(p.a_box_rows * p.a_boxes) * 128u;
+            int sa = 0, sb = 0;
+            uint32_t pha = 1, phb = 1;
+            auto load_a = [&](int i) {
+                mbar_wait_hot(bar_emptyA + 8u * sa, pha);
+                const uint32_t full = bar_fullA + 8u * sa;
+                mbar_arrive_expect_tx(full, a_tx);
+                const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
+                for (int b = 0; b < p.a_boxes; ++b)
+                    tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full, (cb0 + i) * 64, p0 - p.halo + b * p.a_box_rows);
+                if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+            };
+            load_a(0);
+            for (int i = 0; i < ncb; ++i) {
+                if (p.a_stages > 1 && i + 1 < ncb) load_a(i + 1);          // prefetch the next chunk ahead of this one's weights
+                int kcol = (cb0 + i) * 64;
+                for (int tap = 0; tap < p.R * p.S; ++tap, kcol += p.cin) {
+                    mbar_wait_hot(bar_emptyB + 8u * sb, phb);
+                    const uint32_t full = bar_fullB + 8u * sb;
+                    mbar_arrive_expect_tx(full, b_stage_bytes);
+                    tma_load_2d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, kcol, n0);
+                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
                 }
+                if (p.a_stages == 1 && i + 1 < ncb) load_a(i + 1);         // single buffer: only after this chunk's weights are queued
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float t = o[j];
-                if (p.res_mode == 2) t += rs[j];
-                t = apply_act(t, p.act);
-                if (p.res_mode == 1) t += rs[j];
-                o[j] = t;
-            }
-            if (p.out_f32) {
-                float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            } else {
-                uint4 w0, w1;
-                __half2* g0 = reinterpret_cast<__half2*>(&w0);
-                __half2* g1 = reinterpret_cast<__half2*>(&w1);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    g0[q] = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
-                    g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
+        }
+    } else if (warp == 5) {
+        if (elect_one()) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
+            const uint32_t hi = desc_hi(128);
+            const uint32_t row_step = (uint32_t)p.in_Wp * 8u - (uint32_t)p.S * 8u;   // descriptor units (16 B): next filter row
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0, acc = 0;
+            for (int i = 0; i < ncb; ++i) {
+                mbar_wait_hot(bar_fullA + 8u * sa, pha);
+                uint32_t a_lo = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
+                for (int r = 0; r < p.R; ++r, a_lo += row_step) {
+                    for (int sx = 0; sx < p.S; ++sx, a_lo += 8u) {
+                        mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                        tcgen05_fence_after();
+                        if (acc == 0) trace_mark(p, 3);
+                        const uint32_t b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
+                        uint32_t hi_a = hi;
+                        if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;      // base_offset probe (bits 49..51)
+                        umma_f16_lh(tmem_base, a_lo, b_lo, hi_a, idesc, acc);
+                        umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
+                        umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
+                        umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                        acc = 1u;
+                        umma_commit(bar_emptyB + 8u * sb);
+                        if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                    }
                 }
-                uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ctot + p.out_coff + c);
-                op[0] = w0;
-                op[1] = w1;
+                umma_commit(bar_emptyA + 8u * sa);
+                if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+            }
+            umma_commit(bar_tmem);
+            trace_mark(p, 4);
+        }
+    } else {
+        // ================= epilogue =================
+        stage_scale_bias(p, n0, s_sb);
+        const int row = warp * 32 + lane;
+        const long long pp = (long long)p0 + row;
+        const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
+        const int rem = (int)(pp % HpWp);
+        const int y = rem / Wp, x = rem - y * Wp;
+        const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
+        grid_dep_wait();                                       // residual / workspace / output buffers belong to earlier kernels
+        if (p.ksplit == 1) {
+            if (threadIdx.x == 0 && p.trace) { mbar_wait(bar_tmem, 0); trace_mark(p, 5); }
+            epilogue_tile(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
+            if (threadIdx.x == 0) trace_mark(p, 6);
+        } else {
+            const int bn = p.block_n;
+            const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+            float* wtile = p.ws + tile * p.ksplit * (kBlockM * bn);            // [split][row][bn] fp32
+            float* mine = wtile + ((long long)blockIdx.z * kBlockM + row) * bn;
+            mbar_wait(bar_tmem, 0);
+            tcgen05_fence_after();
+            for (int ch = 0; ch < (bn >> 4); ++ch) {
+                if (n0 + ch * 16 >= p.cout) break;
+                __syncwarp();
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), v);
+                tcgen05_wait_ld();
+                if (!valid) continue;
+                float4* dst = reinterpret_cast<float4*>(mine + ch * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                __uint_as_float(v[4 * q + 3])));
+            }
+            __threadfence();
+            epi_bar_sync();
+            if (threadIdx.x == 0) {
+                const int t = atomicAdd(p.tickets + tile, 1);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(flag_slot), "r"(t) : "memory");
+            }
+            epi_bar_sync();
+            int ticket;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ticket) : "r"(flag_slot) : "memory");
+            if (ticket == p.ksplit - 1) {                              // last arrival: every partial of this tile is visible
+                __threadfence();
+                if (threadIdx.x == 0) p.tickets[tile] = 0;             // self-reset for the next launch
+                if (valid) {
+                    const float* rowp = wtile + (long long)row * bn;
+                    for (int ch = 0; ch < (bn >> 4); ++ch) {
+                        const int c = n0 + ch * 16;
+                        if (c >= p.cout) break;
+                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                        if (p.res_mode) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pp * p.res_ctot + p.res_coff + c);
+                            r0 = __ldg(rp); r1 = __ldg(rp + 1);
+                        }
+                        float acc[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                        for (int z = 0; z < p.ksplit; ++z) {           // fixed order: the sum does not depend on arrival order
+                            const float4* src = reinterpret_cast<const float4*>(rowp + (long long)z * kBlockM * bn + ch * 16);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 t = __ldcg(src + q);
+                                acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+                            }
+                        }
+                        finish16(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
+                    }
+                }
             }
         }
     }
@@ -215,6 +543,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         __syncwarp();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+    if (threadIdx.x == 0) trace_mark(p, 7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,8 +586,67 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// Tiling model for the halo kernel.  Per-SM L2 ingest (~42 B/clk ~ 80 GB/s) and the tensor pipe (a 128 x bn x 16 MMA
+// takes ~max(32, bn/2) clocks) bound one CTA; CTAs on one SM share both.  Split-K adds a round trip through the workspace.
+ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets) {
+    const int kSms = 148;
+    const double kSmGBs = 80e3 /* bytes per us */, kClkPerUs = 1900.0, kL2BytesPerUs = 9e6, kFixedUs = 2.5;
+    const int a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
+    ConvTiling best{};
+    best.model_us = 1e30;
+    int bn_cap = 32;
+    while (bn_cap < cout16 && bn_cap < 256) bn_cap <<= 1;
+    for (int bn = bn_cap; bn >= 32; bn >>= 1) {
+        const int n_tiles = (cout16 + bn - 1) / bn;
+        int last_ks = -1;
+        for (int cps = cin_blocks; cps >= 1; --cps) {
+            const int ks = (cin_blocks + cps - 1) / cps;
+            if (ks == last_ks) continue;
+            last_ks = ks;
+            const long long tiles = (long long)m_tiles * n_tiles;
+            if (ks > 1 && ((size_t)ks * tiles * kBlockM * bn * 4 > ws_bytes || tiles > max_tickets)) continue;
+            if (ks > 16) continue;
+            const int a_stages = std::min(cps, taps == 1 ? 4 : 2);
+            const int b_stage = bn * 128;
+            const int b_loads = cps * taps;
+            const int fixed = a_stages * a_stage_bytes + 4096;   // + barriers, TMEM slot, scale/bias staging
+            if (fixed + 2 * b_stage > 200 * 1024 && b_loads > 1) continue;
+            int b_stages = std::min(8, b_loads);
+            // prefer a footprint that lets two CTAs share an SM (epilogue of one overlaps the main loop of the other)
+            int fit2 = (110 * 1024 - fixed) / b_stage, fit1 = (200 * 1024 - fixed) / b_stage;
+            if (fit2 >= std::min(4, b_loads)) b_stages = std::min(b_stages, fit2);
+            else b_stages = std::min(b_stages, std::max(1, fit1));
+            if (b_stages < 1) continue;
+            const int smem = fixed + b_stages * b_stage;
+            if (smem > 220 * 1024) continue;
+            const int occ = smem <= 112 * 1024 ? 2 : 1;
+            const long long ctas = tiles * ks;
+            const double per_sm = std::ceil((double)ctas / kSms);
+            const double rounds = std::ceil((double)ctas / (kSms * occ));
+            const double bytes = (double)cps * ((double)a_rows * 128 + (double)taps * bn * 128);
+            // one k-step = 4 MMAs of 128 x bn x 16 (~bn/2 clocks each) issued by a single thread that also polls two barriers:
+            // below ~150 clocks per step the issue loop, not the tensor pipe, is the limit
+            const double mma_clk = (double)cps * taps * std::max(150.0, 4 * std::max(32.0, bn / 2.0));
+            double t = per_sm * std::max(bytes / kSmGBs, mma_clk / kClkPerUs) + rounds * kFixedUs;
+            t = std::max(t, ctas * bytes / kL2BytesPerUs);
+            if (ks > 1) t += 1.5 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / kSmGBs;
+            if (t < best.model_us * 0.97) {                  // ties go to the earlier (larger bn, fewer splits) candidate
+                best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.a_stages = a_stages; best.b_stages = b_stages;
+                best.occupancy = occ; best.smem_bytes = smem; best.model_us = t;
+            }
+        }
+    }
+    return best;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* w_packed, int R, int S, int stride,
-                  const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real) {
+                  const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
+                  const ConvWorkspace* ws) {
     ConvTcParams& p = L.p;
     memset(&L, 0, sizeof(L));
     YDST_CHECK(in.C % 16 == 0, "conv_tc needs Cin %% 16 == 0 (got %d)", in.C);
@@ -287,6 +675,47 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
         p.mode = 0;
         p.P_total = out.pixels();
         m_tiles = (int)((p.P_total + kBlockM - 1) / kBlockM);
+        const int halo = R == 3 ? in.W + 2 + 1 : 0;
+        const int a_rows = kBlockM + 2 * halo;
+        if (p.block_k == 64 && a_rows * 128 <= 96 * 1024 && env_int("YDST_CONV_V2", 1)) {
+            // ---- halo kernel ----
+            p.v2 = 1;
+            p.halo = halo;
+            p.a_boxes = (a_rows + 255) / 256;
+            p.a_box_rows = (a_rows + p.a_boxes - 1) / p.a_boxes;
+            ConvTiling t = conv_tc_choose_tiling(m_tiles, p.cout, R * S, p.cin_blocks, p.a_box_rows * p.a_boxes, ws ? ws->partial_bytes : 0,
+                                                 ws ? ws->n_tickets : 0);
+            YDST_CHECK(t.bn >= 32, "no feasible tiling for this convolution");
+            const int force_cps = env_int("YDST_FORCE_CPS", 0);         // test hook: force a K split of the planner's tile
+            if (force_cps > 0 && ws && t.a_stages >= std::min(2, std::min(force_cps, p.cin_blocks))) {
+                const int cps = std::min(force_cps, p.cin_blocks);
+                const int ks = (p.cin_blocks + cps - 1) / cps;
+                const long long tiles = (long long)m_tiles * ((p.cout + t.bn - 1) / t.bn);
+                if ((size_t)ks * tiles * kBlockM * t.bn * 4 <= ws->partial_bytes && tiles <= ws->n_tickets) {
+                    t.cbs_per_split = cps; t.ksplit = ks; t.a_stages = std::min(t.a_stages, cps);
+                }
+            }
+            p.block_n = t.bn; p.ksplit = t.ksplit; p.cbs_per_split = t.cbs_per_split; p.a_stages = t.a_stages; p.b_stages = t.b_stages;
+            p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
+            p.bo_mode = env_int("YDST_BO_MODE", 0);
+            cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
+            cuuint64_t strides[1] = {(cuuint64_t)in.ctot * 2};
+            cuuint32_t box[2] = {64u, (cuuint32_t)p.a_box_rows};
+            encode(&L.tmA[0], in.base + in.coff, 2, dims, strides, box, 128);
+            const int K = R * S * in.C;
+            cuuint64_t bdims[2] = {(cuuint64_t)K, (cuuint64_t)p.cout};
+            cuuint64_t bstrides[1] = {(cuuint64_t)K * 2};
+            cuuint32_t bbox[2] = {64u, (cuuint32_t)t.bn};
+            encode(&L.tmB, w_packed, 2, bdims, bstrides, bbox, 128);
+            L.stages = 0;
+            L.smem_bytes = t.smem_bytes + 1024;
+            L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + t.bn - 1) / t.bn), (unsigned)t.ksplit);
+            if (getenv("YDST_DEBUG_PLAN"))
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d a_st %d b_st %d a_rows %d smem %d model %.1fus\n",
+                        R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.a_stages, t.b_stages,
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, t.model_us);
+            return;
+        }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
         cuuint64_t strides[1] = {(cuuint64_t)in.ctot * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)kBlockM};
@@ -330,8 +759,11 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
     int stages = std::max(2, std::min(8, (100 * 1024) / stage_bytes));
     stages = std::min(stages, std::max(num_kb, 1));
     L.stages = stages;
-    L.smem_bytes = stages * stage_bytes + 16 * stages + 16 + 1024;
+    L.smem_bytes = stages * stage_bytes + 16 * stages + 16 + 2048 + 1024;   // + scale/bias staging, alignment slack
     L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + bn - 1) / bn), 1);
+    if (getenv("YDST_DEBUG_PLAN"))
+        fprintf(stderr, "conv_plan k%d s%d cin %d cout %d out %dx%dx%d grid %ux%u bn %d bk %d stages %d smem %d\n", R, stride, in.C, p.cout,
+                out.N, out.H, out.W, L.grid.x, L.grid.y, bn, p.block_k, stages, L.smem_bytes);
 }
 
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
@@ -343,6 +775,41 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
     ConvTcMaps maps;
     memcpy(maps.a, L.tmA, sizeof(maps.a));
     maps.b = L.tmB;
+    if (L.p.v2) {
+        static bool attr2_set = false;
+        static int use_pdl = 1;
+        if (!attr2_set) {
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            use_pdl = env_int("YDST_PDL", 1);
+            attr2_set = true;
+        }
+        static unsigned long long* trace_dev = nullptr;
+        static int trace_on = -1;
+        if (trace_on < 0) {
+            trace_on = env_int("YDST_CONV_TRACE", 0);
+            if (trace_on) { YDST_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(unsigned long long))); }
+        }
+        ConvTcParams prm = L.p;
+        if (trace_on) { YDST_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * 8, stream)); prm.trace = trace_dev; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = L.grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+        YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, maps, prm));
+        if (trace_on) {
+            unsigned long long h[16];
+            YDST_CUDA(cudaStreamSynchronize(stream));
+            YDST_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+            auto d = [&](int a, int b) { return h[b] && h[a] ? (long long)(h[b] - h[a]) : -1LL; };
+            fprintf(stderr, "conv_trace k%d cin %d cout %d %dx%dx%d grid %ux%ux%u bn %d | setup %lld depwait %lld first_data %lld mma_issued %lld "
+                            "acc_ready %lld epilogue_done %lld exit %lld clk | cta0 %.2f us, last CTA started +%.2f us\n",
+                    L.p.R, L.p.cin, L.p.cout, L.p.N, L.p.Ho, L.p.Wo, L.grid.x, L.grid.y, L.grid.z, L.p.block_n, d(0, 1), d(0, 2), d(0, 3), d(0, 4),
+                    d(0, 5), d(0, 6), d(0, 7), (h[9] - h[8]) * 1e-3, ((long long)h[10] - (long long)h[8]) * 1e-3);
+        }
+        return;
+    }
     conv_tc_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(maps, L.p, L.stages);
     YDST_CUDA(cudaGetLastError());
 }

@@ -29,6 +29,25 @@ struct ConvTcParams {
     const __half* res; int res_ctot, res_coff;
     __half* out; int out_ctot, out_coff;
     float* out_f32;       // when non-null: write fp32 [pixels][cout] instead of fp16 (YOLO head convs)
+    // --- halo kernel (conv_tc2_kernel: stride 1, 64-channel blocks) ---
+    int v2;               // 1: the A chunk (128 output rows + halo) is loaded ONCE per channel block and all taps read it
+    int ksplit;           // K split over channel blocks (grid.z); partial sums meet in `ws`
+    int cbs_per_split;    // channel blocks per split
+    int halo;             // chunk rows before the tile's first pixel (3x3: Wp + 1, 1x1: 0)
+    int a_box_rows, a_boxes;   // the chunk is fetched as a_boxes TMA boxes of a_box_rows rows
+    int a_stages, b_stages;
+    float* ws;            // split-K partials [tile][split][chunk][128][16] fp32
+    int* tickets;         // per output tile arrival counter (self-resetting)
+    unsigned long long* trace;   // debug: CTA (0,0,0) records clock64 at its pipeline milestones (YDST_CONV_TRACE=1)
+    int bo_mode;          // UMMA descriptor base-offset mode for row-shifted starts (validated on hardware)
+};
+
+// split-K scratch shared by all convs of one owner (Detector / Reid): kernels of one owner run on one stream, in order
+struct ConvWorkspace {
+    float* partial = nullptr;
+    size_t partial_bytes = 0;
+    int* tickets = nullptr;
+    int n_tickets = 0;
 };
 
 struct ConvTcLaunch {
@@ -42,7 +61,11 @@ struct ConvTcLaunch {
 
 // Host: encode tensor maps + pick tiling.  `w_packed` is fp16 [cout16][R*S*cin] (K-major).
 void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* w_packed, int R, int S, int stride,
-                  const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real);
+                  const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
+                  const ConvWorkspace* ws = nullptr);
+// the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
+struct ConvTiling { int bn, ksplit, cbs_per_split, a_stages, b_stages, occupancy, smem_bytes; double model_us; };
+ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets);
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
 double conv_tc_flops(const ConvTcLaunch& L);   // useful 2*M*N*K (logical, unpadded)
 

@@ -36,6 +36,15 @@ Act make_act(DeviceArena& arena, int N, int H, int W, int C) {
     return a;
 }
 
+ConvWorkspace make_conv_workspace(DeviceArena& arena, size_t partial_bytes, int n_tickets) {
+    ConvWorkspace w;
+    w.partial = (float*)arena.alloc(partial_bytes, false);
+    w.partial_bytes = partial_bytes;
+    w.tickets = (int*)arena.alloc(sizeof(int) * n_tickets, true);
+    w.n_tickets = n_tickets;
+    return w;
+}
+
 std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w, int cout, int cin, int k, const float* gamma,
                                        const float* beta, const float* mean, const float* var, const float* conv_bias, bool first_layer) {
     auto cw = std::make_unique<ConvWeights>();
@@ -135,6 +144,7 @@ Detector::Detector(const ydst_layer_desc* layers, int n, const float* weights, s
 
 void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size_t n_weights) {
     in_f32_ = (float*)arena_.alloc((size_t)batch * H * W * 3 * sizeof(float));
+    ws_ = make_conv_workspace(arena_);
     // readers of each layer's output
     std::vector<std::vector<int>> readers(n);
     for (int l = 0; l < n; ++l) {
@@ -237,7 +247,7 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
                     geo.N = batch; geo.H = shp[l].H; geo.W = shp[l].W; geo.C = d.filters; geo.ctot = cw->cout16; geo.coff = 0;
                     op.kind = OP_CONV_TC;
                     conv_tc_plan(op.conv, out[l - 1], geo, cw->w16, d.size, d.size, d.stride, cw->scale, cw->bias, d.activation, 0, nullptr,
-                                 head_f32[l], d.filters);
+                                 head_f32[l], d.filters, &ws_);
                     out[l] = geo;
                 } else {
                     out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
@@ -251,7 +261,7 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
                         const Act* res = nullptr;
                         if (fuse_sc) { res = &out[L[l + 1].src[0]]; fused_away[l + 1] = true; }
                         conv_tc_plan(op.conv, out[l - 1], out[l], cw->w16, d.size, d.size, d.stride, cw->scale, cw->bias, d.activation,
-                                     fuse_sc ? 1 : 0, res, nullptr, d.filters);
+                                     fuse_sc ? 1 : 0, res, nullptr, d.filters, &ws_);
                     }
                 }
                 if (op.kind == OP_CONV_TC) plan.flops += conv_tc_flops(op.conv) * ((double)d.filters / op.conv.p.cout);
@@ -390,6 +400,7 @@ Reid::Reid(const float* weights, size_t n_weights, int max_batch_) : max_batch(m
     in_f32_ = (float*)arena_.alloc((size_t)max_batch * 128 * 64 * 3 * sizeof(float));
     feat_ = (float*)arena_.alloc((size_t)max_batch * 512 * sizeof(float));
     err_flag = (int*)arena_.alloc(sizeof(int));
+    ws_ = make_conv_workspace(arena_);
     bufs_.push_back(make_act(arena_, max_batch, 128, 64, 64));          // 0: stem out
     int h = 64, w = 32;
     for (int s = 0; s < 4; ++s) {
@@ -428,17 +439,17 @@ const Plan& Reid::plan_for(int m) {
             Act y = (x.base == A.base) ? B : A;
             if (s > 0 && blk == 0) y = A;                                // x lives in the previous stage's buffers
             Op c1; c1.kind = OP_CONV_TC;
-            conv_tc_plan(c1.conv, x, T, w1->w16, 3, 3, down ? 2 : 1, w1->scale, w1->bias, ACT_RELU, 0, nullptr, nullptr, w1->cout);
+            conv_tc_plan(c1.conv, x, T, w1->w16, 3, 3, down ? 2 : 1, w1->scale, w1->bias, ACT_RELU, 0, nullptr, nullptr, w1->cout, &ws_);
             plan.ops.push_back(c1); plan.flops += conv_tc_flops(c1.conv);
             Act res = x;
             if (down) {
                 Op cd; cd.kind = OP_CONV_TC;
-                conv_tc_plan(cd.conv, x, D, wd->w16, 1, 1, 2, wd->scale, wd->bias, ACT_LINEAR, 0, nullptr, nullptr, wd->cout);
+                conv_tc_plan(cd.conv, x, D, wd->w16, 1, 1, 2, wd->scale, wd->bias, ACT_LINEAR, 0, nullptr, nullptr, wd->cout, &ws_);
                 plan.ops.push_back(cd); plan.flops += conv_tc_flops(cd.conv);
                 res = D;
             }
             Op c2; c2.kind = OP_CONV_TC;
-            conv_tc_plan(c2.conv, T, y, w2->w16, 3, 3, 1, w2->scale, w2->bias, ACT_RELU, 2, &res, nullptr, w2->cout);
+            conv_tc_plan(c2.conv, T, y, w2->w16, 3, 3, 1, w2->scale, w2->bias, ACT_RELU, 2, &res, nullptr, w2->cout, &ws_);
             plan.ops.push_back(c2); plan.flops += conv_tc_flops(c2.conv);
             x = y;
         }

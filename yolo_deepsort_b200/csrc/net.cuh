@@ -74,6 +74,7 @@ private:
     std::vector<float*> head_f32_;    // fp32 buffers of the yolo head convs
     void build(const ydst_layer_desc* layers, int n, const float* weights, size_t n_weights);
     DeviceArena arena_;
+    ConvWorkspace ws_;
     std::vector<std::unique_ptr<ConvWeights>> weights_;
     float* in_f32_ = nullptr;    // [batch][H][W][3]
 };
@@ -88,6 +89,7 @@ public:
 private:
     const Plan& plan_for(int m);
     DeviceArena arena_;
+    ConvWorkspace ws_;
     std::vector<std::unique_ptr<ConvWeights>> weights_;
     std::map<int, Plan> plans_;
     float* in_f32_ = nullptr;    // [max_batch][128][64][3]
@@ -99,5 +101,7 @@ private:
 std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w_oihw, int cout, int cin, int k, const float* gamma,
                                        const float* beta, const float* mean, const float* var, const float* conv_bias, bool first_layer);
 Act make_act(DeviceArena& arena, int N, int H, int W, int C);
+// split-K scratch for one owner's convolutions (zeroed tickets; see conv_tc.cuh)
+ConvWorkspace make_conv_workspace(DeviceArena& arena, size_t partial_bytes = (size_t)48 << 20, int n_tickets = 8192);
 
 }  // namespace ydst
