@@ -180,6 +180,34 @@ def profile_ops(pipe, frames_dev, t0, n=4):
     return kind[:k], layer[:k], flops[:k], nbytes[:k], ms[:k].astype(np.float64), n
 
 
+def stage_times(model, ds, frames_dev, dets, device, reps=20):
+    """Untimed-leg breakdown: ms per call of the detector forward, NMS, and ReID extraction (same boxes as the last frame),
+    each looped back to back on the stream between two CUDA events.  The tracker's share is the step time minus these."""
+    import torch
+    from yolo_deepsort_b200._lib import check, lib, ptr, stream_ptr
+    L = lib()
+    h = model.handle(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) / reps, 4)
+
+    out["detector_forward"] = timed(lambda: check(L.ydst_detector_forward_u8(h, ptr(frames_dev[0]), None, stream_ptr())))
+    dd = torch.zeros((300, 6), device=device); nn = torch.zeros(1, dtype=torch.int32, device=device)
+    out["nms"] = timed(lambda: check(L.ydst_detector_nms(h, 0.5, 0.4, ptr(dd), ptr(nn), stream_ptr())))
+    if dets is not None and len(dets):
+        d = torch.from_numpy(dets[:, :4].copy()).to(device)
+        tlwh = torch.stack([d[:, 0], d[:, 1], d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]], 1).contiguous()
+        out["reid_extract_m%d" % len(dets)] = timed(lambda: ds.extractor.extract(frames_dev[0], tlwh))
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -280,6 +308,7 @@ def run_ours(args):
             "share_of_step": round(conv_ms / (worst_ms / K), 4),
             "hbm_frac_conv": round(float(nbytes[conv].sum()) / nprof / (conv_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), 4) if conv_ms > 0 else None}
 
+    stages = stage_times(model, ds, dev, dets, device)
     out = {"metric": METRIC, "value": round(fps, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
            "ms_per_step": round(worst_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "fp16", "data": "synthetic",
@@ -291,7 +320,7 @@ def run_ours(args):
                       "parallelism": f"{world} independent streams (no data-path collective)"},
            "e2e": {"value": round(fps_e2e, 2), "unit": UNIT, "ms_per_step": round(worst_e2e / K, 4),
                    "h2d_bytes_per_step": int(SIZE * SIZE * 3), "d2h_bytes_per_step": int(d2h // K)},
-           "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof}
+           "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "stage_ms": stages}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(args.cpu_frames, 2)

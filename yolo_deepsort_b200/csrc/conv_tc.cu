@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 namespace ydst {
 
@@ -104,9 +105,8 @@ __device__ __forceinline__ void act16(float (&o)[16], int act) {
     }
 }
 
-__device__ __forceinline__ void finish16(const ConvTcParams& p, const float (&acc)[16], int c, const float* s_scale, const float* s_bias,
-                                         const uint4& r0, const uint4& r1, long long pix) {
-    float o[16];
+__device__ __forceinline__ void compute16(const ConvTcParams& p, const float (&acc)[16], const float* s_scale, const float* s_bias,
+                                          const uint4& r0, const uint4& r1, float (&o)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j], s_scale[j], s_bias[j]);
     if (p.res_mode) {
@@ -131,19 +131,27 @@ __device__ __forceinline__ void finish16(const ConvTcParams& p, const float (&ac
     } else {
         act16(o, p.act);
     }
+}
+__device__ __forceinline__ void pack16(const float (&o)[16], uint4& w0, uint4& w1) {
+    __half2* g0 = reinterpret_cast<__half2*>(&w0);
+    __half2* g1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        g0[q] = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+        g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
+    }
+}
+__device__ __forceinline__ void finish16(const ConvTcParams& p, const float (&acc)[16], int c, const float* s_scale, const float* s_bias,
+                                         const uint4& r0, const uint4& r1, long long pix) {
+    float o[16];
+    compute16(p, acc, s_scale, s_bias, r0, r1, o);
     if (p.out_f32) {
         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c);
 #pragma unroll
         for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     } else {
         uint4 w0, w1;
-        __half2* g0 = reinterpret_cast<__half2*>(&w0);
-        __half2* g1 = reinterpret_cast<__half2*>(&w1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            g0[q] = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
-            g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
-        }
+        pack16(o, w0, w1);
         uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ctot + p.out_coff + c);
         op[0] = w0;
         op[1] = w1;
@@ -200,6 +208,66 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
     }
+}
+
+// TMA-store variant (halo kernel, cout % 64 == 0, fp16 output): every thread-per-row global store of the direct epilogue
+// touches its own 128-byte line (32 lines per warp instruction), which costs ~2000 clocks per 64-column group in the LSU.
+// Here each 64-column group is written to a 128B-swizzled [128 rows][64 cols] staging tile in shared memory (the operand
+// stages are dead by then) and one elected thread hands it to the TMA store unit.  Invalid rows (border pixels) are written
+// as zeros, which is what the border already holds; rows past the end of the tensor are clipped by TMA.
+__device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* out_map, uint32_t stage_smem, uint32_t tmem_base,
+                                                  int warp, int n0, int p0, long long pix, bool valid, const float* s_sb, uint32_t bar_tmem) {
+    const int ngroups = p.block_n >> 6;
+    const int row = threadIdx.x;                                   // 0..127
+    uint4 rcur[8], rnext[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rcur[q] = rnext[q] = make_uint4(0, 0, 0, 0);
+    load_res_group(p, pix, n0, 64, valid, rcur);
+    mbar_wait(bar_tmem, 0);
+    tcgen05_fence_after();
+    for (int g = 0; g < ngroups; ++g) {
+        const int c0 = n0 + g * 64;
+        if (c0 >= p.cout) break;
+        __syncwarp();
+        uint32_t v[4][16];
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub)
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 64 + sub * 16), v[sub]);
+        if (g + 1 < ngroups && c0 + 64 < p.cout) load_res_group(p, pix, c0 + 64, 64, valid, rnext);
+        if (g >= 2) {                                              // the buffer about to be refilled was read by store g-2
+            if (threadIdx.x == 0) tma_store_wait_read<1>();
+            epi_bar_sync();
+        }
+        tcgen05_wait_ld();
+        const uint32_t buf = stage_smem + (uint32_t)(g & 1) * (kBlockM * 128u);
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+            if (valid) {
+                float acc[16], o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[sub][j]);
+                const int cl = g * 64 + sub * 16;
+                compute16(p, acc, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], o);
+                pack16(o, w0, w1);
+            }
+            const uint32_t rbase = buf + (uint32_t)row * 128u;
+            const uint32_t x = (uint32_t)(row & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((((uint32_t)(2 * sub)) ^ x) << 4)), "r"(w0.x), "r"(w0.y),
+                         "r"(w0.z), "r"(w0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((((uint32_t)(2 * sub + 1)) ^ x) << 4)), "r"(w1.x), "r"(w1.y),
+                         "r"(w1.z), "r"(w1.w) : "memory");
+        }
+        fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (threadIdx.x == 0) {
+            tma_store_2d(out_map, buf, p.out_coff + c0, p0);
+            tma_store_commit();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+    }
+    if (threadIdx.x == 0) tma_store_wait_read<0>();                // smem must outlive the bulk reads; the writes are complete at grid end
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,14 +420,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
 // (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
+__global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) trace_mark(p, 0);
 
-    const uint32_t a_stage_bytes = ((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u;
-    const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+    const bool k3 = p.R == 3;
+    // A stage: 3x3 -> one halo chunk (a_boxes x a_box_rows rows of 128 B); 1x1 -> tpb tiles of 128 rows
+    const uint32_t a_stage_bytes = k3 ? (((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u) : (uint32_t)p.tpb * (kBlockM * 128u);
+    const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+    const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
@@ -378,9 +449,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constan
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 4 && lane == 0) {
+    if (warp == 4 && elect_one()) {
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
+        if (p.store_tma) tma_prefetch_desc(&maps.a[1]);
     }
     if (warp == 5) {
         tmem_alloc(tmem_slot, tmem_cols);
@@ -398,36 +470,52 @@ __global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constan
     const int p0 = blockIdx.x * kBlockM;
     const int cb0 = blockIdx.z * p.cbs_per_split;
     const int ncb = min(p.cbs_per_split, p.cin_blocks - cb0);
+    // macro step = one A stage: a channel block with all its taps (3x3) or a group of tpb channel blocks (1x1)
+    const int nmacro = k3 ? ncb : (ncb + p.tpb - 1) / p.tpb;
+    const int nbs = k3 ? 9 / p.tpb : 1;                        // weight stages per macro step
 
     if (warp == 4) {
         if (elect_one()) {
             // ================= TMA producer =================
-            grid_dep_wait();                                   // the input is the previous kernel's output
-            trace_mark(p, 2);
-            const uint32_t a_tx = (uint32_t)(p.a_box_rows * p.a_boxes) * 128u;
             int sa = 0, sb = 0;
             uint32_t pha = 1, phb = 1;
+            int jm = 0, js = 0;                                // next weight stage to issue: macro step jm, sub-stage js
+            const int total_b = nmacro * nbs;
+            auto issue_b = [&]() {
+                mbar_wait_hot(bar_emptyB + 8u * sb, phb);
+                const uint32_t full = bar_fullB + 8u * sb;
+                mbar_arrive_expect_tx(full, b_stage_bytes);
+                if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * p.tpb);
+                else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * p.tpb);
+                if (++js == nbs) { js = 0; ++jm; }
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+            };
             auto load_a = [&](int i) {
                 mbar_wait_hot(bar_emptyA + 8u * sa, pha);
                 const uint32_t full = bar_fullA + 8u * sa;
-                mbar_arrive_expect_tx(full, a_tx);
                 const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
-                for (int b = 0; b < p.a_boxes; ++b)
-                    tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full, (cb0 + i) * 64, p0 - p.halo + b * p.a_box_rows);
+                if (k3) {
+                    mbar_arrive_expect_tx(full, (uint32_t)(p.a_box_rows * p.a_boxes) * 128u);
+                    for (int b = 0; b < p.a_boxes; ++b)
+                        tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full, (cb0 + i) * 64, p0 - p.halo + b * p.a_box_rows);
+                } else {
+                    mbar_arrive_expect_tx(full, a_stage_bytes);
+                    tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * p.tpb);
+                }
                 if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
             };
+            // weights never depend on the previous kernel: queue them before waiting on the grid dependency, so that under
+            // programmatic dependent launch they stream in while the producer of our input is still draining
+            int issued = 0;
+            const int pre = p.pdl ? p.b_stages : 1;            // without an overlapping predecessor, get the first chunk moving early
+            for (; issued < total_b && issued < pre; ++issued) issue_b();
+            grid_dep_wait();                                   // the activations are the previous kernel's output
+            trace_mark(p, 2);
             load_a(0);
-            for (int i = 0; i < ncb; ++i) {
-                if (p.a_stages > 1 && i + 1 < ncb) load_a(i + 1);          // prefetch the next chunk ahead of this one's weights
-                int kcol = (cb0 + i) * 64;
-                for (int tap = 0; tap < p.R * p.S; ++tap, kcol += p.cin) {
-                    mbar_wait_hot(bar_emptyB + 8u * sb, phb);
-                    const uint32_t full = bar_fullB + 8u * sb;
-                    mbar_arrive_expect_tx(full, b_stage_bytes);
-                    tma_load_2d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, kcol, n0);
-                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
-                }
-                if (p.a_stages == 1 && i + 1 < ncb) load_a(i + 1);         // single buffer: only after this chunk's weights are queued
+            for (int i = 0; i < nmacro; ++i) {
+                if (p.a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
+                for (; issued < (i + 1) * nbs; ++issued) issue_b();
+                if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
             }
         }
     } else if (warp == 5) {
@@ -435,28 +523,55 @@ __global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constan
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
             const uint32_t hi = desc_hi(128);
-            const uint32_t row_step = (uint32_t)p.in_Wp * 8u - (uint32_t)p.S * 8u;   // descriptor units (16 B): next filter row
+            const uint32_t b_tile16 = b_tile_bytes >> 4;
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0, acc = 0;
-            for (int i = 0; i < ncb; ++i) {
+            for (int i = 0; i < nmacro; ++i) {
                 mbar_wait_hot(bar_fullA + 8u * sa, pha);
-                uint32_t a_lo = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
-                for (int r = 0; r < p.R; ++r, a_lo += row_step) {
-                    for (int sx = 0; sx < p.S; ++sx, a_lo += 8u) {
-                        mbar_wait_hot(bar_fullB + 8u * sb, phb);
-                        tcgen05_fence_after();
-                        if (acc == 0) trace_mark(p, 3);
-                        const uint32_t b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
-                        uint32_t hi_a = hi;
-                        if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;      // base_offset probe (bits 49..51)
-                        umma_f16_lh(tmem_base, a_lo, b_lo, hi_a, idesc, acc);
-                        umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
-                        umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
-                        umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
-                        acc = 1u;
-                        umma_commit(bar_emptyB + 8u * sb);
-                        if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
+                if (k3) {
+                    const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;        // 16-byte units: next filter row
+                    uint32_t a_lo = a_lo0;
+                    int t_in = 0;
+                    uint32_t b_lo = 0;
+                    for (int r = 0; r < 3; ++r, a_lo += row_step) {
+                        for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
+                            if (t_in == 0) {
+                                mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                                tcgen05_fence_after();
+                                if (acc == 0) trace_mark(p, 3);
+                                b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
+                            }
+                            uint32_t hi_a = hi;
+                            if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
+                            umma_f16_lh(tmem_base, a_lo, b_lo, hi_a, idesc, acc);
+                            umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
+                            umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
+                            umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                            acc = 1u;
+                            b_lo += b_tile16;
+                            if (++t_in == p.tpb) {
+                                t_in = 0;
+                                umma_commit(bar_emptyB + 8u * sb);
+                                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                            }
+                        }
                     }
+                } else {
+                    mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                    tcgen05_fence_after();
+                    if (acc == 0) trace_mark(p, 3);
+                    uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
+                    const int nsl = min(p.tpb, ncb - i * p.tpb);                  // the last group of a split may be short
+                    for (int t = 0; t < nsl; ++t, a_lo += (kBlockM * 128u) >> 4, b_lo += b_tile16) {
+                        umma_f16_lh(tmem_base, a_lo, b_lo, hi, idesc, acc);
+                        umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi, idesc, 1u);
+                        umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi, idesc, 1u);
+                        umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi, idesc, 1u);
+                        acc = 1u;
+                    }
+                    umma_commit(bar_emptyB + 8u * sb);
+                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
                 }
                 umma_commit(bar_emptyA + 8u * sa);
                 if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
@@ -467,7 +582,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constan
     } else {
         // ================= epilogue =================
         stage_scale_bias(p, n0, s_sb);
-        const int row = warp * 32 + lane;
+        const int row = threadIdx.x;
         const long long pp = (long long)p0 + row;
         const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
         const int rem = (int)(pp % HpWp);
@@ -476,7 +591,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc2_kernel(const __grid_constan
         grid_dep_wait();                                       // residual / workspace / output buffers belong to earlier kernels
         if (p.ksplit == 1) {
             if (threadIdx.x == 0 && p.trace) { mbar_wait(bar_tmem, 0); trace_mark(p, 5); }
-            epilogue_tile(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
+            if (p.store_tma) epilogue_tile_tma(p, &maps.a[1], smem_base, tmem_base, warp, n0, p0, pp, valid, s_sb, bar_tmem);
+            else epilogue_tile(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
             if (threadIdx.x == 0) trace_mark(p, 6);
         } else {
             const int bn = p.block_n;
@@ -586,63 +702,80 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// Tiling model for the halo kernel.  Per-SM L2 ingest (~42 B/clk ~ 80 GB/s) and the tensor pipe (a 128 x bn x 16 MMA
-// takes ~max(32, bn/2) clocks) bound one CTA; CTAs on one SM share both.  Split-K adds a round trip through the workspace.
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// Tiling model for the halo kernel (clocks at ~1.9 GHz; constants measured with YDST_CONV_TRACE on B200).
+// A CTA costs  setup (~900) + first-data latency (~2200) + main loop + epilogue,  where the main loop is the slowest of
+//   * operand bytes / fill rate -- an SM ingests ~42 B/clk from L2, and no more than (bytes in flight) / (~2100 clk latency);
+//   * tensor time: a 128 x bn x 16 MMA takes ~max(16, bn/2) clocks;
+//   * barrier round trips of the single issuing thread (~150 clocks per stage).
+// Small-M layers may split K over channel blocks (grid.z); the fp32 partials then take a round trip through the workspace.
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets) {
     const int kSms = 148;
-    const double kSmGBs = 80e3 /* bytes per us */, kClkPerUs = 1900.0, kL2BytesPerUs = 9e6, kFixedUs = 2.5;
-    const int a_stage_bytes = (a_rows * 128 + 1023) & ~1023;
+    const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 150.0, kClkPerUs = 1900.0;
+    const int chunk_bytes = (a_rows * 128 + 1023) & ~1023;
+    const bool tma_store_ok = cout16 % 64 == 0;
     ConvTiling best{};
     best.model_us = 1e30;
     int bn_cap = 32;
     while (bn_cap < cout16 && bn_cap < 256) bn_cap <<= 1;
     for (int bn = bn_cap; bn >= 32; bn >>= 1) {
         const int n_tiles = (cout16 + bn - 1) / bn;
+        const long long tiles = (long long)m_tiles * n_tiles;
         int last_ks = -1;
         for (int cps = cin_blocks; cps >= 1; --cps) {
             const int ks = (cin_blocks + cps - 1) / cps;
             if (ks == last_ks) continue;
             last_ks = ks;
-            const long long tiles = (long long)m_tiles * n_tiles;
             if (ks > 1 && ((size_t)ks * tiles * kBlockM * bn * 4 > ws_bytes || tiles > max_tickets)) continue;
             if (ks > 16) continue;
-            const int a_stages = std::min(cps, taps == 1 ? 4 : 2);
-            const int b_stage = bn * 128;
-            const int b_loads = cps * taps;
-            const int fixed = a_stages * a_stage_bytes + 4096;   // + barriers, TMEM slot, scale/bias staging
-            if (fixed + 2 * b_stage > 200 * 1024 && b_loads > 1) continue;
-            int b_stages = std::min(8, b_loads);
-            // prefer a footprint that lets two CTAs share an SM (epilogue of one overlaps the main loop of the other)
-            int fit2 = (110 * 1024 - fixed) / b_stage, fit1 = (200 * 1024 - fixed) / b_stage;
-            if (fit2 >= std::min(4, b_loads)) b_stages = std::min(b_stages, fit2);
-            else b_stages = std::min(b_stages, std::max(1, fit1));
-            if (b_stages < 1) continue;
-            const int smem = fixed + b_stages * b_stage;
-            if (smem > 220 * 1024) continue;
-            const int occ = smem <= 112 * 1024 ? 2 : 1;
             const long long ctas = tiles * ks;
-            const double per_sm = std::ceil((double)ctas / kSms);
-            const double rounds = std::ceil((double)ctas / (kSms * occ));
-            const double bytes = (double)cps * ((double)a_rows * 128 + (double)taps * bn * 128);
-            // one k-step = 4 MMAs of 128 x bn x 16 (~bn/2 clocks each) issued by a single thread that also polls two barriers:
-            // below ~150 clocks per step the issue loop, not the tensor pipe, is the limit
-            const double mma_clk = (double)cps * taps * std::max(150.0, 4 * std::max(32.0, bn / 2.0));
-            double t = per_sm * std::max(bytes / kSmGBs, mma_clk / kClkPerUs) + rounds * kFixedUs;
-            t = std::max(t, ctas * bytes / kL2BytesPerUs);
-            if (ks > 1) t += 1.5 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / kSmGBs;
-            if (t < best.model_us * 0.97) {                  // ties go to the earlier (larger bn, fewer splits) candidate
-                best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.a_stages = a_stages; best.b_stages = b_stages;
-                best.occupancy = occ; best.smem_bytes = smem; best.model_us = t;
+            const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = 108 * 1024;
+            const int tpb_opts3[3] = {9, 3, 1}, tpb_opts1[3] = {4, 2, 1};
+            for (int oi = 0; oi < 3; ++oi) {
+                const int tpb = taps == 9 ? tpb_opts3[oi] : tpb_opts1[oi];
+                if (taps == 1 && tpb > cps) continue;
+                const int nmacro = taps == 9 ? cps : (cps + tpb - 1) / tpb;
+                const int nbs = taps == 9 ? 9 / tpb : 1;
+                const int total_b = nmacro * nbs;
+                const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * 128;
+                const int b_stage = tpb * bn * 128;
+                const int a_stages = std::min(nmacro, taps == 9 ? 2 : 4);
+                const int fixed = a_stages * a_stage + 4096;
+                for (int pass = 0; pass < 2; ++pass) {           // pass 0: leave room for a second CTA on the SM; pass 1: whole SM
+                    const int budget = pass == 0 ? budget_2 : budget_max;
+                    if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
+                    int b_stages = std::min(std::min(8, total_b), (budget - fixed) / b_stage);
+                    if (b_stages < std::min(2, total_b)) continue;
+                    int smem = fixed + b_stages * b_stage;
+                    smem = std::max(smem, 36 * 1024);             // the TMA-store epilogue stages two 16 KB groups at the start of smem
+                    const int occ = smem <= 112 * 1024 ? 2 : 1;
+                    const double inflight = (double)a_stages * a_stage + (double)b_stages * b_stage;
+                    const double rate = std::min(kFill, inflight / kLat);
+                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * 128.0) + (double)taps * bn * 128);
+                    const double mma = (double)cps * taps * 4 * std::max(16.0, bn / 2.0);
+                    const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
+                    const double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
+                    const bool st = tma_store_ok && bn >= 64 && ks == 1;
+                    const double epi = 700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0);
+                    const double per_sm = std::ceil((double)ctas / kSms);
+                    double t = kSetup + kFirst + per_sm * main_clk + std::ceil(per_sm / occ) * epi;
+                    if (ks > 1) t += 1500.0 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / 30.0;
+                    t /= kClkPerUs;
+                    if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
+                        best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_stages;
+                        best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t;
+                    }
+                }
             }
         }
     }
     return best;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* w_packed, int R, int S, int stride,
                   const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
@@ -687,33 +820,56 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                                                  ws ? ws->n_tickets : 0);
             YDST_CHECK(t.bn >= 32, "no feasible tiling for this convolution");
             const int force_cps = env_int("YDST_FORCE_CPS", 0);         // test hook: force a K split of the planner's tile
-            if (force_cps > 0 && ws && t.a_stages >= std::min(2, std::min(force_cps, p.cin_blocks))) {
+            if (force_cps > 0 && ws) {
                 const int cps = std::min(force_cps, p.cin_blocks);
                 const int ks = (p.cin_blocks + cps - 1) / cps;
                 const long long tiles = (long long)m_tiles * ((p.cout + t.bn - 1) / t.bn);
                 if ((size_t)ks * tiles * kBlockM * t.bn * 4 <= ws->partial_bytes && tiles <= ws->n_tickets) {
-                    t.cbs_per_split = cps; t.ksplit = ks; t.a_stages = std::min(t.a_stages, cps);
+                    t.cbs_per_split = cps; t.ksplit = ks;
+                    if (R == 1) t.tpb = std::min(t.tpb, cps);
+                    const int nmacro = R == 3 ? cps : (cps + t.tpb - 1) / t.tpb;
+                    t.a_stages = std::min(t.a_stages, nmacro);
+                    t.b_stages = std::min(t.b_stages, nmacro * (R == 3 ? 9 / t.tpb : 1));
                 }
             }
             p.block_n = t.bn; p.ksplit = t.ksplit; p.cbs_per_split = t.cbs_per_split; p.a_stages = t.a_stages; p.b_stages = t.b_stages;
+            p.tpb = t.tpb;
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
-            cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
-            cuuint64_t strides[1] = {(cuuint64_t)in.ctot * 2};
-            cuuint32_t box[2] = {64u, (cuuint32_t)p.a_box_rows};
-            encode(&L.tmA[0], in.base + in.coff, 2, dims, strides, box, 128);
+            p.store_tma = (!out_f32 && p.cout % 64 == 0 && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
             const int K = R * S * in.C;
-            cuuint64_t bdims[2] = {(cuuint64_t)K, (cuuint64_t)p.cout};
-            cuuint64_t bstrides[1] = {(cuuint64_t)K * 2};
-            cuuint32_t bbox[2] = {64u, (cuuint32_t)t.bn};
-            encode(&L.tmB, w_packed, 2, bdims, bstrides, bbox, 128);
+            if (R == 3) {
+                cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
+                cuuint64_t strides[1] = {(cuuint64_t)in.ctot * 2};
+                cuuint32_t box[2] = {64u, (cuuint32_t)p.a_box_rows};
+                encode(&L.tmA[0], in.base + in.coff, 2, dims, strides, box, 128);
+                cuuint64_t bdims[3] = {(cuuint64_t)in.C, (cuuint64_t)p.cout, 9};
+                cuuint64_t bstrides[2] = {(cuuint64_t)K * 2, (cuuint64_t)in.C * 2};
+                cuuint32_t bbox[3] = {64u, (cuuint32_t)t.bn, (cuuint32_t)t.tpb};
+                encode(&L.tmB, w_packed, 3, bdims, bstrides, bbox, 128);
+            } else {
+                cuuint64_t dims[3] = {64, (cuuint64_t)p.P_total, (cuuint64_t)p.cin_blocks};
+                cuuint64_t strides[2] = {(cuuint64_t)in.ctot * 2, 128};
+                cuuint32_t box[3] = {64u, (cuuint32_t)kBlockM, (cuuint32_t)t.tpb};
+                encode(&L.tmA[0], in.base + in.coff, 3, dims, strides, box, 128);
+                cuuint64_t bdims[3] = {64, (cuuint64_t)p.cout, (cuuint64_t)p.cin_blocks};
+                cuuint64_t bstrides[2] = {(cuuint64_t)K * 2, 128};
+                cuuint32_t bbox[3] = {64u, (cuuint32_t)t.bn, (cuuint32_t)t.tpb};
+                encode(&L.tmB, w_packed, 3, bdims, bstrides, bbox, 128);
+            }
+            if (p.store_tma) {
+                cuuint64_t dims[2] = {(cuuint64_t)out.ctot, (cuuint64_t)p.P_total};
+                cuuint64_t strides[1] = {(cuuint64_t)out.ctot * 2};
+                cuuint32_t box[2] = {64u, (cuuint32_t)kBlockM};
+                encode(&L.tmA[1], out.base, 2, dims, strides, box, 128);
+            }
             L.stages = 0;
             L.smem_bytes = t.smem_bytes + 1024;
             L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + t.bn - 1) / t.bn), (unsigned)t.ksplit);
             if (getenv("YDST_DEBUG_PLAN"))
-                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d a_st %d b_st %d a_rows %d smem %d model %.1fus\n",
-                        R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.a_stages, t.b_stages,
-                        p.a_box_rows * p.a_boxes, L.smem_bytes, t.model_us);
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d model %.1fus\n",
+                        R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.tpb, t.a_stages, t.b_stages,
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, t.model_us);
             return;
         }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -766,6 +922,30 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 out.N, out.H, out.W, L.grid.x, L.grid.y, bn, p.block_k, stages, L.smem_bytes);
 }
 
+static constexpr int kTraceSlots = 1024;
+static int g_trace_on = -1, g_trace_next = 0;
+static unsigned long long* g_trace_dev = nullptr;
+static int g_trace_desc[kTraceSlots], g_trace_shape[kTraceSlots];
+
+void conv_tc_trace_dump() {
+    if (g_trace_on != 2 || !g_trace_dev) return;
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> h((size_t)kTraceSlots * 16);
+    cudaMemcpy(h.data(), g_trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    const int n = std::min(g_trace_next, kTraceSlots);
+    unsigned long long t0 = 0;
+    for (int i = 0; i < n; ++i) {
+        const int slot = (g_trace_next - n + i) % kTraceSlots;
+        const unsigned long long* r = &h[(size_t)slot * 16];
+        if (!r[8]) continue;
+        if (!t0) t0 = r[8];
+        fprintf(stderr, "conv_timeline %4d k%d cin %4d bn %3d W %3d cout %4d start %10.2f us dur %7.2f us  (clk: setup %llu first_data %llu mma %llu acc %llu epi %llu exit %llu)\n",
+                i, g_trace_desc[slot] / 1000000, (g_trace_desc[slot] / 100) % 10000, (g_trace_desc[slot] % 100) * 32, g_trace_shape[slot] / 10000,
+                g_trace_shape[slot] % 10000, (r[8] - t0) * 1e-3, (r[9] - r[8]) * 1e-3, r[1] - r[0], r[3] ? r[3] - r[0] : 0, r[4] ? r[4] - r[0] : 0,
+                r[5] ? r[5] - r[0] : 0, r[6] ? r[6] - r[0] : 0, r[7] - r[0]);
+    }
+}
+
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -783,14 +963,24 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
             use_pdl = env_int("YDST_PDL", 1);
             attr2_set = true;
         }
-        static unsigned long long* trace_dev = nullptr;
-        static int trace_on = -1;
-        if (trace_on < 0) {
-            trace_on = env_int("YDST_CONV_TRACE", 0);
-            if (trace_on) { YDST_CUDA(cudaMalloc(&trace_dev, 16 * sizeof(unsigned long long))); }
+        if (g_trace_on < 0) {
+            g_trace_on = env_int("YDST_CONV_TRACE", 0);
+            if (g_trace_on) {
+                YDST_CUDA(cudaMalloc(&g_trace_dev, kTraceSlots * 16 * sizeof(unsigned long long)));
+                YDST_CUDA(cudaMemset(g_trace_dev, 0, kTraceSlots * 16 * sizeof(unsigned long long)));
+            }
         }
+        const int trace_on = g_trace_on;
+        unsigned long long* trace_dev = g_trace_dev;
         ConvTcParams prm = L.p;
-        if (trace_on) { YDST_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * 8, stream)); prm.trace = trace_dev; }
+        prm.pdl = use_pdl;
+        if (trace_on == 1) { YDST_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * 8, stream)); prm.trace = trace_dev; }
+        if (trace_on == 2) {                                  // timeline mode: one slot per launch, no synchronisation
+            const int slot = g_trace_next++ % kTraceSlots;
+            prm.trace = trace_dev + (size_t)slot * 16;          // not re-zeroed: a memset node would break the PDL chain
+            g_trace_desc[slot] = L.p.R * 1000000 + L.p.cin * 100 + (L.p.block_n >> 5);   // compact tag: k, cin, bn/32
+            g_trace_shape[slot] = L.p.Wo * 10000 + L.p.cout;
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = L.grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute at[1];
@@ -798,7 +988,7 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
         YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, maps, prm));
-        if (trace_on) {
+        if (trace_on == 1) {
             unsigned long long h[16];
             YDST_CUDA(cudaStreamSynchronize(stream));
             YDST_CUDA(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));

@@ -36,9 +36,12 @@ struct ConvTcParams {
     int halo;             // chunk rows before the tile's first pixel (3x3: Wp + 1, 1x1: 0)
     int a_box_rows, a_boxes;   // the chunk is fetched as a_boxes TMA boxes of a_box_rows rows
     int a_stages, b_stages;
+    int tpb;              // 64-channel K slices per weight stage (3x3: filter taps, 1 | 3 | 9; 1x1: channel blocks)
+    int store_tma;        // 1: epilogue stages 64-column groups in swizzled smem and writes them with TMA bulk stores
     float* ws;            // split-K partials [tile][split][chunk][128][16] fp32
     int* tickets;         // per output tile arrival counter (self-resetting)
     unsigned long long* trace;   // debug: CTA (0,0,0) records clock64 at its pipeline milestones (YDST_CONV_TRACE=1)
+    int pdl;              // launched with programmatic stream serialization (the producer then prefetches all weight stages first)
     int bo_mode;          // UMMA descriptor base-offset mode for row-shifted starts (validated on hardware)
 };
 
@@ -64,9 +67,10 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                   const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
                   const ConvWorkspace* ws = nullptr);
 // the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
-struct ConvTiling { int bn, ksplit, cbs_per_split, a_stages, b_stages, occupancy, smem_bytes; double model_us; };
+struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes; double model_us; };
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets);
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
+void conv_tc_trace_dump();   // YDST_CONV_TRACE=2: print the per-launch timeline collected so far (debug aid)
 double conv_tc_flops(const ConvTcLaunch& L);   // useful 2*M*N*K (logical, unpadded)
 
 }  // namespace ydst

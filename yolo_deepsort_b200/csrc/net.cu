@@ -102,7 +102,39 @@ static double conv_bytes(const ConvTcLaunch& L) {
     return 2.0 * (in_px * p.cin + (double)p.N * p.Ho * p.Wo * p.cout * (p.out_f32 ? 2.0 : 1.0) + (double)p.cout * p.R * p.S * p.cin);
 }
 
+static void run_ops(const Plan& plan, cudaStream_t st);
+
+static int graphs_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("YDST_GRAPH");
+        v = e ? atoi(e) : 1;
+        if (getenv("YDST_CONV_TRACE") && atoi(getenv("YDST_CONV_TRACE")) == 1) v = 0;   // that mode synchronises after every conv
+    }
+    return v;
+}
+
 void run_plan(const Plan& plan, cudaStream_t st) {
+    if (g_profiling || !graphs_enabled()) { run_ops(plan, st); return; }
+    if (!plan.exec) {
+        if (plan.runs++ == 0) { run_ops(plan, st); return; }             // first run eager: one-time attribute / driver-entry setup
+        // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+        static thread_local cudaStream_t cap = nullptr;
+        if (!cap) YDST_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        YDST_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        try { run_ops(plan, cap); }
+        catch (...) { cudaStreamEndCapture(cap, &g); if (g) cudaGraphDestroy(g); throw; }
+        YDST_CUDA(cudaStreamEndCapture(cap, &g));
+        YDST_CUDA(cudaGraphInstantiate(&plan.exec, g, 0));
+        YDST_CUDA(cudaGraphDestroy(g));
+        count_launch(-plan.launches);                                      // the capture pass launched nothing
+    }
+    YDST_CUDA(cudaGraphLaunch(plan.exec, st));
+    count_launch(plan.launches);
+}
+
+static void run_ops(const Plan& plan, cudaStream_t st) {
     for (const Op& op : plan.ops) {
         OpSample smp;
         if (g_profiling) {

@@ -47,6 +47,15 @@ struct Plan {
     std::vector<Op> ops;
     int launches = 0;
     double flops = 0;
+    // The op list is static (fixed buffers, fixed shapes), so after one eager run it is captured into a CUDA graph:
+    // one launch per forward, kernel->kernel edges (programmatic where the convs ask for it) instead of ~100 stream launches.
+    mutable cudaGraphExec_t exec = nullptr;
+    mutable int runs = 0;
+    Plan() = default;
+    Plan(const Plan&) = delete;
+    Plan& operator=(const Plan&) = delete;
+    Plan(Plan&& o) noexcept : ops(std::move(o.ops)), launches(o.launches), flops(o.flops), exec(o.exec), runs(o.runs) { o.exec = nullptr; }
+    ~Plan() { if (exec) cudaGraphExecDestroy(exec); }
 };
 void run_plan(const Plan& plan, cudaStream_t st);
 
