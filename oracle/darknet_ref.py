@@ -163,24 +163,36 @@ def yolo_decode(x, anchors, num_classes, img_dim):
                       conf_cls[..., 1:].reshape(B, -1, num_classes)), -1)
 
 
-def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage=False):
+def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage=False, teacher=None, fused=()):
     """Darknet.forward (yolo3/models/models.py:292-313).  x: (B,3,H,W) float32 in [0,1].
+    calibrate_bn=True is a synthetic-weights helper (not reference behaviour): it overwrites each BN's
+    running mean/var in `ws` with the statistics of its input on `x`, so seeded random weights keep
+    unit-scale activations through 75+ layers.
     half_storage=True restates the reference's own half=True mode (yolo3/detect/img_detect.py:48-50,79-82: model.half(),
     fp16 activations and weights) on the CPU: weights and every materialised activation are rounded to fp16, the arithmetic
     stays fp32 (what fp16 tensor-core convolutions do).  The first conv keeps fp32 weights and input and the head convs keep
-    fp32 outputs, as the CUDA path does; a conv whose result only feeds the next shortcut is rounded after the add.
-    calibrate_bn=True is a synthetic-weights helper (not reference behaviour): it overwrites each BN's
-    running mean/var in `ws` with the statistics of its input on `x`, so seeded random weights keep
-    unit-scale activations through 75+ layers."""
+    fp32 outputs, as the CUDA path does.
+    teacher: optional list (one entry per layer, None allowed) of layer outputs produced by ANOTHER implementation; every
+    layer then reads its inputs from `teacher` instead of from this function's own outputs, so each layer is checked in
+    isolation on identical inputs and rounding noise cannot compound through the depth of the net (test aid).
+    fused: cfg indices of convolutions whose following shortcut is applied inside the conv (the other implementation's
+    buffer for that layer holds the post-add tensor); the shortcut layer then passes its input through."""
     x = torch.as_tensor(x)
     img_dim = (x.shape[2], x.shape[3])
     outs, yolo = [], []
     it = iter(ws)
     h16 = (lambda t_: t_.half().float()) if half_storage else (lambda t_: t_)
     body = blocks[1:]
+
+    def src(i, li):
+        i = i if i >= 0 else li + i
+        return teacher[i] if teacher is not None and teacher[i] is not None else outs[i]
+
     with torch.no_grad():
         for li, b in enumerate(body):
             t = b["type"]
+            if li > 0 and t in ("convolutional", "maxpool", "upsample"):
+                x = src(li - 1, li)
             if t == "convolutional":
                 d = next(it)
                 k = int(b["size"])
@@ -197,8 +209,10 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage
                     x = F.leaky_relu(x, 0.1)
                 elif b["activation"] == "mish":
                     x = _mish(x)
-                nxt = body[li + 1]["type"] if li + 1 < len(body) else ""
-                if nxt not in ("yolo", "shortcut"):
+                nxt = body[li + 1] if li + 1 < len(body) else {"type": ""}
+                if li in fused:
+                    x = h16(x + src(li + 1 + int(nxt["from"]), 0))
+                elif nxt["type"] not in ("yolo", "shortcut"):
                     x = h16(x)
             elif t == "maxpool":
                 k, s = int(b["size"]), int(b["stride"])
@@ -209,16 +223,16 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage
                 s = int(b["stride"])
                 x = x.repeat_interleave(s, 2).repeat_interleave(s, 3)
             elif t == "route":
-                x = torch.cat([outs[int(i)] for i in b["layers"].split(",")], 1)
+                x = torch.cat([src(int(i), li) for i in b["layers"].split(",")], 1)
                 if "groups" in b:
                     x = x.chunk(int(b["groups"]), dim=1)[int(b["group_id"])]
             elif t == "shortcut":
-                x = h16(outs[-1] + outs[int(b["from"])])
+                x = src(li - 1, li) if (li - 1) in fused else h16(src(li - 1, li) + src(int(b["from"]), li))
             elif t == "yolo":
                 mask = [int(v) for v in b["mask"].split(",")]
                 a = [int(v) for v in b["anchors"].split(",")]
                 anchors = [(a[2 * i], a[2 * i + 1]) for i in mask]
-                x = yolo_decode(x, anchors, int(b["classes"]), img_dim)
+                x = yolo_decode(src(li - 1, li), anchors, int(b["classes"]), img_dim)
                 yolo.append(x)
             outs.append(x)
     y = torch.cat(yolo, 1)

@@ -28,6 +28,8 @@ struct ydst_pipeline {
     float *tlwh = nullptr, *confd = nullptr, *cls = nullptr, *feat = nullptr;
     int* h_counts = nullptr;      // pinned: [0] m, [1] n_dets, [2] overflow, [3] crop error flag
     float* h_dets = nullptr;      // pinned 300 x 6
+    float* h_cls = nullptr;       // pinned: class ids of the tracker inputs (float, as the detector emits them)
+    int* h_payload = nullptr;
 };
 
 static cudaStream_t S(void* s) { return (cudaStream_t)s; }
@@ -422,6 +424,8 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
     if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
     YDST_CUDA(cudaMallocHost(&p->h_counts, sizeof(int) * 8));
     YDST_CUDA(cudaMallocHost(&p->h_dets, sizeof(float) * 6 * md));
+    YDST_CUDA(cudaMallocHost(&p->h_cls, sizeof(float) * md));
+    p->h_payload = new int[md];
     *out = p;
     YDST_API_END
 }
@@ -429,7 +433,7 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
     YDST_API_BEGIN
     if (p) {
         cudaFree(p->frame_dev); cudaFree(p->tlwh); cudaFree(p->confd); cudaFree(p->cls); cudaFree(p->feat); cudaFree(p->mask_dev);
-        cudaFreeHost(p->h_counts); cudaFreeHost(p->h_dets);
+        cudaFreeHost(p->h_counts); cudaFreeHost(p->h_dets); cudaFreeHost(p->h_cls); delete[] p->h_payload;
         delete p;
     }
     YDST_API_END
@@ -443,6 +447,8 @@ static int pipeline_run(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out
     det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, p->tlwh, p->confd, p->cls, st);
     YDST_CUDA(cudaMemcpyAsync(p->h_counts, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     if (dets_host) YDST_CUDA(cudaMemcpyAsync(p->h_dets, det.nms_.dets, sizeof(float) * 6 * det.nms_.max_det, cudaMemcpyDeviceToHost, st));
+    // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
+    YDST_CUDA(cudaMemcpyAsync(p->h_cls, p->cls, sizeof(float) * det.nms_.max_det, cudaMemcpyDeviceToHost, st));
     YDST_CUDA(cudaStreamSynchronize(st));
     YDST_CHECK(p->h_counts[2] == 0, "NMS candidate capacity exceeded (%d candidates)", p->h_counts[0]);
     const int n_dets = p->h_counts[1], m = p->h_counts[3];
@@ -452,7 +458,8 @@ static int pipeline_run(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out
     YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), st));
     p->reid->extract(frame_dev, det.H, det.W, p->tlwh, m, p->feat, st);
     YDST_CUDA(cudaMemcpyAsync(p->h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    p->trk->update(p->tlwh, p->feat, nullptr, p->cls, m, out_host, k_host, st);
+    for (int i = 0; i < m; ++i) p->h_payload[i] = (int)p->h_cls[i];
+    p->trk->update(p->tlwh, p->feat, p->h_payload, nullptr, m, out_host, k_host, st);
     if (p->h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
     return 0;
 }

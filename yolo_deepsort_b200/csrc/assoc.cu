@@ -285,59 +285,50 @@ __device__ __forceinline__ int f2ord(float f) {
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 static constexpr int kOrdInf = 0x7f800000;
 
-// 64 gallery rows x 64 detections per CTA, K = 512 in steps of 16; each thread owns a 4x4 micro-tile.
+// 16 gallery rows x 64 detections per CTA (a frame has ~1500 gallery rows x ~50 detections: small row tiles keep ~100 CTAs
+// busy), K = 512 in steps of 16; each thread owns 1 row x 4 detections.
 // Epilogue: d = 1 - dot, segmented min over each track's gallery rows through atomicMin (order independent).
 __global__ void __launch_bounds__(256) cosine_min_kernel(const float* __restrict__ gallery, const int* __restrict__ row_ptr,
                                                          const int* __restrict__ row_track, int G, const float* __restrict__ det, int m,
                                                          int* __restrict__ cost_enc) {
-    __shared__ __align__(16) float As[16][64 + 4];
-    __shared__ __align__(16) float Bs[16][64 + 4];
-    const int g0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    __shared__ __align__(16) float As[16][16 + 1];      // [k][row]
+    __shared__ __align__(16) float Bs[16][64 + 4];      // [k][det]
+    const int g0 = blockIdx.x * 16, j0 = blockIdx.y * 64;
     const int t = threadIdx.x;
-    const int lr = t >> 2, lk = (t & 3) * 4;
-    const int ga = g0 + lr, jb = j0 + lr;
+    const int ar = t >> 4, ak = t & 15;                 // A loader: row ar, k ak
+    const int br = t >> 2, bk = (t & 3) * 4;            // B loader: det br, k bk..bk+3
+    const int ga = g0 + ar, jb = j0 + br;
     const float* arow = ga < G ? gallery + (long long)row_ptr[ga] * kFeat : nullptr;
     const float* brow = jb < m ? det + (long long)jb * kFeat : nullptr;
     const int ty = t >> 4, tx = t & 15;
-    float acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < kFeat; k0 += 16) {
-        const float4 va = arow ? __ldg(reinterpret_cast<const float4*>(arow + k0 + lk)) : make_float4(0, 0, 0, 0);
-        const float4 vb = brow ? __ldg(reinterpret_cast<const float4*>(brow + k0 + lk)) : make_float4(0, 0, 0, 0);
-        As[lk + 0][lr] = va.x; As[lk + 1][lr] = va.y; As[lk + 2][lr] = va.z; As[lk + 3][lr] = va.w;
-        Bs[lk + 0][lr] = vb.x; Bs[lk + 1][lr] = vb.y; Bs[lk + 2][lr] = vb.z; Bs[lk + 3][lr] = vb.w;
+        As[ak][ar] = arow ? __ldg(arow + k0 + ak) : 0.f;
+        const float4 vb = brow ? __ldg(reinterpret_cast<const float4*>(brow + k0 + bk)) : make_float4(0, 0, 0, 0);
+        Bs[bk + 0][br] = vb.x; Bs[bk + 1][br] = vb.y; Bs[bk + 2][br] = vb.z; Bs[bk + 3][br] = vb.w;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float a = As[k][ty];
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            acc[0] = fmaf(a, b4.x, acc[0]); acc[1] = fmaf(a, b4.y, acc[1]);
+            acc[2] = fmaf(a, b4.z, acc[2]); acc[3] = fmaf(a, b4.w, acc[3]);
         }
         __syncthreads();
     }
+    const int g = g0 + ty;
+    if (g >= G) return;
+    const int trk = row_track[g];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int g = g0 + ty * 4 + a;
-        if (g >= G) continue;
-        const int trk = row_track[g];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = j0 + tx * 4 + b;
-            if (j < m) atomicMin(cost_enc + (long long)trk * m + j, f2ord(1.f - acc[a][b]));
-        }
+    for (int b = 0; b < 4; ++b) {
+        const int j = j0 + tx * 4 + b;
+        if (j < m) atomicMin(cost_enc + (long long)trk * m + j, f2ord(1.f - acc[b]));
     }
 }
 void launch_cosine_min(const float* gallery, const int* row_ptr, const int* row_track, int G, const float* det_feat_n, int m,
                        int* cost_enc, cudaStream_t st) {
     if (G == 0 || m == 0) return;
-    dim3 grid(cdiv(G, 64), cdiv(m, 64));
+    dim3 grid(cdiv(G, 16), cdiv(m, 64));
     cosine_min_kernel<<<grid, 256, 0, st>>>(gallery, row_ptr, row_track, G, det_feat_n, m, cost_enc);
     YDST_CUDA(cudaGetLastError());
 }
@@ -445,14 +436,38 @@ struct LsapWork {
     unsigned char *SR, *SC;
 };
 
+static __host__ __device__ inline size_t lsap_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// state_in_smem: the whole solver state (duals, shortest-path costs, predecessor / assignment / remaining arrays) lives in
+// dynamic shared memory instead of the global workspace -- the algorithm is a chain of dependent scans, so every global
+// round trip (~700 clk) sat on the critical path.  cost_in_smem additionally stages the cost matrix when it is small.
 template <int T>
-__global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost, int R, int C, float max_dist, int* __restrict__ col4row_out,
-                                                 int* __restrict__ over_max, LsapWork w) {
+__global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_g, int R, int C, float max_dist, int* __restrict__ col4row_out,
+                                                 int* __restrict__ over_max, LsapWork w, int state_in_smem, int cost_in_smem) {
+    extern __shared__ __align__(16) unsigned char lsap_smem[];
     __shared__ LsapBest s_part[32];
     __shared__ double s_min;
     __shared__ int s_i, s_nrem, s_sink;
     const int tid = threadIdx.x;
     auto bar = [&]() { if (T == 32) __syncwarp(); else __syncthreads(); };
+    const float* cost = cost_g;
+    if (state_in_smem) {
+        unsigned char* p = lsap_smem;
+        w.u = (double*)p; p += lsap_align16(sizeof(double) * R);
+        w.v = (double*)p; p += lsap_align16(sizeof(double) * C);
+        w.spc = (double*)p; p += lsap_align16(sizeof(double) * C);
+        w.path = (int*)p; p += lsap_align16(sizeof(int) * C);
+        w.row4col = (int*)p; p += lsap_align16(sizeof(int) * C);
+        w.remaining = (int*)p; p += lsap_align16(sizeof(int) * C);
+        w.col4row = (int*)p; p += lsap_align16(sizeof(int) * R);
+        w.SR = p; p += lsap_align16(R);
+        w.SC = p; p += lsap_align16(C);
+        if (cost_in_smem) {
+            float* cs = (float*)p;
+            for (int i = tid; i < R * C; i += T) cs[i] = cost_g[i];
+            cost = cs;
+        }
+    }
 
     for (int i = tid; i < R; i += T) { w.u[i] = 0.0; w.col4row[i] = -1; }
     for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; w.path[j] = -1; }
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost,
             best.val = CUDART_INF; best.it = 0x7fffffff; best.una = 0;
             for (int it = tid; it < nrem; it += T) {
                 const int j = w.remaining[it];
-                const double r = mv + (double)__ldg(crow + j) - ui - w.v[j];
+                const double r = mv + (double)crow[j] - ui - w.v[j];
                 double s = w.spc[j];
                 if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
                 LsapBest c;
@@ -564,9 +579,21 @@ void launch_lsap(const float* cost, int R, int C, float max_dist, int* col4row, 
     w.col4row = (int*)p; p += align16(sizeof(int) * R);
     w.SR = p; p += align16(R);
     w.SC = p;
-    if (C <= 96) lsap_kernel<32><<<1, 32, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
-    else if (C <= 1024) lsap_kernel<256><<<1, 256, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
-    else lsap_kernel<1024><<<1, 1024, 0, st>>>(cost, R, C, max_dist, col4row, over_max, w);
+    static bool attr_set = false;
+    if (!attr_set) {
+        YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const size_t state_bytes = lsap_work_bytes(R, C);
+    const size_t cost_bytes = (size_t)R * C * sizeof(float);
+    const int state_in_smem = state_bytes <= 160 * 1024;
+    const int cost_in_smem = state_in_smem && state_bytes + cost_bytes <= 96 * 1024;
+    const size_t smem = state_in_smem ? state_bytes + (cost_in_smem ? cost_bytes : 0) : 0;
+    if (C <= 128) lsap_kernel<32><<<1, 32, smem, st>>>(cost, R, C, max_dist, col4row, over_max, w, state_in_smem, cost_in_smem);
+    else if (C <= 1024) lsap_kernel<256><<<1, 256, smem, st>>>(cost, R, C, max_dist, col4row, over_max, w, state_in_smem, cost_in_smem);
+    else lsap_kernel<1024><<<1, 1024, smem, st>>>(cost, R, C, max_dist, col4row, over_max, w, state_in_smem, cost_in_smem);
     YDST_CUDA(cudaGetLastError());
 }
 

@@ -35,6 +35,17 @@ struct ConvTcMaps {
     CUtensorMap b;
 };
 
+// ask L2 to fetch this CTA's slice of the NEXT layer's weights (they come from HBM: 124 MB of weights do not stay resident)
+__device__ __forceinline__ void prefetch_next_weights(const ConvTcParams& p) {
+    if (!p.pf_bytes) return;
+    const unsigned nctas = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const unsigned chunk = ((p.pf_bytes + nctas - 1) / nctas + 127u) & ~127u;
+    const unsigned long long off = (unsigned long long)cta * chunk;
+    if (off >= p.pf_bytes) return;
+    const unsigned sz = (unsigned)min((unsigned long long)chunk, (unsigned long long)p.pf_bytes - off) & ~15u;
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p.pf_ptr + off), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -351,6 +362,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                 if (++cb == p.cin_blocks) { cb = 0; if (++sx == p.S) { sx = 0; ++r; } }
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
+            prefetch_next_weights(p);
         }
     } else if (warp == 5) {
         if (elect_one()) {
@@ -517,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
                 for (; issued < (i + 1) * nbs; ++issued) issue_b();
                 if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
             }
+            prefetch_next_weights(p);
         }
     } else if (warp == 5) {
         if (elect_one()) {
@@ -782,6 +795,8 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                   const ConvWorkspace* ws) {
     ConvTcParams& p = L.p;
     memset(&L, 0, sizeof(L));
+    L.w_ptr = w_packed;
+    L.w_bytes = (unsigned)((size_t)((cout_real + 15) & ~15) * R * S * in.C * sizeof(__half));
     YDST_CHECK(in.C % 16 == 0, "conv_tc needs Cin %% 16 == 0 (got %d)", in.C);
     YDST_CHECK(in.ctot % 8 == 0 && in.coff % 8 == 0 && out.ctot % 8 == 0 && out.coff % 8 == 0, "channel strides/offsets must be multiples of 8");
     YDST_CHECK((R == 1 && S == 1) || (R == 3 && S == 3), "conv_tc supports 1x1 and 3x3 filters");
@@ -950,6 +965,7 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     ConvTcMaps maps;
@@ -960,6 +976,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         static int use_pdl = 1;
         if (!attr2_set) {
             YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             use_pdl = env_int("YDST_PDL", 1);
             attr2_set = true;
         }

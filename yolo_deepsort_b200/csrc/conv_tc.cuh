@@ -41,6 +41,8 @@ struct ConvTcParams {
     float* ws;            // split-K partials [tile][split][chunk][128][16] fp32
     int* tickets;         // per output tile arrival counter (self-resetting)
     unsigned long long* trace;   // debug: CTA (0,0,0) records clock64 at its pipeline milestones (YDST_CONV_TRACE=1)
+    const void* pf_ptr;   // next convolution's packed weights: each CTA asks L2 to prefetch its slice once its own loads are queued
+    unsigned pf_bytes;
     int pdl;              // launched with programmatic stream serialization (the producer then prefetches all weight stages first)
     int bo_mode;          // UMMA descriptor base-offset mode for row-shifted starts (validated on hardware)
 };
@@ -60,6 +62,8 @@ struct ConvTcLaunch {
     dim3 grid;
     int smem_bytes;
     int stages;
+    const void* w_ptr;    // this convolution's packed weights (what a predecessor prefetches)
+    unsigned w_bytes;
 };
 
 // Host: encode tensor maps + pick tiling.  `w_packed` is fp16 [cout16][R*S*cin] (K-major).

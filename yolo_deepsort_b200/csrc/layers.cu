@@ -39,65 +39,83 @@ void launch_nchw_to_nhwc(const void* src, int src_is_half, float* dst, int N, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// First layer: Cin = 3 makes K = 27, far too thin for a tensor-core tile; one thread per output pixel
-// keeps the 27 inputs in registers and streams the (broadcast) weights from shared memory.
+// First layer: Cin = 3 makes K = 27, far too thin for a tensor-core tile.  One thread computes TWO horizontally adjacent
+// output pixels: their 3 x (3 + stride) x 3 input window sits in registers and every (broadcast) shared-memory weight
+// vector is used for both pixels, which halves the LDS traffic that bounds this kernel.
+template <int STRIDE>
 __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ w,
                                                          const float* __restrict__ scale, const float* __restrict__ bias, int cout,
-                                                         int stride, int act, Act out) {
+                                                         int act, Act out) {
     extern __shared__ float sw[];          // [27][cout] then scale[cout], bias[cout]
     for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) sw[i] = w[i];
     float* ssc = sw + 27 * cout;
     float* sbi = ssc + cout;
     for (int i = threadIdx.x; i < cout; i += blockDim.x) { ssc[i] = scale[i]; sbi[i] = bias[i]; }
     __syncthreads();
+    constexpr int WC = 3 + STRIDE;         // window columns shared by the two pixels
+    const int pairs_x = (out.W + 1) >> 1;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)N * out.H * out.W;
+    const long long total = (long long)N * out.H * pairs_x;
     if (idx >= total) return;
-    const int xo = (int)(idx % out.W);
-    long long t = idx / out.W;
+    const int xo = (int)(idx % pairs_x) * 2;
+    long long t = idx / pairs_x;
     const int yo = (int)(t % out.H);
     const int n = (int)(t / out.H);
-    float v[27];
+    float v[3][WC][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int y = yo * stride - 1 + r, x = xo * stride - 1 + s;
+        for (int s = 0; s < WC; ++s) {
+            const int y = yo * STRIDE - 1 + r, x = xo * STRIDE - 1 + s;
             const bool ok = y >= 0 && y < H && x >= 0 && x < W;
             const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+            for (int c = 0; c < 3; ++c) v[r][s][c] = ok ? __ldg(px + c) : 0.f;
         }
+    const bool two = xo + 1 < out.W;
     const long long pix = ((long long)n * out.Hp() + yo + 1) * out.Wp() + xo + 1;
     __half* op = out.base + pix * out.ctot + out.coff;
     for (int co = 0; co < cout; co += 8) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float acc[2][8];
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + co);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * cout + co + 4);
-            acc[0] = fmaf(v[k], w0.x, acc[0]); acc[1] = fmaf(v[k], w0.y, acc[1]);
-            acc[2] = fmaf(v[k], w0.z, acc[2]); acc[3] = fmaf(v[k], w0.w, acc[3]);
-            acc[4] = fmaf(v[k], w1.x, acc[4]); acc[5] = fmaf(v[k], w1.y, acc[5]);
-            acc[6] = fmaf(v[k], w1.z, acc[6]); acc[7] = fmaf(v[k], w1.w, acc[7]);
-        }
-        uint4 pk;
-        __half2* h = reinterpret_cast<__half2*>(&pk);
+        for (int q = 0; q < 8; ++q) acc[0][q] = acc[1][q] = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float a = apply_act(fmaf(acc[2 * q], ssc[co + 2 * q], sbi[co + 2 * q]), act);
-            const float b = apply_act(fmaf(acc[2 * q + 1], ssc[co + 2 * q + 1], sbi[co + 2 * q + 1]), act);
-            h[q] = __floats2half2_rn(a, b);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int k = (r * 3 + s) * 3 + c;
+                    const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + co);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sw + k * cout + co + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const float a0 = v[r][s][c], a1 = v[r][s + STRIDE][c];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { acc[0][q] = fmaf(a0, wv[q], acc[0][q]); acc[1][q] = fmaf(a1, wv[q], acc[1][q]); }
+                }
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            if (px == 1 && !two) break;
+            uint4 pk;
+            __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = apply_act(fmaf(acc[px][2 * q], ssc[co + 2 * q], sbi[co + 2 * q]), act);
+                const float b = apply_act(fmaf(acc[px][2 * q + 1], ssc[co + 2 * q + 1], sbi[co + 2 * q + 1]), act);
+                h[q] = __floats2half2_rn(a, b);
+            }
+            *reinterpret_cast<uint4*>(op + (long long)px * out.ctot + co) = pk;
         }
-        *reinterpret_cast<uint4*>(op + co) = pk;
     }
 }
 void launch_conv_first(const float* in, int N, int H, int W, const float* w, const float* scale, const float* bias, int cout,
                        int stride, int act, const Act& out, cudaStream_t st) {
     YDST_CHECK(cout % 8 == 0 && cout <= 64, "first-layer conv supports cout in {8..64}, multiple of 8 (got %d)", cout);
-    const long long total = (long long)N * out.H * out.W;
+    YDST_CHECK(stride == 1 || stride == 2, "first-layer conv supports stride 1 and 2");
+    const long long total = (long long)N * out.H * ((out.W + 1) / 2);
     const int smem = (27 * cout + 2 * cout) * (int)sizeof(float);
-    conv_first_kernel<<<cdiv(total, 128), 128, smem, st>>>(in, N, H, W, w, scale, bias, cout, stride, act, out);
+    if (stride == 1) conv_first_kernel<1><<<cdiv(total, 128), 128, smem, st>>>(in, N, H, W, w, scale, bias, cout, act, out);
+    else conv_first_kernel<2><<<cdiv(total, 128), 128, smem, st>>>(in, N, H, W, w, scale, bias, cout, act, out);
     YDST_CUDA(cudaGetLastError());
 }
 

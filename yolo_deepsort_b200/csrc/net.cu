@@ -88,6 +88,18 @@ std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w, int c
     return cw;
 }
 
+// every tensor-core conv prefetches the weights of the next one into L2 (YDST_WEIGHT_PREFETCH=0 disables)
+static void link_weight_prefetch(Plan& plan) {
+    const char* e = getenv("YDST_WEIGHT_PREFETCH");
+    if (e && atoi(e) == 0) return;
+    Op* prev = nullptr;
+    for (Op& op : plan.ops) {
+        if (op.kind != OP_CONV_TC) continue;
+        if (prev) { prev->conv.p.pf_ptr = op.conv.w_ptr; prev->conv.p.pf_bytes = op.conv.w_bytes; }
+        prev = &op;
+    }
+}
+
 static bool g_profiling = false;
 static std::vector<OpSample> g_samples;
 void profile_begin() { g_profiling = true; g_samples.clear(); }
@@ -361,6 +373,7 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
         }
     }
     YDST_CHECK(wp == n_weights, "weights payload has %zu floats, network consumes %zu", n_weights, wp);
+    link_weight_prefetch(plan);
     plan.launches = (int)plan.ops.size();
     out_ = out;
     head_f32_ = head_f32;
@@ -490,6 +503,7 @@ const Plan& Reid::plan_for(int m) {
         Op op; op.kind = OP_AVGPOOL_L2; op.a = x; op.fdst = feat_;
         plan.ops.push_back(op);
     }
+    link_weight_prefetch(plan);
     plan.launches = (int)plan.ops.size();
     return plans_.emplace(m, std::move(plan)).first->second;
 }

@@ -67,7 +67,8 @@ __global__ void nms_mask_kernel(const NmsCand* __restrict__ sorted, const int* _
     const float off_a = a.cls * 4096.f;
     const float ax1 = a.x1 + off_a, ay1 = a.y1 + off_a, ax2 = a.x2 + off_a, ay2 = a.y2 + off_a;
     const float area_a = (ax2 - ax1) * (ay2 - ay1);
-    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+    const int nw = (n + 63) >> 6;              // words beyond the candidate count are never read by the sweep
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {
         unsigned long long bits = 0;
         for (int b = 0; b < 64; ++b) {
             const int j = w * 64 + b;
@@ -86,12 +87,27 @@ __global__ void nms_mask_kernel(const NmsCand* __restrict__ sorted, const int* _
     }
 }
 
-// ---- 4. sequential sweep (one warp), output kept rows in score order, capped at max_det ----
-__global__ void nms_sweep_kernel(const NmsCand* __restrict__ sorted, const int* __restrict__ count, int cap,
-                                 const unsigned long long* __restrict__ mask, int words, int max_det, float* __restrict__ dets,
-                                 int* __restrict__ n_out, int* __restrict__ overflow) {
+// ---- 4. sequential sweep (warp 0), output kept rows in score order, capped at max_det ----
+// The sweep is a dependent chain (candidate i is kept only if no earlier kept candidate suppressed it), so the mask rows it
+// ORs in are first staged in shared memory by the whole block (n x ceil(n/64) words, up to kSweepSmemRows candidates);
+// beyond that it reads them from global memory.
+static constexpr int kSweepSmemRows = 1024;
+__global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restrict__ sorted, const int* __restrict__ count, int cap,
+                                                        const unsigned long long* __restrict__ mask, int words, int max_det,
+                                                        float* __restrict__ dets, int* __restrict__ n_out, int* __restrict__ overflow) {
+    extern __shared__ unsigned long long smask[];
     const int total = *count;
     const int n = min(total, cap);
+    const int nw = (n + 63) >> 6;
+    const bool staged = n <= kSweepSmemRows;
+    if (staged) {
+        for (int e = threadIdx.x; e < n * nw; e += blockDim.x) {
+            const int i = e / nw, w = e - i * nw;
+            smask[e] = mask[(long long)i * words + w];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     if (lane == 0) *overflow = total > cap ? 1 : 0;
     // removed bits live in registers: word w is held by lane w % 32, slot w / 32 (words <= 128)
@@ -108,11 +124,10 @@ __global__ void nms_sweep_kernel(const NmsCand* __restrict__ sorted, const int* 
             dets[kept * 6 + lane] = v;
         }
         ++kept;
-        const unsigned long long* row = mask + (long long)i * words;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const int ww = s * 32 + lane;
-            if (ww < words) removed[s] |= row[ww];
+            if (ww < nw) removed[s] |= staged ? smask[i * nw + ww] : mask[(long long)i * words + ww];
         }
     }
     if (lane == 0) *n_out = min(kept, max_det);
@@ -167,8 +182,14 @@ void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaSt
     YDST_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 4, st));
     nms_collect_kernel<<<(rows + 255) / 256, 256, 0, st>>>(pred, rows, nf, conf, cand, cap, counters);
     nms_rank_kernel<<<cap / 256 > 0 ? cap / 256 : 1, 256, 0, st>>>(cand, counters, cap, sorted);
-    nms_mask_kernel<<<cap, 128, 0, st>>>(sorted, counters, cap, iou, mask, words);
-    nms_sweep_kernel<<<1, 32, 0, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
+    nms_mask_kernel<<<cap, 64, 0, st>>>(sorted, counters, cap, iou, mask, words);
+    static bool attr_set = false;
+    const int sweep_smem = kSweepSmemRows * (kSweepSmemRows / 64) * (int)sizeof(unsigned long long);
+    if (!attr_set) {
+        YDST_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+        attr_set = true;
+    }
+    nms_sweep_kernel<<<1, 256, sweep_smem, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
     YDST_CUDA(cudaGetLastError());
     count_launch(4);
 }

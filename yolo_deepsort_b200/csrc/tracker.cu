@@ -12,6 +12,8 @@
 #include "tracker.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace ydst {
@@ -117,6 +119,10 @@ Tracker::Assign Tracker::solve(const float* cost, const std::vector<int>& tis, c
 void Tracker::update(const float* tlwh, const float* feat, const int* payload_host, const float* cls_dev, int m, int32_t* out_host,
                      int* k_host, cudaStream_t st) {
     YDST_CHECK(m <= cap_d_, "%d detections exceed the tracker's detection capacity %d", m, cap_d_);
+    static const bool trace = getenv("YDST_TRACKER_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = trace ? now() : 0;
+    double t_a = 0, t_b = 0, t_c = 0;
     ibuf_used_ = 0;
     launches_last = 0;
     std::vector<int> payload(m, 0);
@@ -169,6 +175,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         launches_last += 3;
         A = solve(cost_, confirmed, all_dets, (float)max_dist_, st);
     }
+    if (trace) t_a = now();
     std::vector<int> iou_cand = unconfirmed, um_t_a;
     for (int k : A.um_t) (tracks[k].tsu == 1 ? iou_cand : um_t_a).push_back(k);
     Assign B;
@@ -185,6 +192,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         ++launches_last;
         B = solve(cost_, iou_cand, A.um_d, (float)max_iou_, st);
     }
+    if (trace) t_b = now();
     std::vector<std::pair<int, int>> matches = A.matches;
     matches.insert(matches.end(), B.matches.begin(), B.matches.end());
     last_matches = matches;
@@ -256,7 +264,11 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         ++launches_last;
         YDST_CUDA(cudaMemcpyAsync(h_f_, out_mean_, (size_t)K * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    if (trace) t_c = now();
     YDST_CUDA(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "tracker_trace n %d m %d conf %zu | appearance stage %.1f us, iou stage (%zu x %zu) %.1f us, update+spawn enqueue %.1f us, final sync %.1f us\n",
+                n, m, confirmed.size(), t_a - t_begin, iou_cand.size(), A.um_d.size(), t_b - t_a, t_c - t_b, now() - t_c);
     for (int k = 0; k < K; ++k) {
         // fp32, same operation order as the reference: w = a*h; tl = c - wh/2; br = wh + tl; clamp tl >= 0; int32 truncation
         volatile float cx = h_f_[k * 8 + 0], cy = h_f_[k * 8 + 1], a = h_f_[k * 8 + 2], h = h_f_[k * 8 + 3];
