@@ -75,6 +75,9 @@ __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 28)) __trap();          // a protocol bug must abort the launch, never hang the GPU
 }
 
+__device__ __forceinline__ void trace_mark_epi(const ConvTcParams& p, int slot) {      // thread 100: a row that is valid in CTA 0
+    if (p.trace && threadIdx.x == 100 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = (unsigned long long)clock64();
+}
 __device__ __forceinline__ void trace_mark(const ConvTcParams& p, int slot) {
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
         p.trace[slot] = (unsigned long long)clock64();
@@ -98,28 +101,35 @@ __device__ __forceinline__ void trace_mark(const ConvTcParams& p, int slot) {
 // 128-byte fp16 store per pixel and group (fp32 for the YOLO heads).  The residual of group g+1 is fetched while group g is
 // computed, and group 0's before the accumulator is even complete.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void act16_mish(float (&o)[16]) {
-#pragma unroll 4
-    for (int j = 0; j < 16; ++j) o[j] = apply_act(o[j], ACT_MISH);
-}
-
 // activation over 16 values with the (warp-uniform) kind test hoisted out of the element loop
+// kMish selects the kernel instantiation that carries the (long) Mish code: everything else stays small and keeps o[] in registers
+template <bool kMish>
 __device__ __forceinline__ void act16(float (&o)[16], int act) {
     if (act == ACT_LEAKY) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : 0.1f * o[j];
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.1f * o[j]);      // == (x > 0 ? x : 0.1x) for every finite x
     } else if (act == ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-    } else if (act == ACT_MISH) {
-        act16_mish(o);
+    } else if (kMish && act == ACT_MISH) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = apply_act(o[j], ACT_MISH);
     }
 }
 
+template <bool kMish>
 __device__ __forceinline__ void compute16(const ConvTcParams& p, const float (&acc)[16], const float* s_scale, const float* s_bias,
                                           const uint4& r0, const uint4& r1, float (&o)[16]) {
+    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);       // 16-byte aligned (s_sb and the 16-column offsets are)
+    const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j], s_scale[j], s_bias[j]);
+    for (int q = 0; q < 4; ++q) {
+        const float4 sc = sc4[q], bi = bi4[q];
+        o[4 * q + 0] = fmaf(acc[4 * q + 0], sc.x, bi.x);
+        o[4 * q + 1] = fmaf(acc[4 * q + 1], sc.y, bi.y);
+        o[4 * q + 2] = fmaf(acc[4 * q + 2], sc.z, bi.z);
+        o[4 * q + 3] = fmaf(acc[4 * q + 3], sc.w, bi.w);
+    }
     if (p.res_mode) {
         float rs[16];
         const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
@@ -134,13 +144,13 @@ __device__ __forceinline__ void compute16(const ConvTcParams& p, const float (&a
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] += rs[j];
         }
-        act16(o, p.act);
+        act16<kMish>(o, p.act);
         if (p.res_mode == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] += rs[j];
         }
     } else {
-        act16(o, p.act);
+        act16<kMish>(o, p.act);
     }
 }
 __device__ __forceinline__ void pack16(const float (&o)[16], uint4& w0, uint4& w1) {
@@ -152,10 +162,11 @@ __device__ __forceinline__ void pack16(const float (&o)[16], uint4& w0, uint4& w
         g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
     }
 }
+template <bool kMish>
 __device__ __forceinline__ void finish16(const ConvTcParams& p, const float (&acc)[16], int c, const float* s_scale, const float* s_bias,
                                          const uint4& r0, const uint4& r1, long long pix) {
     float o[16];
-    compute16(p, acc, s_scale, s_bias, r0, r1, o);
+    compute16<kMish>(p, acc, s_scale, s_bias, r0, r1, o);
     if (p.out_f32) {
         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c);
 #pragma unroll
@@ -184,6 +195,7 @@ __device__ __forceinline__ void stage_scale_bias(const ConvTcParams& p, int n0, 
     epi_bar_sync();
 }
 
+template <bool kMish>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int warp, int n0, long long pix, bool valid,
                                               const float* s_sb, uint32_t bar_tmem) {
     const int gw = p.block_n < 64 ? p.block_n : 64;
@@ -213,7 +225,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[sub][j]);
                     const int cl = g * gw + sub * 16;
-                    finish16(p, acc, c0 + sub * 16, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], pix);
+                    finish16<kMish>(p, acc, c0 + sub * 16, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], pix);
                 }
         }
 #pragma unroll
@@ -226,8 +238,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
 // Here each 64-column group is written to a 128B-swizzled [128 rows][64 cols] staging tile in shared memory (the operand
 // stages are dead by then) and one elected thread hands it to the TMA store unit.  Invalid rows (border pixels) are written
 // as zeros, which is what the border already holds; rows past the end of the tensor are clipped by TMA.
-__device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* out_map, uint32_t stage_smem, uint32_t tmem_base,
-                                                  int warp, int n0, int p0, long long pix, bool valid, const float* s_sb, uint32_t bar_tmem) {
+template <bool kMish>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* out_map, uint32_t stage_smem,
+                                                  unsigned char* stage_ptr, uint32_t tmem_base, int warp, int n0, int p0, long long pix,
+                                                  bool valid, const float* s_sb, uint32_t bar_tmem) {
     const int ngroups = p.block_n >> 6;
     const int row = threadIdx.x;                                   // 0..127
     uint4 rcur[8], rnext[8];
@@ -250,6 +264,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
             epi_bar_sync();
         }
         tcgen05_wait_ld();
+        if (g == 0) trace_mark_epi(p, 11);
         const uint32_t buf = stage_smem + (uint32_t)(g & 1) * (kBlockM * 128u);
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
@@ -259,18 +274,19 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[sub][j]);
                 const int cl = g * 64 + sub * 16;
-                compute16(p, acc, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], o);
+                compute16<kMish>(p, acc, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], o);
                 pack16(o, w0, w1);
             }
-            const uint32_t rbase = buf + (uint32_t)row * 128u;
-            const uint32_t x = (uint32_t)(row & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((((uint32_t)(2 * sub)) ^ x) << 4)), "r"(w0.x), "r"(w0.y),
-                         "r"(w0.z), "r"(w0.w) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((((uint32_t)(2 * sub + 1)) ^ x) << 4)), "r"(w1.x), "r"(w1.y),
-                         "r"(w1.z), "r"(w1.w) : "memory");
+            uint4* rbase = reinterpret_cast<uint4*>(stage_ptr + (size_t)(g & 1) * (kBlockM * 128u) + (size_t)row * 128u);
+            const int x = row & 7;
+            rbase[(2 * sub) ^ x] = w0;
+            rbase[(2 * sub + 1) ^ x] = w1;
         }
+        if (g == 0) trace_mark_epi(p, 12);
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (g == 0) trace_mark_epi(p, 13);
         epi_bar_sync();
+        if (g == 0) trace_mark_epi(p, 14);
         if (threadIdx.x == 0) {
             tma_store_2d(out_map, buf, p.out_coff + c0, p0);
             tma_store_commit();
@@ -284,6 +300,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
 // ---------------------------------------------------------------------------------------------
 // Tap-per-stage kernel: stride-2 convolutions (parity sub-lattice tensor maps) and channel blocks narrower than 64.
 // ---------------------------------------------------------------------------------------------
+template <bool kMish>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // barriers: full[s] at +8s, empty[s] at +8(stages+s), tmem_full at +16*stages, tmem ptr after it, then scale/bias
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * stages, bar_tmem = bar_base + 16u * stages;
     const uint32_t tmem_slot = bar_tmem + 8u;
-    float* s_sb = reinterpret_cast<float*>(smem_raw + (bar_tmem + 16u - smem_u32(smem_raw)));
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (((bar_tmem + 16u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
 
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             pix = ((long long)img * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
         }
         grid_dep_wait();
-        epilogue_tile(p, tmem_base, warp, n0, pix, valid, s_sb, bar_tmem);
+        epilogue_tile<kMish>(p, tmem_base, warp, n0, pix, valid, s_sb, bar_tmem);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -432,6 +449,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
 // (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
 // ---------------------------------------------------------------------------------------------
+template <bool kMish>
 __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -450,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
     const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
     const uint32_t bar_tmem = bar_emptyB + 8u * p.b_stages;
     const uint32_t tmem_slot = bar_tmem + 8u, flag_slot = tmem_slot + 4u;
-    float* s_sb = reinterpret_cast<float*>(smem_raw + (bar_tmem + 16u - smem_u32(smem_raw)));
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (((bar_tmem + 16u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
 
@@ -604,8 +622,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
         grid_dep_wait();                                       // residual / workspace / output buffers belong to earlier kernels
         if (p.ksplit == 1) {
             if (threadIdx.x == 0 && p.trace) { mbar_wait(bar_tmem, 0); trace_mark(p, 5); }
-            if (p.store_tma) epilogue_tile_tma(p, &maps.a[1], smem_base, tmem_base, warp, n0, p0, pp, valid, s_sb, bar_tmem);
-            else epilogue_tile(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
+            if (p.store_tma)
+                epilogue_tile_tma<kMish>(p, &maps.a[1], smem_base, smem_raw + (smem_base - smem_u32(smem_raw)), tmem_base, warp, n0, p0, pp, valid, s_sb,
+                                  bar_tmem);
+            else epilogue_tile<kMish>(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
             if (threadIdx.x == 0) trace_mark(p, 6);
         } else {
             const int bn = p.block_n;
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
                                 acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
                             }
                         }
-                        finish16(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
+                        finish16<kMish>(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
                     }
                 }
             }
@@ -958,14 +978,18 @@ void conv_tc_trace_dump() {
                 i, g_trace_desc[slot] / 1000000, (g_trace_desc[slot] / 100) % 10000, (g_trace_desc[slot] % 100) * 32, g_trace_shape[slot] / 10000,
                 g_trace_shape[slot] % 10000, (r[8] - t0) * 1e-3, (r[9] - r[8]) * 1e-3, r[1] - r[0], r[3] ? r[3] - r[0] : 0, r[4] ? r[4] - r[0] : 0,
                 r[5] ? r[5] - r[0] : 0, r[6] ? r[6] - r[0] : 0, r[7] - r[0]);
+        if (r[11]) fprintf(stderr, "    epilogue thread 100, group 0: tmem loaded %llu, computed+staged %llu, proxy fence %llu, barrier %llu\n", r[11] - r[0],
+                           r[12] - r[0], r[13] - r[0], r[14] - r[0]);
     }
 }
 
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     ConvTcMaps maps;
@@ -975,9 +999,11 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         static bool attr2_set = false;
         static int use_pdl = 1;
         if (!attr2_set) {
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             use_pdl = env_int("YDST_PDL", 1);
             attr2_set = true;
         }
@@ -1005,7 +1031,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-        YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, maps, prm));
+        if (L.p.act == ACT_MISH) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, maps, prm));
+        else YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false>, maps, prm));
         if (trace_on == 1) {
             unsigned long long h[16];
             YDST_CUDA(cudaStreamSynchronize(stream));
@@ -1018,7 +1045,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         }
         return;
     }
-    conv_tc_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(maps, L.p, L.stages);
+    if (L.p.act == ACT_MISH) conv_tc_kernel<true><<<L.grid, kThreads, L.smem_bytes, stream>>>(maps, L.p, L.stages);
+    else conv_tc_kernel<false><<<L.grid, kThreads, L.smem_bytes, stream>>>(maps, L.p, L.stages);
     YDST_CUDA(cudaGetLastError());
 }
 
