@@ -412,21 +412,21 @@ void launch_transpose(const float* src, float* dst, int rows, int cols, cudaStre
 //   among the scanned columns with the lowest path cost pick the LAST unassigned one in array order,
 //   or, if none is unassigned, the FIRST one.
 // ================================================================================================
+// A scan candidate is (path cost, key): the winner is the lexicographic minimum, with
+//   key = C - 1 - it  for an unassigned column (so the LAST unassigned column in array order wins a tie), and
+//   key = C + it      for an assigned one      (FIRST assigned column, and only if no unassigned column ties) --
+// scipy's selection rule as one integer, which keeps the warp reduction to three shuffles per level.
 struct LsapBest {
     double val;
-    int it;
-    int una;
+    int key;
 };
 __device__ __forceinline__ bool lsap_better(const LsapBest& a, const LsapBest& b) {
-    if (a.val != b.val) return a.val < b.val;
-    if (a.una != b.una) return a.una != 0;
-    return a.una ? a.it > b.it : a.it < b.it;
+    return a.val < b.val || (a.val == b.val && a.key < b.key);
 }
 __device__ __forceinline__ LsapBest lsap_shfl(const LsapBest& v, int o) {
     LsapBest r;
     r.val = __shfl_xor_sync(0xffffffffu, v.val, o);
-    r.it = __shfl_xor_sync(0xffffffffu, v.it, o);
-    r.una = __shfl_xor_sync(0xffffffffu, v.una, o);
+    r.key = __shfl_xor_sync(0xffffffffu, v.key, o);
     return r;
 }
 
@@ -482,14 +482,14 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
             const double mv = s_min, ui = w.u[i];
             const float* crow = cost + (long long)i * C;
             LsapBest best;
-            best.val = CUDART_INF; best.it = 0x7fffffff; best.una = 0;
+            best.val = CUDART_INF; best.key = 0x7fffffff;
             for (int it = tid; it < nrem; it += T) {
                 const int j = w.remaining[it];
                 const double r = mv + (double)crow[j] - ui - w.v[j];
                 double s = w.spc[j];
                 if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
                 LsapBest c;
-                c.val = s; c.it = it; c.una = w.row4col[j] == -1;
+                c.val = s; c.key = w.row4col[j] == -1 ? C - 1 - it : C + it;
                 if (lsap_better(c, best)) best = c;
             }
 #pragma unroll
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                 if (tid < 32) {
                     LsapBest b2;
                     if (tid < T / 32) b2 = s_part[tid];
-                    else { b2.val = CUDART_INF; b2.it = 0x7fffffff; b2.una = 0; }
+                    else { b2.val = CUDART_INF; b2.key = 0x7fffffff; }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const LsapBest other = lsap_shfl(b2, o);
@@ -518,10 +518,11 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                 if (!(best.val < CUDART_INF)) {
                     s_sink = -2;                              // infeasible (cannot happen with finite costs)
                 } else {
-                    const int j = w.remaining[best.it];
+                    const int bit = best.key < C ? C - 1 - best.key : best.key - C;      // position in `remaining`
+                    const int j = w.remaining[bit];
                     if (w.row4col[j] == -1) s_sink = j; else s_i = w.row4col[j];
                     w.SC[j] = 1;
-                    w.remaining[best.it] = w.remaining[nrem - 1];
+                    w.remaining[bit] = w.remaining[nrem - 1];
                     s_nrem = nrem - 1;
                 }
             }

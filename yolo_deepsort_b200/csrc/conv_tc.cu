@@ -464,7 +464,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
-    const uint32_t bar_fullA = bar_base, bar_emptyA = bar_fullA + 8u * p.a_stages;
+    const int nab = k3 ? p.a_boxes : 1;                        // "full" barriers per A stage: one per TMA box of the halo chunk
+    const uint32_t bar_fullA = bar_base, bar_emptyA = bar_fullA + 8u * p.a_stages * nab;
     const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
     const uint32_t bar_tmem = bar_emptyB + 8u * p.b_stages;
     const uint32_t tmem_slot = bar_tmem + 8u, flag_slot = tmem_slot + 4u;
@@ -473,7 +474,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
     while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.a_stages; ++s) { mbar_init(bar_fullA + 8u * s, 1); mbar_init(bar_emptyA + 8u * s, 1); }
+        for (int s = 0; s < p.a_stages * nab; ++s) mbar_init(bar_fullA + 8u * s, 1);
+        for (int s = 0; s < p.a_stages; ++s) mbar_init(bar_emptyA + 8u * s, 1);
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
         mbar_init(bar_tmem, 1);
         fence_barrier_init();
@@ -522,12 +524,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
             };
             auto load_a = [&](int i) {
                 mbar_wait_hot(bar_emptyA + 8u * sa, pha);
-                const uint32_t full = bar_fullA + 8u * sa;
+                const uint32_t full = bar_fullA + 8u * (uint32_t)(sa * nab);
                 const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
                 if (k3) {
-                    mbar_arrive_expect_tx(full, (uint32_t)(p.a_box_rows * p.a_boxes) * 128u);
-                    for (int b = 0; b < p.a_boxes; ++b)
-                        tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full, (cb0 + i) * 64, p0 - p.halo + b * p.a_box_rows);
+                    // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
+                    for (int b = 0; b < p.a_boxes; ++b) {
+                        mbar_arrive_expect_tx(full + 8u * b, (uint32_t)p.a_box_rows * 128u);
+                        tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
+                                    p0 - p.halo + b * p.a_box_rows);
+                    }
                 } else {
                     mbar_arrive_expect_tx(full, a_stage_bytes);
                     tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * p.tpb);
@@ -558,14 +563,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0, acc = 0;
             for (int i = 0; i < nmacro; ++i) {
-                mbar_wait_hot(bar_fullA + 8u * sa, pha);
+                const uint32_t fullA = bar_fullA + 8u * (uint32_t)(sa * nab);
+                mbar_wait_hot(fullA, pha);
                 const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
                 if (k3) {
                     const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;        // 16-byte units: next filter row
                     uint32_t a_lo = a_lo0;
-                    int t_in = 0;
+                    int t_in = 0, box_ready = 0;
                     uint32_t b_lo = 0;
                     for (int r = 0; r < 3; ++r, a_lo += row_step) {
+                        // filter row r reads chunk rows up to r*Wp + 2 + 127
+                        const int need = min(p.a_boxes - 1, (r * p.in_Wp + 129) / p.a_box_rows);
+                        while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
                         for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
                             if (t_in == 0) {
                                 mbar_wait_hot(bar_fullB + 8u * sb, phb);
@@ -748,7 +757,7 @@ static int env_int(const char* name, int dflt) {
 // Small-M layers may split K over channel blocks (grid.z); the fp32 partials then take a round trip through the workspace.
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets) {
     const int kSms = 148;
-    const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 150.0, kClkPerUs = 1900.0;
+    const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 600.0, kClkPerUs = 1900.0;
     const int chunk_bytes = (a_rows * 128 + 1023) & ~1023;
     const bool tma_store_ok = cout16 % 64 == 0;
     ConvTiling best{};
@@ -767,10 +776,13 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
             if (ks > 16) continue;
             const long long ctas = tiles * ks;
             const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = 108 * 1024;
-            const int tpb_opts3[3] = {9, 3, 1}, tpb_opts1[3] = {4, 2, 1};
+            // weight-stage granularity: one TMA instruction costs the producer thread ~200 clocks to issue, so boxes below
+            // ~16 KB make the PRODUCER the bottleneck (measured: tpb = 1 everywhere cost 15 % end to end); the step term below
+            // steers towards multi-slice stages, the first-stage term keeps them from growing without bound
+            const int tpb_opts3[3] = {9, 3, 1}, tpb_opts1[3] = {8, 4, 2};
             for (int oi = 0; oi < 3; ++oi) {
-                const int tpb = taps == 9 ? tpb_opts3[oi] : tpb_opts1[oi];
-                if (taps == 1 && tpb > cps) continue;
+                const int tpb = taps == 9 ? tpb_opts3[oi] : std::min(tpb_opts1[oi], cps);
+                if (taps == 1 && oi > 0 && tpb == std::min(tpb_opts1[oi - 1], cps)) continue;     // same as the previous option
                 const int nmacro = taps == 9 ? cps : (cps + tpb - 1) / tpb;
                 const int nbs = taps == 9 ? 9 / tpb : 1;
                 const int total_b = nmacro * nbs;
@@ -782,7 +794,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                     const int budget = pass == 0 ? budget_2 : budget_max;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
                     int b_stages = std::min(std::min(8, total_b), (budget - fixed) / b_stage);
-                    if (b_stages < std::min(2, total_b)) continue;
+                    if (b_stages < 1) continue;
                     int smem = fixed + b_stages * b_stage;
                     smem = std::max(smem, 36 * 1024);             // the TMA-store epilogue stages two 16 KB groups at the start of smem
                     const int occ = smem <= 112 * 1024 ? 2 : 1;
@@ -806,6 +818,10 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
             }
         }
     }
+    if (getenv("YDST_DEBUG_PLAN"))
+        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d model %.1f us\n", m_tiles,
+                cout16, taps, cin_blocks, best.bn, best.ksplit, best.cbs_per_split, best.tpb, best.a_stages, best.b_stages, best.smem_bytes,
+                best.occupancy, best.model_us);
     return best;
 }
 

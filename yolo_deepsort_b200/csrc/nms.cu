@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
                                                         const unsigned long long* __restrict__ mask, int words, int max_det,
                                                         float* __restrict__ dets, int* __restrict__ n_out, int* __restrict__ overflow) {
     extern __shared__ unsigned long long smask[];
+    __shared__ int s_kept[1024];               // max_det <= 1024 (Nms::init)
     const int total = *count;
     const int n = min(total, cap);
     const int nw = (n + 63) >> 6;
@@ -118,11 +119,7 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
         const unsigned long long mine = removed[w >> 5];
         const unsigned long long word = __shfl_sync(0xffffffffu, mine, w & 31);
         if ((word >> (i & 63)) & 1ull) continue;
-        if (kept < max_det && lane < 6) {
-            const NmsCand c = sorted[i];
-            const float v = lane == 0 ? c.x1 : lane == 1 ? c.y1 : lane == 2 ? c.x2 : lane == 3 ? c.y2 : lane == 4 ? c.score : c.cls;
-            dets[kept * 6 + lane] = v;
-        }
+        if (kept < max_det && lane == 0) s_kept[kept] = i;       // rows are gathered after the sweep, off the dependent chain
         ++kept;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -130,7 +127,14 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
             if (ww < nw) removed[s] |= staged ? smask[i * nw + ww] : mask[(long long)i * words + ww];
         }
     }
-    if (lane == 0) *n_out = min(kept, max_det);
+    const int nk = min(kept, max_det);
+    if (lane == 0) *n_out = nk;
+    __syncwarp();
+    for (int e = lane; e < nk * 6; e += 32) {
+        const int k = e / 6, f = e - k * 6;
+        const NmsCand& c = sorted[s_kept[k]];
+        dets[e] = f == 0 ? c.x1 : f == 1 ? c.y1 : f == 2 ? c.x2 : f == 3 ? c.y2 : f == 4 ? c.score : c.cls;
+    }
 }
 
 // ---- 5. hand-off: resize_boxes, xyxy -> tlwh, class mask; order preserved (one block, ballot scan) ----
