@@ -32,6 +32,10 @@ CASES = [
     ("3x3_s1_152_wide_halo", 1, 152, 152, 64, 128, 3, 1, True, 1, 0, False),
     ("1x1_s1_768_concat_k", 1, 38, 38, 768, 256, 1, 1, True, 1, 0, False),
     ("reid_64x32_batch3", 3, 64, 32, 64, 64, 3, 1, True, 3, 2, False),
+    ("persistent_reid_64x32_batch12", 12, 64, 32, 64, 64, 3, 1, True, 3, 2, False),
+    ("persistent_1x1_152", 1, 152, 152, 128, 64, 1, 1, True, 1, 0, False),
+    ("persistent_two_n_tiles_batch20", 20, 32, 16, 128, 256, 3, 1, True, 1, 1, False),
+    ("persistent_f32_out", 2, 152, 152, 64, 48, 1, 1, False, 0, 0, True),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),

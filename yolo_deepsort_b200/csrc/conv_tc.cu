@@ -197,14 +197,14 @@ __device__ __forceinline__ void stage_scale_bias(const ConvTcParams& p, int n0, 
 
 template <bool kMish>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tmem_base, int warp, int n0, long long pix, bool valid,
-                                              const float* s_sb, uint32_t bar_tmem) {
+                                              const float* s_sb, uint32_t bar_tmem, uint32_t parity = 0, uint32_t bar_release = 0) {
     const int gw = p.block_n < 64 ? p.block_n : 64;
     const int ngroups = p.block_n / gw;
     uint4 rcur[8], rnext[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) rcur[q] = rnext[q] = make_uint4(0, 0, 0, 0);
     load_res_group(p, pix, n0, gw, valid, rcur);
-    mbar_wait(bar_tmem, 0);
+    mbar_wait(bar_tmem, parity);
     tcgen05_fence_after();
     for (int g = 0; g < ngroups; ++g) {
         const int c0 = n0 + g * gw;
@@ -231,6 +231,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
     }
+    if (bar_release) {                                             // the accumulator has been read: hand it back to the MMA issuer
+        tcgen05_fence_before();
+        mbar_arrive(bar_release);
+    }
 }
 
 // TMA-store variant (halo kernel, cout % 64 == 0, fp16 output): every thread-per-row global store of the direct epilogue
@@ -241,16 +245,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
 template <bool kMish>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* out_map, uint32_t stage_smem,
                                                   unsigned char* stage_ptr, uint32_t tmem_base, int warp, int n0, int p0, long long pix,
-                                                  bool valid, const float* s_sb, uint32_t bar_tmem) {
+                                                  bool valid, const float* s_sb, uint32_t bar_tmem, uint32_t parity, uint32_t bar_release,
+                                                  int& stores) {
     const int ngroups = p.block_n >> 6;
     const int row = threadIdx.x;                                   // 0..127
     uint4 rcur[8], rnext[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) rcur[q] = rnext[q] = make_uint4(0, 0, 0, 0);
     load_res_group(p, pix, n0, 64, valid, rcur);
-    mbar_wait(bar_tmem, 0);
+    mbar_wait(bar_tmem, parity);
     tcgen05_fence_after();
-    for (int g = 0; g < ngroups; ++g) {
+    for (int g = 0; g < ngroups; ++g, ++stores) {
         const int c0 = n0 + g * 64;
         if (c0 >= p.cout) break;
         __syncwarp();
@@ -259,13 +264,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
         for (int sub = 0; sub < 4; ++sub)
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 64 + sub * 16), v[sub]);
         if (g + 1 < ngroups && c0 + 64 < p.cout) load_res_group(p, pix, c0 + 64, 64, valid, rnext);
-        if (g >= 2) {                                              // the buffer about to be refilled was read by store g-2
+        if (stores >= 2) {                                         // the buffer about to be refilled was read two stores ago
             if (threadIdx.x == 0) tma_store_wait_read<1>();
             epi_bar_sync();
         }
         tcgen05_wait_ld();
+        if (bar_release && (g + 1 == ngroups || c0 + 64 >= p.cout)) {   // last read of this accumulator: hand it back to the MMA issuer
+            tcgen05_fence_before();
+            mbar_arrive(bar_release);
+        }
         if (g == 0) trace_mark_epi(p, 11);
-        const uint32_t buf = stage_smem + (uint32_t)(g & 1) * (kBlockM * 128u);
+        const uint32_t buf = stage_smem + (uint32_t)(stores & 1) * (kBlockM * 128u);
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
             uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
@@ -277,7 +286,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
                 compute16<kMish>(p, acc, s_sb + cl, s_sb + p.block_n + cl, rcur[2 * sub], rcur[2 * sub + 1], o);
                 pack16(o, w0, w1);
             }
-            uint4* rbase = reinterpret_cast<uint4*>(stage_ptr + (size_t)(g & 1) * (kBlockM * 128u) + (size_t)row * 128u);
+            uint4* rbase = reinterpret_cast<uint4*>(stage_ptr + (size_t)(stores & 1) * (kBlockM * 128u) + (size_t)row * 128u);
             const int x = row & 7;
             rbase[(2 * sub) ^ x] = w0;
             rbase[(2 * sub + 1) ^ x] = w1;
@@ -294,7 +303,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
     }
-    if (threadIdx.x == 0) tma_store_wait_read<0>();                // smem must outlive the bulk reads; the writes are complete at grid end
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,8 +457,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
 // (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
 // ---------------------------------------------------------------------------------------------
-template <bool kMish>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
+template <bool kMish, bool kPers>
+__global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -461,23 +469,27 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
     const uint32_t a_stage_bytes = k3 ? (((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u) : (uint32_t)p.tpb * (kBlockM * 128u);
     const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
-    const uint32_t a_base = smem_base;
+    // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
+    // (they are being refilled for the next tile while the epilogue runs); otherwise the staging aliases the dead stages
+    const uint32_t stage_area = (kPers && p.store_tma) ? 2u * kBlockM * 128u : 0u;
+    const uint32_t a_base = smem_base + stage_area;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
     const int nab = k3 ? p.a_boxes : 1;                        // "full" barriers per A stage: one per TMA box of the halo chunk
     const uint32_t bar_fullA = bar_base, bar_emptyA = bar_fullA + 8u * p.a_stages * nab;
     const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
-    const uint32_t bar_tmem = bar_emptyB + 8u * p.b_stages;
-    const uint32_t tmem_slot = bar_tmem + 8u, flag_slot = tmem_slot + 4u;
-    float* s_sb = reinterpret_cast<float*>(smem_raw + (((bar_tmem + 16u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
+    const uint32_t bar_tfull = bar_emptyB + 8u * p.b_stages;   // [2] accumulator complete
+    const uint32_t bar_tempty = bar_tfull + 16u;               // [2] accumulator drained by the epilogue (128 arrivals)
+    const uint32_t tmem_slot = bar_tempty + 16u, flag_slot = tmem_slot + 4u;
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.block_n) tmem_cols <<= 1;
+    while ((int)tmem_cols < p.block_n * (kPers ? 2 : 1)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_stages * nab; ++s) mbar_init(bar_fullA + 8u * s, 1);
         for (int s = 0; s < p.a_stages; ++s) mbar_init(bar_emptyA + 8u * s, 1);
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
-        mbar_init(bar_tmem, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, 128); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -498,59 +510,72 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int n0 = blockIdx.y * p.block_n;
-    const int p0 = blockIdx.x * kBlockM;
     const int cb0 = blockIdx.z * p.cbs_per_split;
     const int ncb = min(p.cbs_per_split, p.cin_blocks - cb0);
     // macro step = one A stage: a channel block with all its taps (3x3) or a group of tpb channel blocks (1x1)
     const int nmacro = k3 ? ncb : (ncb + p.tpb - 1) / p.tpb;
     const int nbs = k3 ? 9 / p.tpb : 1;                        // weight stages per macro step
+    // tile iteration: a normal launch owns tile (blockIdx.x, blockIdx.y); a persistent CTA strides over all tiles, M fastest
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    auto tile_at = [&](int it, int& tm, int& tn) -> bool {
+        if (!kPers) { tm = blockIdx.x; tn = blockIdx.y; return it == 0; }
+        const int t = blockIdx.x + it * gridDim.x;
+        if (t >= total_tiles) return false;
+        tm = t % p.m_tiles; tn = t / p.m_tiles;
+        return true;
+    };
 
     if (warp == 4) {
         if (elect_one()) {
             // ================= TMA producer =================
             int sa = 0, sb = 0;
             uint32_t pha = 1, phb = 1;
-            int jm = 0, js = 0;                                // next weight stage to issue: macro step jm, sub-stage js
-            const int total_b = nmacro * nbs;
-            auto issue_b = [&]() {
-                mbar_wait_hot(bar_emptyB + 8u * sb, phb);
-                const uint32_t full = bar_fullB + 8u * sb;
-                mbar_arrive_expect_tx(full, b_stage_bytes);
-                if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * p.tpb);
-                else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * p.tpb);
-                if (++js == nbs) { js = 0; ++jm; }
-                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
-            };
-            auto load_a = [&](int i) {
-                mbar_wait_hot(bar_emptyA + 8u * sa, pha);
-                const uint32_t full = bar_fullA + 8u * (uint32_t)(sa * nab);
-                const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
-                if (k3) {
-                    // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
-                    for (int b = 0; b < p.a_boxes; ++b) {
-                        mbar_arrive_expect_tx(full + 8u * b, (uint32_t)p.a_box_rows * 128u);
-                        tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
-                                    p0 - p.halo + b * p.a_box_rows);
+            int tm, tn;
+            for (int it = 0; tile_at(it, tm, tn); ++it) {
+                const int p0 = tm * kBlockM, n0 = tn * p.block_n;
+                int jm = 0, js = 0;                            // next weight stage to issue: macro step jm, sub-stage js
+                const int total_b = nmacro * nbs;
+                auto issue_b = [&]() {
+                    mbar_wait_hot(bar_emptyB + 8u * sb, phb);
+                    const uint32_t full = bar_fullB + 8u * sb;
+                    mbar_arrive_expect_tx(full, b_stage_bytes);
+                    if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * p.tpb);
+                    else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * p.tpb);
+                    if (++js == nbs) { js = 0; ++jm; }
+                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                };
+                auto load_a = [&](int i) {
+                    mbar_wait_hot(bar_emptyA + 8u * sa, pha);
+                    const uint32_t full = bar_fullA + 8u * (uint32_t)(sa * nab);
+                    const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
+                    if (k3) {
+                        // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
+                        for (int b = 0; b < p.a_boxes; ++b) {
+                            mbar_arrive_expect_tx(full + 8u * b, (uint32_t)p.a_box_rows * 128u);
+                            tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
+                                        p0 - p.halo + b * p.a_box_rows);
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(full, a_stage_bytes);
+                        tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * p.tpb);
                     }
-                } else {
-                    mbar_arrive_expect_tx(full, a_stage_bytes);
-                    tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * p.tpb);
+                    if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+                };
+                int issued = 0;
+                if (it == 0) {
+                    // weights never depend on the previous kernel: queue them before waiting on the grid dependency, so that
+                    // under programmatic dependent launch they stream in while the producer of our input is still draining
+                    const int pre = p.pdl ? p.b_stages : 1;
+                    for (; issued < total_b && issued < pre; ++issued) issue_b();
+                    grid_dep_wait();                           // the activations are the previous kernel's output
+                    trace_mark(p, 2);
                 }
-                if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
-            };
-            // weights never depend on the previous kernel: queue them before waiting on the grid dependency, so that under
-            // programmatic dependent launch they stream in while the producer of our input is still draining
-            int issued = 0;
-            const int pre = p.pdl ? p.b_stages : 1;            // without an overlapping predecessor, get the first chunk moving early
-            for (; issued < total_b && issued < pre; ++issued) issue_b();
-            grid_dep_wait();                                   // the activations are the previous kernel's output
-            trace_mark(p, 2);
-            load_a(0);
-            for (int i = 0; i < nmacro; ++i) {
-                if (p.a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
-                for (; issued < (i + 1) * nbs; ++issued) issue_b();
-                if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
+                load_a(0);
+                for (int i = 0; i < nmacro; ++i) {
+                    if (p.a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
+                    for (; issued < (i + 1) * nbs; ++issued) issue_b();
+                    if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
+                }
             }
             prefetch_next_weights(p);
         }
@@ -561,139 +586,161 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc2_kernel(const __grid_cons
             const uint32_t hi = desc_hi(128);
             const uint32_t b_tile16 = b_tile_bytes >> 4;
             int sa = 0, sb = 0;
-            uint32_t pha = 0, phb = 0, acc = 0;
-            for (int i = 0; i < nmacro; ++i) {
-                const uint32_t fullA = bar_fullA + 8u * (uint32_t)(sa * nab);
-                mbar_wait_hot(fullA, pha);
-                const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
-                if (k3) {
-                    const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;        // 16-byte units: next filter row
-                    uint32_t a_lo = a_lo0;
-                    int t_in = 0, box_ready = 0;
-                    uint32_t b_lo = 0;
-                    for (int r = 0; r < 3; ++r, a_lo += row_step) {
-                        // filter row r reads chunk rows up to r*Wp + 2 + 127
-                        const int need = min(p.a_boxes - 1, (r * p.in_Wp + 129) / p.a_box_rows);
-                        while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
-                        for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
-                            if (t_in == 0) {
-                                mbar_wait_hot(bar_fullB + 8u * sb, phb);
-                                tcgen05_fence_after();
-                                if (acc == 0) trace_mark(p, 3);
-                                b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
-                            }
-                            uint32_t hi_a = hi;
-                            if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
-                            umma_f16_lh(tmem_base, a_lo, b_lo, hi_a, idesc, acc);
-                            umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
-                            umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
-                            umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
-                            acc = 1u;
-                            b_lo += b_tile16;
-                            if (++t_in == p.tpb) {
-                                t_in = 0;
-                                umma_commit(bar_emptyB + 8u * sb);
-                                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+            uint32_t pha = 0, phb = 0;
+            int tm, tn;
+            for (int it = 0; tile_at(it, tm, tn); ++it) {
+                const int ab = it & 1;                         // accumulator buffer
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n);
+                if (kPers) mbar_wait_hot(bar_tempty + 8u * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                uint32_t acc = 0;
+                for (int i = 0; i < nmacro; ++i) {
+                    const uint32_t fullA = bar_fullA + 8u * (uint32_t)(sa * nab);
+                    mbar_wait_hot(fullA, pha);
+                    const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
+                    if (k3) {
+                        const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;        // 16-byte units: next filter row
+                        uint32_t a_lo = a_lo0;
+                        int t_in = 0, box_ready = 0;
+                        uint32_t b_lo = 0;
+                        for (int r = 0; r < 3; ++r, a_lo += row_step) {
+                            // filter row r reads chunk rows up to r*Wp + 2 + 127
+                            const int need = min(p.a_boxes - 1, (r * p.in_Wp + 129) / p.a_box_rows);
+                            while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
+                            for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
+                                if (t_in == 0) {
+                                    mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                                    tcgen05_fence_after();
+                                    if (acc == 0 && it == 0) trace_mark(p, 3);
+                                    b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
+                                }
+                                uint32_t hi_a = hi;
+                                if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
+                                umma_f16_lh(tmem_d, a_lo, b_lo, hi_a, idesc, acc);
+                                umma_f16_lh(tmem_d, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
+                                umma_f16_lh(tmem_d, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
+                                umma_f16_lh(tmem_d, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                                acc = 1u;
+                                b_lo += b_tile16;
+                                if (++t_in == p.tpb) {
+                                    t_in = 0;
+                                    umma_commit(bar_emptyB + 8u * sb);
+                                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                                }
                             }
                         }
+                    } else {
+                        mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                        tcgen05_fence_after();
+                        if (acc == 0 && it == 0) trace_mark(p, 3);
+                        uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
+                        const int nsl = min(p.tpb, ncb - i * p.tpb);                  // the last group of a split may be short
+                        for (int t = 0; t < nsl; ++t, a_lo += (kBlockM * 128u) >> 4, b_lo += b_tile16) {
+                            umma_f16_lh(tmem_d, a_lo, b_lo, hi, idesc, acc);
+                            umma_f16_lh(tmem_d, a_lo + 2u, b_lo + 2u, hi, idesc, 1u);
+                            umma_f16_lh(tmem_d, a_lo + 4u, b_lo + 4u, hi, idesc, 1u);
+                            umma_f16_lh(tmem_d, a_lo + 6u, b_lo + 6u, hi, idesc, 1u);
+                            acc = 1u;
+                        }
+                        umma_commit(bar_emptyB + 8u * sb);
+                        if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
                     }
-                } else {
-                    mbar_wait_hot(bar_fullB + 8u * sb, phb);
-                    tcgen05_fence_after();
-                    if (acc == 0) trace_mark(p, 3);
-                    uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
-                    const int nsl = min(p.tpb, ncb - i * p.tpb);                  // the last group of a split may be short
-                    for (int t = 0; t < nsl; ++t, a_lo += (kBlockM * 128u) >> 4, b_lo += b_tile16) {
-                        umma_f16_lh(tmem_base, a_lo, b_lo, hi, idesc, acc);
-                        umma_f16_lh(tmem_base, a_lo + 2u, b_lo + 2u, hi, idesc, 1u);
-                        umma_f16_lh(tmem_base, a_lo + 4u, b_lo + 4u, hi, idesc, 1u);
-                        umma_f16_lh(tmem_base, a_lo + 6u, b_lo + 6u, hi, idesc, 1u);
-                        acc = 1u;
-                    }
-                    umma_commit(bar_emptyB + 8u * sb);
-                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                    umma_commit(bar_emptyA + 8u * sa);
+                    if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
                 }
-                umma_commit(bar_emptyA + 8u * sa);
-                if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+                umma_commit(bar_tfull + 8u * ab);
+                if (it == 0) trace_mark(p, 4);
             }
-            umma_commit(bar_tmem);
-            trace_mark(p, 4);
         }
     } else {
         // ================= epilogue =================
-        stage_scale_bias(p, n0, s_sb);
         const int row = threadIdx.x;
-        const long long pp = (long long)p0 + row;
         const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
-        const int rem = (int)(pp % HpWp);
-        const int y = rem / Wp, x = rem - y * Wp;
-        const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
-        grid_dep_wait();                                       // residual / workspace / output buffers belong to earlier kernels
-        if (p.ksplit == 1) {
-            if (threadIdx.x == 0 && p.trace) { mbar_wait(bar_tmem, 0); trace_mark(p, 5); }
-            if (p.store_tma)
-                epilogue_tile_tma<kMish>(p, &maps.a[1], smem_base, smem_raw + (smem_base - smem_u32(smem_raw)), tmem_base, warp, n0, p0, pp, valid, s_sb,
-                                  bar_tmem);
-            else epilogue_tile<kMish>(p, tmem_base, warp, n0, pp, valid, s_sb, bar_tmem);
-            if (threadIdx.x == 0) trace_mark(p, 6);
-        } else {
-            const int bn = p.block_n;
-            const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
-            float* wtile = p.ws + tile * p.ksplit * (kBlockM * bn);            // [split][row][bn] fp32
-            float* mine = wtile + ((long long)blockIdx.z * kBlockM + row) * bn;
-            mbar_wait(bar_tmem, 0);
-            tcgen05_fence_after();
-            for (int ch = 0; ch < (bn >> 4); ++ch) {
-                if (n0 + ch * 16 >= p.cout) break;
-                __syncwarp();
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), v);
-                tcgen05_wait_ld();
-                if (!valid) continue;
-                float4* dst = reinterpret_cast<float4*>(mine + ch * 16);
+        int stores = 0, staged_tn = -1;
+        int tm, tn;
+        for (int it = 0; tile_at(it, tm, tn); ++it) {
+            const int p0 = tm * kBlockM, n0 = tn * p.block_n;
+            const int ab = it & 1;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n);
+            const uint32_t bar_full = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
+            const uint32_t bar_rel = kPers ? bar_tempty + 8u * ab : 0u;
+            if (tn != staged_tn) {                             // M runs fastest: the column block (and its scale/bias) rarely changes
+                if (it > 0) epi_bar_sync();                    // everyone is done with the previous tile's scale/bias
+                stage_scale_bias(p, n0, s_sb);
+                staged_tn = tn;
+            }
+            const long long pp = (long long)p0 + row;
+            const int rem = (int)(pp % HpWp);
+            const int y = rem / Wp, x = rem - y * Wp;
+            const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
+            if (it == 0) grid_dep_wait();                      // residual / workspace / output buffers belong to earlier kernels
+            if (p.ksplit == 1) {
+                if (it == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
+                if (p.store_tma)
+                    epilogue_tile_tma<kMish>(p, &maps.a[1], smem_base, smem_raw + (smem_base - smem_u32(smem_raw)), tmem_d, warp, n0, p0, pp, valid,
+                                             s_sb, bar_full, par, bar_rel, stores);
+                else epilogue_tile<kMish>(p, tmem_d, warp, n0, pp, valid, s_sb, bar_full, par, bar_rel);
+                if (it == 0 && threadIdx.x == 0) trace_mark(p, 6);
+            } else {
+                const int bn = p.block_n;
+                const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+                float* wtile = p.ws + tile * p.ksplit * (kBlockM * bn);            // [split][row][bn] fp32
+                float* mine = wtile + ((long long)blockIdx.z * kBlockM + row) * bn;
+                mbar_wait(bar_full, 0);
+                tcgen05_fence_after();
+                for (int ch = 0; ch < (bn >> 4); ++ch) {
+                    if (n0 + ch * 16 >= p.cout) break;
+                    __syncwarp();
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), v);
+                    tcgen05_wait_ld();
+                    if (!valid) continue;
+                    float4* dst = reinterpret_cast<float4*>(mine + ch * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                                __uint_as_float(v[4 * q + 3])));
-            }
-            __threadfence();
-            epi_bar_sync();
-            if (threadIdx.x == 0) {
-                const int t = atomicAdd(p.tickets + tile, 1);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(flag_slot), "r"(t) : "memory");
-            }
-            epi_bar_sync();
-            int ticket;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ticket) : "r"(flag_slot) : "memory");
-            if (ticket == p.ksplit - 1) {                              // last arrival: every partial of this tile is visible
+                    for (int q = 0; q < 4; ++q)
+                        __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                    __uint_as_float(v[4 * q + 3])));
+                }
                 __threadfence();
-                if (threadIdx.x == 0) p.tickets[tile] = 0;             // self-reset for the next launch
-                if (valid) {
-                    const float* rowp = wtile + (long long)row * bn;
-                    for (int ch = 0; ch < (bn >> 4); ++ch) {
-                        const int c = n0 + ch * 16;
-                        if (c >= p.cout) break;
-                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-                        if (p.res_mode) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pp * p.res_ctot + p.res_coff + c);
-                            r0 = __ldg(rp); r1 = __ldg(rp + 1);
-                        }
-                        float acc[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-                        for (int z = 0; z < p.ksplit; ++z) {           // fixed order: the sum does not depend on arrival order
-                            const float4* src = reinterpret_cast<const float4*>(rowp + (long long)z * kBlockM * bn + ch * 16);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 t = __ldcg(src + q);
-                                acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+                epi_bar_sync();
+                if (threadIdx.x == 0) {
+                    const int t = atomicAdd(p.tickets + tile, 1);
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(flag_slot), "r"(t) : "memory");
+                }
+                epi_bar_sync();
+                int ticket;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ticket) : "r"(flag_slot) : "memory");
+                if (ticket == p.ksplit - 1) {                              // last arrival: every partial of this tile is visible
+                    __threadfence();
+                    if (threadIdx.x == 0) p.tickets[tile] = 0;             // self-reset for the next launch
+                    if (valid) {
+                        const float* rowp = wtile + (long long)row * bn;
+                        for (int ch = 0; ch < (bn >> 4); ++ch) {
+                            const int c = n0 + ch * 16;
+                            if (c >= p.cout) break;
+                            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                            if (p.res_mode) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(p.res + pp * p.res_ctot + p.res_coff + c);
+                                r0 = __ldg(rp); r1 = __ldg(rp + 1);
                             }
+                            float acc[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                            for (int z = 0; z < p.ksplit; ++z) {           // fixed order: the sum does not depend on arrival order
+                                const float4* src = reinterpret_cast<const float4*>(rowp + (long long)z * kBlockM * bn + ch * 16);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 t = __ldcg(src + q);
+                                    acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+                                }
+                            }
+                            finish16<kMish>(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
                         }
-                        finish16<kMish>(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
                     }
                 }
             }
         }
+        if (p.store_tma && threadIdx.x == 0) tma_store_wait_read<0>();    // smem must outlive the bulk reads; writes are complete at grid end
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -790,15 +837,23 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                 const int b_stage = tpb * bn * 128;
                 const int a_stages = std::min(nmacro, taps == 9 ? 2 : 4);
                 const int fixed = a_stages * a_stage + 4096;
-                for (int pass = 0; pass < 2; ++pass) {           // pass 0: leave room for a second CTA on the SM; pass 1: whole SM
-                    const int budget = pass == 0 ? budget_2 : budget_max;
+                // pass 0: leave room for a second CTA on the SM; pass 1: whole SM; pass 2: persistent -- one CTA per SM loops over
+                // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const bool pers = pass == 2;
+                    if (pers && (ks > 1 || tiles <= kSms || bn > 256 / 1 || !env_int("YDST_PERSISTENT", 1))) continue;
+                    const int staging = pers ? 32 * 1024 : 0;
+                    const int budget = (pass == 0 ? budget_2 : budget_max) - staging;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
-                    int b_stages = std::min(std::min(8, total_b), (budget - fixed) / b_stage);
-                    if (b_stages < 1) continue;
-                    int smem = fixed + b_stages * b_stage;
+                    // a persistent CTA prefetches the next tile's operands while the current one computes: two stages of each at least
+                    const int a_st = pers ? std::max(2, a_stages) : a_stages;
+                    const int fixed_p = a_st * a_stage + 4096;
+                    int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
+                    if (b_stages < (pers ? 2 : 1)) continue;
+                    int smem = fixed_p + b_stages * b_stage + staging;
                     smem = std::max(smem, 36 * 1024);             // the TMA-store epilogue stages two 16 KB groups at the start of smem
-                    const int occ = smem <= 112 * 1024 ? 2 : 1;
-                    const double inflight = (double)a_stages * a_stage + (double)b_stages * b_stage;
+                    const int occ = (!pers && smem <= 112 * 1024) ? 2 : 1;
+                    const double inflight = (double)a_st * a_stage + (double)b_stages * b_stage;
                     const double rate = std::min(kFill, inflight / kLat);
                     const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * 128.0) + (double)taps * bn * 128);
                     const double mma = (double)cps * taps * 4 * std::max(16.0, bn / 2.0);
@@ -808,20 +863,22 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                     const double epi = 700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0);
                     const double per_sm = std::ceil((double)ctas / kSms);
                     double t = kSetup + kFirst + per_sm * main_clk + std::ceil(per_sm / occ) * epi;
+                    if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, epi) + epi;   // front paid once, epilogues hidden
+                    else if (per_sm > 1) t += (per_sm - 1) / occ * (kSetup + kFirst);          // every further wave pays the front again
                     if (ks > 1) t += 1500.0 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / 30.0;
                     t /= kClkPerUs;
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
-                        best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_stages;
-                        best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t;
+                        best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
+                        best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
                     }
                 }
             }
         }
     }
     if (getenv("YDST_DEBUG_PLAN"))
-        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d model %.1f us\n", m_tiles,
+        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d pers %d model %.1f us\n", m_tiles,
                 cout16, taps, cin_blocks, best.bn, best.ksplit, best.cbs_per_split, best.tpb, best.a_stages, best.b_stages, best.smem_bytes,
-                best.occupancy, best.model_us);
+                best.occupancy, best.persistent, best.model_us);
     return best;
 }
 
@@ -885,9 +942,12 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             }
             p.block_n = t.bn; p.ksplit = t.ksplit; p.cbs_per_split = t.cbs_per_split; p.a_stages = t.a_stages; p.b_stages = t.b_stages;
             p.tpb = t.tpb;
+            p.m_tiles = m_tiles; p.n_tiles = (p.cout + t.bn - 1) / t.bn;
+            p.persistent = t.persistent;
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
             p.store_tma = (!out_f32 && p.cout % 64 == 0 && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
+            if (t.persistent && !p.store_tma) t.smem_bytes -= 32 * 1024;   // no staging area needed
             const int K = R * S * in.C;
             if (R == 3) {
                 cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -917,10 +977,11 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             L.stages = 0;
             L.smem_bytes = t.smem_bytes + 1024;
             L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + t.bn - 1) / t.bn), (unsigned)t.ksplit);
+            if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
             if (getenv("YDST_DEBUG_PLAN"))
-                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d model %.1fus\n",
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d model %.1fus\n",
                         R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.tpb, t.a_stages, t.b_stages,
-                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, t.model_us);
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, t.model_us);
             return;
         }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1015,11 +1076,13 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         static bool attr2_set = false;
         static int use_pdl = 1;
         if (!attr2_set) {
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            YDST_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            const void* fns[4] = {(const void*)conv_tc2_kernel<false, false>, (const void*)conv_tc2_kernel<false, true>,
+                                  (const void*)conv_tc2_kernel<true, false>, (const void*)conv_tc2_kernel<true, true>};
+            for (const void* fn : fns) {
+                YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
+                YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
             use_pdl = env_int("YDST_PDL", 1);
             attr2_set = true;
         }
@@ -1047,8 +1110,11 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-        if (L.p.act == ACT_MISH) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, maps, prm));
-        else YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false>, maps, prm));
+        const bool mish = L.p.act == ACT_MISH, pers = L.p.persistent != 0;
+        if (mish && pers) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true>, maps, prm));
+        else if (mish) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false>, maps, prm));
+        else if (pers) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true>, maps, prm));
+        else YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false>, maps, prm));
         if (trace_on == 1) {
             unsigned long long h[16];
             YDST_CUDA(cudaStreamSynchronize(stream));
