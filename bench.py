@@ -256,10 +256,16 @@ def run_ours(args):
     barrier(device); torch.cuda.synchronize()
     clocks.start()
     launches0 = L.ydst_launch_count()
+    # software-pipelined steady state (ydst_pipeline_submit/_collect): the detector half of frame t+1 is enqueued before the
+    # ReID + association half of frame t is collected; exactly K frames are submitted AND collected inside the timed region
     e0.record()
-    for _ in range(K):
-        tracks, dets = pipe.step(dev[W.clip_index(t)]); t += 1
-        n_dets.append(len(dets)); n_trk.append(0 if tracks is None else len(tracks))
+    for i in range(K):
+        pipe.submit(dev[W.clip_index(t)]); t += 1
+        if i > 0:
+            tracks, dets = pipe.collect()
+            n_dets.append(len(dets)); n_trk.append(0 if tracks is None else len(tracks))
+    tracks, dets = pipe.collect()
+    n_dets.append(len(dets)); n_trk.append(0 if tracks is None else len(tracks))
     e1.record()
     torch.cuda.synchronize()
     launches = L.ydst_launch_count() - launches0
@@ -269,9 +275,13 @@ def run_ours(args):
     d2h = 0
     barrier(device); torch.cuda.synchronize()
     e0.record()
-    for _ in range(K):
-        tracks, dets = pipe.step(host_np[W.clip_index(t)]); t += 1
-        d2h += (0 if tracks is None else np.asarray(tracks).nbytes) + dets.nbytes + 32      # rows + detections + counters
+    for i in range(K):
+        pipe.submit(host_np[W.clip_index(t)]); t += 1                     # pinned host frame -> async H2D inside the timed region
+        if i > 0:
+            tracks, dets = pipe.collect()
+            d2h += (0 if tracks is None else np.asarray(tracks).nbytes) + dets.nbytes + 32      # rows + detections + counters
+    tracks, dets = pipe.collect()
+    d2h += (0 if tracks is None else np.asarray(tracks).nbytes) + dets.nbytes + 32
     e1.record()
     torch.cuda.synchronize()
     clocks.stop()
@@ -317,6 +327,8 @@ def run_ours(args):
                       "clip": f"{W.N_SCENES} synthetic scenes x {W.HOLD} frames, cycled; random-init weights, calibrated BN/head bias",
                       "tracker": W.TRACKER_KW, "detector": W.DETECT_KW,
                       "l2": "per-step working set (124 MB fp16 weights + ~340 MB activations) exceeds the 126 MB L2; no explicit flush",
+                      "pipelining": "one frame of look-ahead: detector(t+1) overlaps ReID+association(t) on two CUDA streams; K frames "
+                                    "submitted and collected inside the timed region",
                       "parallelism": f"{world} independent streams (no data-path collective)"},
            "e2e": {"value": round(fps_e2e, 2), "unit": UNIT, "ms_per_step": round(worst_e2e / K, 4),
                    "h2d_bytes_per_step": int(SIZE * SIZE * 3), "d2h_bytes_per_step": int(d2h // K)},

@@ -195,6 +195,17 @@ int ydst_pipeline_destroy(ydst_pipeline* p);
  * + *n_dets_host receive the post-NMS, box-rescaled detections; out_host/k_host as in ydst_tracker_update. */
 int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out_host, int* k_host, float* dets_host,
                        int* n_dets_host, void* stream);
+/* Software-pipelined form of the same step: _submit enqueues the DETECTOR half of a frame (copy, Darknet, NMS, hand-off) on an
+ * internal stream and returns at once; _collect finishes the OLDEST submitted frame (crops, ReID, DeepSort.update with its host
+ * lifecycle) on a second internal stream and returns its rows.  Up to two frames may be in flight, so the steady state
+ *     submit(f0); for t: { submit(f[t+1]); collect() -> rows of f[t]; }  collect()
+ * runs the detector of frame t+1 under the association of frame t -- the look-ahead the reference's reader thread already has
+ * (yolo3/detect/video_detect.py:86,112 queues decoded frames ahead of the loop).  Results are identical to _step's, frame by frame.
+ * frame: HxWx3 uint8 RGB at the network size, host (pinned recommended) or device; a device frame is copied, so the caller
+ * may reuse its buffer.  want_dets: also bring the post-NMS detections back for _collect's dets_host.                              */
+int ydst_pipeline_submit(ydst_pipeline* p, const uint8_t* frame, int frame_is_host, int want_dets, void* stream);
+int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host);
+int ydst_pipeline_in_flight(const ydst_pipeline* p);
 /* same with the frame already resident on the device (bench "value" leg) */
 int ydst_pipeline_step_dev(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out_host, int* k_host, float* dets_host,
                            int* n_dets_host, void* stream);

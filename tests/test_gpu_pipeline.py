@@ -111,3 +111,28 @@ def test_drop_in_video_detector(tmp_path):
     assert n == len(clip)
     with pytest.raises(IOError):
         next(vd.detect(str(tmp_path / "missing.avi")))
+
+
+def test_lookahead_pipeline_equals_synchronous_steps():
+    """submit/collect with one frame of look-ahead must give, frame by frame, exactly what the synchronous step() gives
+    (same kernels, same order per stream; only the overlap between the detector of t+1 and the association of t differs)."""
+    from oracle.synth import make_frame
+    scenes = [make_frame(416, 416, seed=s) for s in (0, 1, 2)]
+    clip = [scenes[0]] * 4 + [scenes[1]] * 3 + [scenes[2]] * 2 + [scenes[0]] * 3
+    model, blocks, ws, sd, ds, pipe = build(scenes)
+    sync_out = [pipe.step(f) for f in clip]
+    model2, _, _, _, ds2, pipe2 = build(scenes)
+    frames_dev = [torch.from_numpy(f).to(DEV) for f in clip]
+    look_out = list(pipe2.run(frames_dev))
+    host_out = None
+    model3, _, _, _, ds3, pipe3 = build(scenes)
+    host_out = list(pipe3.run(clip))
+    assert len(look_out) == len(sync_out) == len(host_out) == len(clip)
+    for t, ((ta, da), (tb, db), (tc, dc)) in enumerate(zip(sync_out, look_out, host_out)):
+        np.testing.assert_array_equal(da, db, err_msg=f"frame {t}: detections")
+        np.testing.assert_array_equal(da, dc, err_msg=f"frame {t}: detections (host frames)")
+        np.testing.assert_array_equal(np.asarray(ta, np.int32).reshape(-1, 6), np.asarray(tb, np.int32).reshape(-1, 6), err_msg=f"frame {t}: tracks")
+        np.testing.assert_array_equal(np.asarray(ta, np.int32).reshape(-1, 6), np.asarray(tc, np.int32).reshape(-1, 6), err_msg=f"frame {t}")
+    assert pipe2.in_flight() == 0
+    with pytest.raises(Exception):
+        pipe2.collect()                     # nothing in flight

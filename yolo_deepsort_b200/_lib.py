@@ -70,6 +70,9 @@ SIGNATURES = {
     "ydst_tracker_last_matches": (_I, [_P, _P, _I, ctypes.POINTER(_I)]),
     "ydst_pipeline_create": (_I, [_P, _P, _P, _F, _F, _P, _I, ctypes.POINTER(_P)]),
     "ydst_pipeline_destroy": (_I, [_P]),
+    "ydst_pipeline_submit": (_I, [_P, _P, _I, _I, _P]),
+    "ydst_pipeline_collect": (_I, [_P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I)]),
+    "ydst_pipeline_in_flight": (_I, [_P]),
     "ydst_pipeline_step": (_I, [_P, _P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I), _P]),
     "ydst_pipeline_step_dev": (_I, [_P, _P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I), _P]),
 }

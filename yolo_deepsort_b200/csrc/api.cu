@@ -24,11 +24,20 @@ struct ydst_pipeline {
     Detector* det; Reid* reid; Tracker* trk;
     float conf, iou;
     int* mask_dev = nullptr; int n_mask = 0;
-    uint8_t* frame_dev = nullptr;
-    float *tlwh = nullptr, *confd = nullptr, *cls = nullptr, *feat = nullptr;
-    int* h_counts = nullptr;      // pinned: [0] m, [1] n_dets, [2] overflow, [3] crop error flag
-    float* h_dets = nullptr;      // pinned 300 x 6
-    float* h_cls = nullptr;       // pinned: class ids of the tracker inputs (float, as the detector emits them)
+    float* feat = nullptr;
+    // Two frame slots: the detector half of frame t+1 (stream sA) overlaps the ReID + association half of frame t (stream sB)
+    struct Slot {
+        uint8_t* frame_dev = nullptr;
+        float *tlwh = nullptr, *confd = nullptr, *cls = nullptr;
+        int* h_counts = nullptr;      // pinned: [0] candidates, [1] n_dets, [2] overflow, [3] m, [4] crop error flag
+        float* h_dets = nullptr;      // pinned 300 x 6
+        float* h_cls = nullptr;       // pinned: class ids of the tracker inputs (float, as the detector emits them)
+        cudaEvent_t ev_det = nullptr; // detector half done (counters on the host)
+        bool want_dets = false;
+    } slot[2];
+    cudaStream_t sA = nullptr, sB = nullptr;
+    cudaEvent_t ev_in = nullptr;
+    long long submitted = 0, collected = 0;
     int* h_payload = nullptr;
 };
 
@@ -415,16 +424,22 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
     auto* p = new ydst_pipeline();
     p->det = det->impl; p->reid = reid->impl; p->trk = trk->impl; p->conf = conf_thres; p->iou = iou_thres; p->n_mask = n_mask;
     const int md = p->det->nms_.max_det;
-    YDST_CUDA(cudaMalloc(&p->frame_dev, (size_t)p->det->H * p->det->W * 3));
-    YDST_CUDA(cudaMalloc(&p->tlwh, sizeof(float) * 4 * md));
-    YDST_CUDA(cudaMalloc(&p->confd, sizeof(float) * md));
-    YDST_CUDA(cudaMalloc(&p->cls, sizeof(float) * md));
+    for (auto& sl : p->slot) {
+        YDST_CUDA(cudaMalloc(&sl.frame_dev, (size_t)p->det->H * p->det->W * 3));
+        YDST_CUDA(cudaMalloc(&sl.tlwh, sizeof(float) * 4 * md));
+        YDST_CUDA(cudaMalloc(&sl.confd, sizeof(float) * md));
+        YDST_CUDA(cudaMalloc(&sl.cls, sizeof(float) * md));
+        YDST_CUDA(cudaMallocHost(&sl.h_counts, sizeof(int) * 8));
+        YDST_CUDA(cudaMallocHost(&sl.h_dets, sizeof(float) * 6 * md));
+        YDST_CUDA(cudaMallocHost(&sl.h_cls, sizeof(float) * md));
+        YDST_CUDA(cudaEventCreateWithFlags(&sl.ev_det, cudaEventDisableTiming));
+    }
     YDST_CUDA(cudaMalloc(&p->feat, sizeof(float) * 512 * md));
     YDST_CUDA(cudaMalloc(&p->mask_dev, sizeof(int) * (n_mask > 0 ? n_mask : 1)));
     if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
-    YDST_CUDA(cudaMallocHost(&p->h_counts, sizeof(int) * 8));
-    YDST_CUDA(cudaMallocHost(&p->h_dets, sizeof(float) * 6 * md));
-    YDST_CUDA(cudaMallocHost(&p->h_cls, sizeof(float) * md));
+    YDST_CUDA(cudaStreamCreateWithFlags(&p->sA, cudaStreamNonBlocking));
+    YDST_CUDA(cudaStreamCreateWithFlags(&p->sB, cudaStreamNonBlocking));
+    YDST_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     p->h_payload = new int[md];
     *out = p;
     YDST_API_END
@@ -432,43 +447,93 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
 int ydst_pipeline_destroy(ydst_pipeline* p) {
     YDST_API_BEGIN
     if (p) {
-        cudaFree(p->frame_dev); cudaFree(p->tlwh); cudaFree(p->confd); cudaFree(p->cls); cudaFree(p->feat); cudaFree(p->mask_dev);
-        cudaFreeHost(p->h_counts); cudaFreeHost(p->h_dets); cudaFreeHost(p->h_cls); delete[] p->h_payload;
+        if (p->sA) cudaStreamSynchronize(p->sA);
+        if (p->sB) cudaStreamSynchronize(p->sB);
+        for (auto& sl : p->slot) {
+            cudaFree(sl.frame_dev); cudaFree(sl.tlwh); cudaFree(sl.confd); cudaFree(sl.cls);
+            cudaFreeHost(sl.h_counts); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_cls);
+            if (sl.ev_det) cudaEventDestroy(sl.ev_det);
+        }
+        cudaFree(p->feat); cudaFree(p->mask_dev);
+        if (p->sA) cudaStreamDestroy(p->sA);
+        if (p->sB) cudaStreamDestroy(p->sB);
+        if (p->ev_in) cudaEventDestroy(p->ev_in);
+        delete[] p->h_payload;
         delete p;
     }
     YDST_API_END
 }
-static int pipeline_run(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
-                        cudaStream_t st) {
+
+// detector half of one frame, enqueued on sA: H2D (or D2D) of the frame, Darknet forward, NMS, tracker hand-off, small D2H
+static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_is_host, bool want_dets, cudaStream_t caller) {
+    YDST_CHECK(p->submitted - p->collected < 2, "two frames are already in flight: collect one first");
+    ydst_pipeline::Slot& sl = p->slot[p->submitted & 1];
     Detector& det = *p->det;
-    det.forward_u8(frame_dev, nullptr, st);
-    det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, st);
+    const size_t bytes = (size_t)det.H * det.W * 3;
+    if (frame_is_host) {
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev, frame, bytes, cudaMemcpyHostToDevice, p->sA));
+    } else {
+        // the caller's frame was produced on the caller's stream and must stay readable until this frame is collected: keep a copy
+        YDST_CUDA(cudaEventRecord(p->ev_in, caller));
+        YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev, frame, bytes, cudaMemcpyDeviceToDevice, p->sA));
+    }
+    det.forward_u8(sl.frame_dev, nullptr, p->sA);
+    det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, p->sA);
     // frame == network size, so resize_boxes' ratios are exactly 1 (yolo3/utils/model_build.py:12-19)
-    det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, p->tlwh, p->confd, p->cls, st);
-    YDST_CUDA(cudaMemcpyAsync(p->h_counts, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    if (dets_host) YDST_CUDA(cudaMemcpyAsync(p->h_dets, det.nms_.dets, sizeof(float) * 6 * det.nms_.max_det, cudaMemcpyDeviceToHost, st));
+    det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, sl.tlwh, sl.confd, sl.cls, p->sA);
+    YDST_CUDA(cudaMemcpyAsync(sl.h_counts, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->sA));
+    sl.want_dets = want_dets;
+    if (want_dets) YDST_CUDA(cudaMemcpyAsync(sl.h_dets, det.nms_.dets, sizeof(float) * 6 * det.nms_.max_det, cudaMemcpyDeviceToHost, p->sA));
     // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
-    YDST_CUDA(cudaMemcpyAsync(p->h_cls, p->cls, sizeof(float) * det.nms_.max_det, cudaMemcpyDeviceToHost, st));
-    YDST_CUDA(cudaStreamSynchronize(st));
-    YDST_CHECK(p->h_counts[2] == 0, "NMS candidate capacity exceeded (%d candidates)", p->h_counts[0]);
-    const int n_dets = p->h_counts[1], m = p->h_counts[3];
+    YDST_CUDA(cudaMemcpyAsync(sl.h_cls, sl.cls, sizeof(float) * det.nms_.max_det, cudaMemcpyDeviceToHost, p->sA));
+    YDST_CUDA(cudaEventRecord(sl.ev_det, p->sA));
+    ++p->submitted;
+}
+
+// tracker half of the oldest submitted frame, on sB: crops + ReID, then DeepSort.update with its host lifecycle
+static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {
+    YDST_CHECK(p->collected < p->submitted, "no frame in flight: submit one first");
+    ydst_pipeline::Slot& sl = p->slot[p->collected & 1];
+    ++p->collected;
+    Detector& det = *p->det;
+    YDST_CUDA(cudaEventSynchronize(sl.ev_det));
+    YDST_CHECK(sl.h_counts[2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[0]);
+    const int n_dets = sl.h_counts[1], m = sl.h_counts[3];
     if (n_dets_host) *n_dets_host = n_dets;
-    if (dets_host) memcpy(dets_host, p->h_dets, sizeof(float) * 6 * n_dets);
+    if (dets_host && sl.want_dets) memcpy(dets_host, sl.h_dets, sizeof(float) * 6 * n_dets);
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
-    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), st));
-    p->reid->extract(frame_dev, det.H, det.W, p->tlwh, m, p->feat, st);
-    YDST_CUDA(cudaMemcpyAsync(p->h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    for (int i = 0; i < m; ++i) p->h_payload[i] = (int)p->h_cls[i];
-    p->trk->update(p->tlwh, p->feat, p->h_payload, nullptr, m, out_host, k_host, st);
-    if (p->h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sB));
+    p->reid->extract(sl.frame_dev, det.H, det.W, sl.tlwh, m, p->feat, p->sB);
+    YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sB));
+    for (int i = 0; i < m; ++i) p->h_payload[i] = (int)sl.h_cls[i];
+    p->trk->update(sl.tlwh, p->feat, p->h_payload, nullptr, m, out_host, k_host, p->sB);
+    if (sl.h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
     return 0;
 }
+
+int ydst_pipeline_submit(ydst_pipeline* p, const uint8_t* frame, int frame_is_host, int want_dets, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && frame, "null argument");
+    pipeline_submit(p, frame, frame_is_host != 0, want_dets != 0, S(stream));
+    YDST_API_END
+}
+int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && out_host && k_host, "null argument");
+    const int rc = pipeline_collect(p, out_host, k_host, dets_host, n_dets_host);
+    if (rc) return rc;
+    YDST_API_END
+}
+int ydst_pipeline_in_flight(const ydst_pipeline* p) { return p ? (int)(p->submitted - p->collected) : 0; }
+
 int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
                        void* stream) {
     YDST_API_BEGIN
     YDST_CHECK(p && frame_host && out_host && k_host, "null argument");
-    YDST_CUDA(cudaMemcpyAsync(p->frame_dev, frame_host, (size_t)p->det->H * p->det->W * 3, cudaMemcpyHostToDevice, S(stream)));
-    const int rc = pipeline_run(p, p->frame_dev, out_host, k_host, dets_host, n_dets_host, S(stream));
+    YDST_CHECK(p->submitted == p->collected, "ydst_pipeline_step needs an empty pipeline (collect the frames in flight first)");
+    pipeline_submit(p, frame_host, true, dets_host != nullptr, S(stream));
+    const int rc = pipeline_collect(p, out_host, k_host, dets_host, n_dets_host);
     if (rc) return rc;
     YDST_API_END
 }
@@ -476,7 +541,9 @@ int ydst_pipeline_step_dev(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* 
                            void* stream) {
     YDST_API_BEGIN
     YDST_CHECK(p && frame_dev && out_host && k_host, "null argument");
-    const int rc = pipeline_run(p, frame_dev, out_host, k_host, dets_host, n_dets_host, S(stream));
+    YDST_CHECK(p->submitted == p->collected, "ydst_pipeline_step_dev needs an empty pipeline (collect the frames in flight first)");
+    pipeline_submit(p, frame_dev, false, dets_host != nullptr, S(stream));
+    const int rc = pipeline_collect(p, out_host, k_host, dets_host, n_dets_host);
     if (rc) return rc;
     YDST_API_END
 }

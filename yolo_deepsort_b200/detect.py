@@ -122,13 +122,32 @@ class VideoDetector:
             cv2.resizeWindow("result", 960, 540)
         accum_time, curr_fps, fps, prev_time = 0, 0, "FPS: ??", time.time()
         hold_detections, actions, frames = None, [], 0
+        H, W = self.image_detector.model.img_size
+
+        def read_rgb():
+            ok, bgr = vid.read()
+            return cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB) if ok and bgr is not None else None
+
+        # One frame of look-ahead (the reference's reader thread decodes ahead as well, video_detect.py:86,112): when every
+        # frame is a detection frame and the fused pipeline applies, the detector of frame t+1 is submitted before the
+        # ReID + association of frame t is collected, so the two halves overlap on the GPU.  Results are unchanged.
+        lookahead = self._pipeline is not None and self.skip_frames in (-1, 1) and self.action_id is None
+        nxt = read_rgb()
+        submitted = False
         try:
-            while True:
-                ok, bgr = vid.read()
-                if not ok or bgr is None:
-                    break
-                frame = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)
-                if frames % self.skip_frames == 0:
+            while nxt is not None:
+                frame, nxt = nxt, read_rgb()
+                if lookahead and frame.shape[:2] == (H, W) and (nxt is None or nxt.shape[:2] == (H, W)):
+                    if not submitted:
+                        self._pipeline.submit(frame, want_dets=False)
+                    submitted = nxt is not None
+                    if submitted:
+                        self._pipeline.submit(nxt, want_dets=False)
+                    detections, _ = self._pipeline.collect(want_dets=False)
+                    actions = []
+                    hold_detections = detections
+                    frames = 0
+                elif frames % self.skip_frames == 0:
                     detections = self._track(frame)
                     if detections is not None and self.tracker is not None and self.action_id is not None:
                         actions = self.action_id.update(detections)
@@ -161,6 +180,8 @@ class VideoDetector:
                 if real_show and cv2.waitKey(1) & 0xFF == ord('q'):
                     break
         finally:
+            if self._pipeline is not None:
+                self._pipeline.drain()
             vid.release()
             if out is not None:
                 out.release()

@@ -32,6 +32,49 @@ class FramePipeline:
         except Exception:
             pass
 
+    # ---- software-pipelined form: the detector half of frame t+1 runs under the ReID + association half of frame t ----
+    def submit(self, frame, want_dets=True):
+        """Enqueue the detector half of `frame` and return at once (at most two frames may be in flight)."""
+        with torch.cuda.device(self.device):
+            if isinstance(frame, torch.Tensor) and frame.is_cuda:
+                check(lib().ydst_pipeline_submit(self._h, ptr(frame), 0, int(want_dets), stream_ptr()))
+            else:
+                f = frame.numpy() if isinstance(frame, torch.Tensor) else np.ascontiguousarray(frame)
+                assert f.dtype == np.uint8 and f.shape == (self.model.img_size[0], self.model.img_size[1], 3)
+                self._keep = (getattr(self, '_keep', (None, None))[1], f)    # async H2D copies read them until the frames are collected
+                check(lib().ydst_pipeline_submit(self._h, f.ctypes.data, 1, int(want_dets), stream_ptr()))
+
+    def collect(self, want_dets=True):
+        """Finish the oldest submitted frame; same return value as step()."""
+        k, nd = ctypes.c_int(), ctypes.c_int()
+        dets_ptr = self._dets.ctypes.data if want_dets else None
+        with torch.cuda.device(self.device):
+            check(lib().ydst_pipeline_collect(self._h, self._out.ctypes.data, ctypes.byref(k), dets_ptr, ctypes.byref(nd)))
+        dets = self._dets[:nd.value].copy() if want_dets else None
+        if k.value < 0:
+            return None, dets
+        return (self._out[:k.value].copy() if k.value else []), dets
+
+    def in_flight(self):
+        return int(lib().ydst_pipeline_in_flight(self._h))
+
+    def drain(self):
+        while self.in_flight():
+            self.collect(want_dets=False)
+
+    def run(self, frames, want_dets=True):
+        """Generator over an iterable of frames with one frame of look-ahead: yields (tracks, dets) per frame, in order."""
+        it = iter(frames)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        self.submit(cur, want_dets)
+        for nxt in it:
+            self.submit(nxt, want_dets)
+            yield self.collect(want_dets)
+        yield self.collect(want_dets)
+
     def step(self, frame, want_dets=True):
         """frame: (H,W,3) uint8 RGB at the network size; numpy (host, ideally pinned) or a CUDA tensor.
         Returns (tracks, dets): tracks = np.int32 (K,6) or [] -- or None if nothing was detected at all (the reference
