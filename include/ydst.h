@@ -197,7 +197,7 @@ int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out
                        int* n_dets_host, void* stream);
 /* Software-pipelined form of the same step: _submit enqueues the DETECTOR half of a frame (copy, Darknet, NMS, hand-off) on an
  * internal stream and returns at once; _collect finishes the OLDEST submitted frame (crops, ReID, DeepSort.update with its host
- * lifecycle) on a second internal stream and returns its rows.  Up to two frames may be in flight, so the steady state
+ * lifecycle) on a second internal stream and returns its rows.  Up to two frames (2B with a micro-batch) may be in flight, so the steady state
  *     submit(f0); for t: { submit(f[t+1]); collect() -> rows of f[t]; }  collect()
  * runs the detector of frame t+1 under the association of frame t -- the look-ahead the reference's reader thread already has
  * (yolo3/detect/video_detect.py:86,112 queues decoded frames ahead of the loop).  Results are identical to _step's, frame by frame.
@@ -206,6 +206,10 @@ int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out
 int ydst_pipeline_submit(ydst_pipeline* p, const uint8_t* frame, int frame_is_host, int want_dets, void* stream);
 int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host);
 int ydst_pipeline_in_flight(const ydst_pipeline* p);
+/* A detector handle created with batch B > 1 makes B the pipeline's MICRO-BATCH: B consecutive frames of the stream share one
+ * Darknet forward (and one ReID forward), which amortises the per-layer launch latency that bounds a batch-1 frame; up to 2B
+ * frames are then in flight.  _can_submit tells whether the next frame's slot is free.  Per-frame results are unchanged.      */
+int ydst_pipeline_can_submit(const ydst_pipeline* p);
 /* same with the frame already resident on the device (bench "value" leg) */
 int ydst_pipeline_step_dev(ydst_pipeline* p, const uint8_t* frame_dev, int32_t* out_host, int* k_host, float* dets_host,
                            int* n_dets_host, void* stream);

@@ -136,3 +136,23 @@ def test_lookahead_pipeline_equals_synchronous_steps():
     assert pipe2.in_flight() == 0
     with pytest.raises(Exception):
         pipe2.collect()                     # nothing in flight
+    # micro-batches of 2 and 3 consecutive frames per Darknet / ReID forward (12 frames: 3 leaves no remainder, 5 does)
+    from yolo_deepsort_b200 import DeepSort, FramePipeline
+    for mb in (2, 3, 5):
+        ds_mb = DeepSort(sd, max_dist=0.3, min_confidence=1, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30, use_cuda=True, device=DEV)
+        pipe_mb = FramePipeline(model, ds_mb, thres=0.5, nms_thres=0.4, class_mask=[0, 2, 4], micro_batch=mb)
+        out_mb = list(pipe_mb.run(frames_dev if mb != 3 else clip))
+        assert len(out_mb) == len(clip)
+        ids = IdBijection()
+        for t, ((ta, da), (tb, db)) in enumerate(zip(sync_out, out_mb)):
+            # a batch-B forward tiles the convolutions differently (other N tile / K split), so scores move in the last fp16 bits:
+            # two nearly tied detections may swap places, and with them the ids of the tracks they spawn -> order-free comparison
+            assert da.shape == db.shape, f"micro_batch {mb} frame {t}"
+            pd = match_boxes(db[:, :4], da[:, :4])
+            np.testing.assert_allclose(db[pd], da, rtol=2e-3, atol=2e-2, err_msg=f"micro_batch {mb} frame {t}: detections")
+            a, b = np.asarray(ta, np.int32).reshape(-1, 6), np.asarray(tb, np.int32).reshape(-1, 6)
+            assert a.shape == b.shape
+            pt = match_boxes(b[:, :4], a[:, :4])
+            assert np.abs(b[pt, :4] - a[:, :4]).max(initial=0) <= 1
+            np.testing.assert_array_equal(b[pt, 5], a[:, 5])
+            ids.check(b[pt, 4], a[:, 4], f"micro_batch {mb} frame {t}")

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ydst_pipeline_submit": (_I, [_P, _P, _I, _I, _P]),
     "ydst_pipeline_collect": (_I, [_P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I)]),
     "ydst_pipeline_in_flight": (_I, [_P]),
+    "ydst_pipeline_can_submit": (_I, [_P]),
     "ydst_pipeline_step": (_I, [_P, _P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I), _P]),
     "ydst_pipeline_step_dev": (_I, [_P, _P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I), _P]),
 }

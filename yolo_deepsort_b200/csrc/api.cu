@@ -24,16 +24,20 @@ struct ydst_pipeline {
     Detector* det; Reid* reid; Tracker* trk;
     float conf, iou;
     int* mask_dev = nullptr; int n_mask = 0;
-    float* feat = nullptr;
-    // Two frame slots: the detector half of frame t+1 (stream sA) overlaps the ReID + association half of frame t (stream sB)
+    int B = 1;                        // detector micro-batch: frames per slot
+    float* feat = nullptr;            // [B * max_det][512]
+    // Two slots of B frames: the detector half of the next B frames (stream sA) overlaps the ReID + association half of the
+    // previous B (stream sB).  Frame f lives in slot (f / B) & 1, position f % B.
     struct Slot {
-        uint8_t* frame_dev = nullptr;
-        float *tlwh = nullptr, *confd = nullptr, *cls = nullptr;
-        int* h_counts = nullptr;      // pinned: [0] candidates, [1] n_dets, [2] overflow, [3] m, [4] crop error flag
-        float* h_dets = nullptr;      // pinned 300 x 6
-        float* h_cls = nullptr;       // pinned: class ids of the tracker inputs (float, as the detector emits them)
+        uint8_t* frame_dev = nullptr; // [B][H*W*3]
+        float *tlwh = nullptr, *confd = nullptr, *cls = nullptr;   // [B][max_det](x4)
+        int* h_counts = nullptr;      // pinned [B][8]: [0] candidates, [1] n_dets, [2] overflow, [3] m, [4] crop error flag
+        float* h_dets = nullptr;      // pinned [B][300 x 6]
+        float* h_cls = nullptr;       // pinned [B][max_det]: class ids of the tracker inputs (float, as the detector emits them)
         cudaEvent_t ev_det = nullptr; // detector half done (counters on the host)
-        bool want_dets = false;
+        bool want_dets = false, launched = false, feat_ready = false;
+        int n_frames = 0;             // frames stored
+        int feat_off[8] = {0};        // first feature row of each frame
     } slot[2];
     cudaStream_t sA = nullptr, sB = nullptr;
     cudaEvent_t ev_in = nullptr;
@@ -420,21 +424,22 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
                          const int* class_mask_host, int n_mask, ydst_pipeline** out) {
     YDST_API_BEGIN
     YDST_CHECK(det && reid && trk && out, "null argument");
-    YDST_CHECK(det->impl->batch == 1, "the per-frame pipeline needs a batch-1 detector");
+    YDST_CHECK(det->impl->batch >= 1 && det->impl->batch <= 8, "the per-frame pipeline takes a detector with batch 1..8 (its micro-batch)");
     auto* p = new ydst_pipeline();
     p->det = det->impl; p->reid = reid->impl; p->trk = trk->impl; p->conf = conf_thres; p->iou = iou_thres; p->n_mask = n_mask;
-    const int md = p->det->nms_.max_det;
+    p->B = det->impl->batch;
+    const int md = p->det->nms_.max_det, B = p->B;
     for (auto& sl : p->slot) {
-        YDST_CUDA(cudaMalloc(&sl.frame_dev, (size_t)p->det->H * p->det->W * 3));
-        YDST_CUDA(cudaMalloc(&sl.tlwh, sizeof(float) * 4 * md));
-        YDST_CUDA(cudaMalloc(&sl.confd, sizeof(float) * md));
-        YDST_CUDA(cudaMalloc(&sl.cls, sizeof(float) * md));
-        YDST_CUDA(cudaMallocHost(&sl.h_counts, sizeof(int) * 8));
-        YDST_CUDA(cudaMallocHost(&sl.h_dets, sizeof(float) * 6 * md));
-        YDST_CUDA(cudaMallocHost(&sl.h_cls, sizeof(float) * md));
+        YDST_CUDA(cudaMalloc(&sl.frame_dev, (size_t)B * p->det->H * p->det->W * 3));
+        YDST_CUDA(cudaMalloc(&sl.tlwh, sizeof(float) * 4 * md * B));
+        YDST_CUDA(cudaMalloc(&sl.confd, sizeof(float) * md * B));
+        YDST_CUDA(cudaMalloc(&sl.cls, sizeof(float) * md * B));
+        YDST_CUDA(cudaMallocHost(&sl.h_counts, sizeof(int) * 8 * B));
+        YDST_CUDA(cudaMallocHost(&sl.h_dets, sizeof(float) * 6 * md * B));
+        YDST_CUDA(cudaMallocHost(&sl.h_cls, sizeof(float) * md * B));
         YDST_CUDA(cudaEventCreateWithFlags(&sl.ev_det, cudaEventDisableTiming));
     }
-    YDST_CUDA(cudaMalloc(&p->feat, sizeof(float) * 512 * md));
+    YDST_CUDA(cudaMalloc(&p->feat, sizeof(float) * 512 * md * B));
     YDST_CUDA(cudaMalloc(&p->mask_dev, sizeof(int) * (n_mask > 0 ? n_mask : 1)));
     if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
     YDST_CUDA(cudaStreamCreateWithFlags(&p->sA, cudaStreamNonBlocking));
@@ -464,50 +469,86 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
     YDST_API_END
 }
 
-// detector half of one frame, enqueued on sA: H2D (or D2D) of the frame, Darknet forward, NMS, tracker hand-off, small D2H
+// frame f may be stored once every frame of the batch that used its slot before (batch f/B - 2) has been collected
+static bool pipeline_can_submit(const ydst_pipeline* p) {
+    const long long f = p->submitted;
+    return p->collected >= (f / p->B - 1) * p->B;
+}
+
+// detector half of one slot, enqueued on sA: Darknet forward over its frames, then per frame NMS, tracker hand-off, small D2H.
+// A partially filled slot (end of stream / synchronous step) runs the same batch plan; the unused images are ignored.
+static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) {
+    Detector& det = *p->det;
+    const int md = det.nms_.max_det;
+    det.forward_u8(sl.frame_dev, nullptr, p->sA);
+    for (int b = 0; b < sl.n_frames; ++b) {
+        det.nms_.run(det.pred + (size_t)b * det.rows * det.fields, det.rows, det.fields, p->conf, p->iou, p->sA);
+        // frame == network size, so resize_boxes' ratios are exactly 1 (yolo3/utils/model_build.py:12-19)
+        det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, sl.tlwh + (size_t)b * md * 4, sl.confd + (size_t)b * md, sl.cls + (size_t)b * md, p->sA);
+        YDST_CUDA(cudaMemcpyAsync(sl.h_counts + b * 8, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->sA));
+        if (sl.want_dets)
+            YDST_CUDA(cudaMemcpyAsync(sl.h_dets + (size_t)b * md * 6, det.nms_.dets, sizeof(float) * 6 * md, cudaMemcpyDeviceToHost, p->sA));
+        // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
+        YDST_CUDA(cudaMemcpyAsync(sl.h_cls + (size_t)b * md, sl.cls + (size_t)b * md, sizeof(float) * md, cudaMemcpyDeviceToHost, p->sA));
+    }
+    YDST_CUDA(cudaEventRecord(sl.ev_det, p->sA));
+    sl.launched = true;
+}
+
 static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_is_host, bool want_dets, cudaStream_t caller) {
-    YDST_CHECK(p->submitted - p->collected < 2, "two frames are already in flight: collect one first");
-    ydst_pipeline::Slot& sl = p->slot[p->submitted & 1];
+    YDST_CHECK(pipeline_can_submit(p), "the pipeline is full (%lld frames in flight): collect one first", p->submitted - p->collected);
+    ydst_pipeline::Slot& sl = p->slot[(p->submitted / p->B) & 1];
+    const int sub = (int)(p->submitted % p->B);
     Detector& det = *p->det;
     const size_t bytes = (size_t)det.H * det.W * 3;
+    if (sub == 0) { sl.n_frames = 0; sl.launched = false; sl.feat_ready = false; sl.want_dets = false; }
     if (frame_is_host) {
-        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev, frame, bytes, cudaMemcpyHostToDevice, p->sA));
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, cudaMemcpyHostToDevice, p->sA));
     } else {
         // the caller's frame was produced on the caller's stream and must stay readable until this frame is collected: keep a copy
         YDST_CUDA(cudaEventRecord(p->ev_in, caller));
         YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
-        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev, frame, bytes, cudaMemcpyDeviceToDevice, p->sA));
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, cudaMemcpyDeviceToDevice, p->sA));
     }
-    det.forward_u8(sl.frame_dev, nullptr, p->sA);
-    det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, p->sA);
-    // frame == network size, so resize_boxes' ratios are exactly 1 (yolo3/utils/model_build.py:12-19)
-    det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, sl.tlwh, sl.confd, sl.cls, p->sA);
-    YDST_CUDA(cudaMemcpyAsync(sl.h_counts, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->sA));
-    sl.want_dets = want_dets;
-    if (want_dets) YDST_CUDA(cudaMemcpyAsync(sl.h_dets, det.nms_.dets, sizeof(float) * 6 * det.nms_.max_det, cudaMemcpyDeviceToHost, p->sA));
-    // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
-    YDST_CUDA(cudaMemcpyAsync(sl.h_cls, sl.cls, sizeof(float) * det.nms_.max_det, cudaMemcpyDeviceToHost, p->sA));
-    YDST_CUDA(cudaEventRecord(sl.ev_det, p->sA));
+    sl.want_dets = sl.want_dets || want_dets;
+    sl.n_frames = sub + 1;
     ++p->submitted;
+    if (sl.n_frames == p->B) pipeline_launch_detector(p, sl);
 }
 
-// tracker half of the oldest submitted frame, on sB: crops + ReID, then DeepSort.update with its host lifecycle
+// tracker half of the oldest submitted frame, on sB: crops + ReID (once per slot, all its frames in one forward), then
+// DeepSort.update with its host lifecycle
 static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {
     YDST_CHECK(p->collected < p->submitted, "no frame in flight: submit one first");
-    ydst_pipeline::Slot& sl = p->slot[p->collected & 1];
+    ydst_pipeline::Slot& sl = p->slot[(p->collected / p->B) & 1];
+    const int sub = (int)(p->collected % p->B);
     ++p->collected;
     Detector& det = *p->det;
-    YDST_CUDA(cudaEventSynchronize(sl.ev_det));
-    YDST_CHECK(sl.h_counts[2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[0]);
-    const int n_dets = sl.h_counts[1], m = sl.h_counts[3];
+    const int md = det.nms_.max_det;
+    const size_t bytes = (size_t)det.H * det.W * 3;
+    if (!sl.launched) pipeline_launch_detector(p, sl);                 // partial batch
+    if (!sl.feat_ready) {
+        YDST_CUDA(cudaEventSynchronize(sl.ev_det));
+        const uint8_t* frames[8]; const float* boxes[8]; int ms[8];
+        int off = 0;
+        for (int b = 0; b < sl.n_frames; ++b) {
+            YDST_CHECK(sl.h_counts[b * 8 + 2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[b * 8]);
+            frames[b] = sl.frame_dev + b * bytes; boxes[b] = sl.tlwh + (size_t)b * md * 4;
+            ms[b] = sl.h_counts[b * 8 + 1] > 0 ? sl.h_counts[b * 8 + 3] : 0;
+            sl.feat_off[b] = off; off += ms[b];
+        }
+        YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sB));
+        p->reid->extract_multi(frames, det.H, det.W, boxes, ms, sl.n_frames, p->feat, p->sB);
+        YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sB));
+        sl.feat_ready = true;
+    }
+    const int n_dets = sl.h_counts[sub * 8 + 1], m = sl.h_counts[sub * 8 + 3];
     if (n_dets_host) *n_dets_host = n_dets;
-    if (dets_host && sl.want_dets) memcpy(dets_host, sl.h_dets, sizeof(float) * 6 * n_dets);
+    if (dets_host && sl.want_dets) memcpy(dets_host, sl.h_dets + (size_t)sub * md * 6, sizeof(float) * 6 * n_dets);
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
-    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sB));
-    p->reid->extract(sl.frame_dev, det.H, det.W, sl.tlwh, m, p->feat, p->sB);
-    YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sB));
-    for (int i = 0; i < m; ++i) p->h_payload[i] = (int)sl.h_cls[i];
-    p->trk->update(sl.tlwh, p->feat, p->h_payload, nullptr, m, out_host, k_host, p->sB);
+    const float* h_cls = sl.h_cls + (size_t)sub * md;
+    for (int i = 0; i < m; ++i) p->h_payload[i] = (int)h_cls[i];
+    p->trk->update(sl.tlwh + (size_t)sub * md * 4, p->feat + (size_t)sl.feat_off[sub] * 512, p->h_payload, nullptr, m, out_host, k_host, p->sB);
     if (sl.h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
     return 0;
 }
@@ -526,6 +567,7 @@ int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, floa
     YDST_API_END
 }
 int ydst_pipeline_in_flight(const ydst_pipeline* p) { return p ? (int)(p->submitted - p->collected) : 0; }
+int ydst_pipeline_can_submit(const ydst_pipeline* p) { return p && pipeline_can_submit(p) ? 1 : 0; }
 
 int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host,
                        void* stream) {

@@ -12,14 +12,17 @@ from ._lib import check, lib, ptr, stream_ptr
 
 
 class FramePipeline:
-    def __init__(self, model, deepsort, thres=0.5, nms_thres=0.4, class_mask=None):
+    def __init__(self, model, deepsort, thres=0.5, nms_thres=0.4, class_mask=None, micro_batch=1):
+        """micro_batch > 1: that many consecutive frames share one Darknet forward and one ReID forward (run() / submit() /
+        collect() then keep up to 2*micro_batch frames in flight); per-frame results are unchanged."""
         self.model, self.deepsort = model, deepsort
+        self.micro_batch = int(micro_batch)
         self.device = model._device
         mask = np.ascontiguousarray(class_mask if class_mask is not None else [], dtype=np.int32)
         self._mask = mask
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib().ydst_pipeline_create(model.handle(1), deepsort.extractor.handle, deepsort.tracker.handle, float(thres),
+            check(lib().ydst_pipeline_create(model.handle(self.micro_batch), deepsort.extractor.handle, deepsort.tracker.handle, float(thres),
                                              float(nms_thres), mask.ctypes.data if mask.size else None, int(mask.size),
                                              ctypes.byref(self._h)))
         self._out = np.zeros((deepsort.tracker.cap_tracks, 6), np.int32)
@@ -41,7 +44,7 @@ class FramePipeline:
             else:
                 f = frame.numpy() if isinstance(frame, torch.Tensor) else np.ascontiguousarray(frame)
                 assert f.dtype == np.uint8 and f.shape == (self.model.img_size[0], self.model.img_size[1], 3)
-                self._keep = (getattr(self, '_keep', (None, None))[1], f)    # async H2D copies read them until the frames are collected
+                self._keep = (getattr(self, '_keep', ()) + (f,))[-4 * self.micro_batch:]   # async H2D copies read them until collected
                 check(lib().ydst_pipeline_submit(self._h, f.ctypes.data, 1, int(want_dets), stream_ptr()))
 
     def collect(self, want_dets=True):
@@ -62,18 +65,23 @@ class FramePipeline:
         while self.in_flight():
             self.collect(want_dets=False)
 
+    def can_submit(self):
+        return bool(lib().ydst_pipeline_can_submit(self._h))
+
     def run(self, frames, want_dets=True):
-        """Generator over an iterable of frames with one frame of look-ahead: yields (tracks, dets) per frame, in order."""
+        """Generator over an iterable of frames with look-ahead (one frame, or a micro-batch): yields (tracks, dets) per frame,
+        in order."""
         it = iter(frames)
-        try:
-            cur = next(it)
-        except StopIteration:
-            return
-        self.submit(cur, want_dets)
-        for nxt in it:
-            self.submit(nxt, want_dets)
+        done = False
+        while True:
+            while not done and self.can_submit():
+                try:
+                    self.submit(next(it), want_dets)
+                except StopIteration:
+                    done = True
+            if not self.in_flight():
+                return
             yield self.collect(want_dets)
-        yield self.collect(want_dets)
 
     def step(self, frame, want_dets=True):
         """frame: (H,W,3) uint8 RGB at the network size; numpy (host, ideally pinned) or a CUDA tensor.
