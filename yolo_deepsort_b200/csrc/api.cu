@@ -25,10 +25,13 @@ struct ydst_pipeline {
     float conf, iou;
     int* mask_dev = nullptr; int n_mask = 0;
     int B = 1;                        // detector micro-batch: frames per slot
-    float* feat = nullptr;            // [B * max_det][512]
-    // Two slots of B frames: the detector half of the next B frames (stream sA) overlaps the ReID + association half of the
-    // previous B (stream sB).  Frame f lives in slot (f / B) & 1, position f % B.
+    // Three slots of B frames form a three-stage pipeline over three streams: Darknet + NMS of batch k+2 (sA), crops + ReID of
+    // batch k+1 (sC) and DeepSort.update of batch k (sB, with its host lifecycle).  Frame f lives in slot (f / B) % 3, position f % B.
+    static constexpr int kSlots = 3;
     struct Slot {
+        float* feat = nullptr;        // [B * max_det][512]
+        cudaEvent_t ev_feat = nullptr;
+        bool reid_launched = false;
         uint8_t* frame_dev = nullptr; // [B][H*W*3]
         float *tlwh = nullptr, *confd = nullptr, *cls = nullptr;   // [B][max_det](x4)
         int* h_counts = nullptr;      // pinned [B][8]: [0] candidates, [1] n_dets, [2] overflow, [3] m, [4] crop error flag
@@ -36,12 +39,15 @@ struct ydst_pipeline {
         float* h_cls = nullptr;       // pinned [B][max_det]: class ids of the tracker inputs (float, as the detector emits them)
         cudaEvent_t ev_det = nullptr; // detector half done (counters on the host)
         bool want_dets = false, launched = false, feat_ready = false;
+        bool busy = false;            // holds frames that have not all been collected yet
         int n_frames = 0;             // frames stored
+        int n_collected = 0;
         int feat_off[8] = {0};        // first feature row of each frame
-    } slot[2];
-    cudaStream_t sA = nullptr, sB = nullptr;
+    } slot[kSlots];
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;
     cudaEvent_t ev_in = nullptr;
     long long submitted = 0, collected = 0;
+    long long fill = 0, drain = 0;    // slot sequence numbers: slot[fill % kSlots] accepts frames, slot[drain % kSlots] is collected from
     int* h_payload = nullptr;
 };
 
@@ -438,12 +444,14 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
         YDST_CUDA(cudaMallocHost(&sl.h_dets, sizeof(float) * 6 * md * B));
         YDST_CUDA(cudaMallocHost(&sl.h_cls, sizeof(float) * md * B));
         YDST_CUDA(cudaEventCreateWithFlags(&sl.ev_det, cudaEventDisableTiming));
+        YDST_CUDA(cudaEventCreateWithFlags(&sl.ev_feat, cudaEventDisableTiming));
+        YDST_CUDA(cudaMalloc(&sl.feat, sizeof(float) * 512 * md * B));
     }
-    YDST_CUDA(cudaMalloc(&p->feat, sizeof(float) * 512 * md * B));
     YDST_CUDA(cudaMalloc(&p->mask_dev, sizeof(int) * (n_mask > 0 ? n_mask : 1)));
     if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
     YDST_CUDA(cudaStreamCreateWithFlags(&p->sA, cudaStreamNonBlocking));
     YDST_CUDA(cudaStreamCreateWithFlags(&p->sB, cudaStreamNonBlocking));
+    YDST_CUDA(cudaStreamCreateWithFlags(&p->sC, cudaStreamNonBlocking));
     YDST_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     p->h_payload = new int[md];
     *out = p;
@@ -454,14 +462,17 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
     if (p) {
         if (p->sA) cudaStreamSynchronize(p->sA);
         if (p->sB) cudaStreamSynchronize(p->sB);
+        if (p->sC) cudaStreamSynchronize(p->sC);
         for (auto& sl : p->slot) {
-            cudaFree(sl.frame_dev); cudaFree(sl.tlwh); cudaFree(sl.confd); cudaFree(sl.cls);
+            cudaFree(sl.frame_dev); cudaFree(sl.tlwh); cudaFree(sl.confd); cudaFree(sl.cls); cudaFree(sl.feat);
             cudaFreeHost(sl.h_counts); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_cls);
             if (sl.ev_det) cudaEventDestroy(sl.ev_det);
+            if (sl.ev_feat) cudaEventDestroy(sl.ev_feat);
         }
-        cudaFree(p->feat); cudaFree(p->mask_dev);
+        cudaFree(p->mask_dev);
         if (p->sA) cudaStreamDestroy(p->sA);
         if (p->sB) cudaStreamDestroy(p->sB);
+        if (p->sC) cudaStreamDestroy(p->sC);
         if (p->ev_in) cudaEventDestroy(p->ev_in);
         delete[] p->h_payload;
         delete p;
@@ -469,10 +480,10 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
     YDST_API_END
 }
 
-// frame f may be stored once every frame of the batch that used its slot before (batch f/B - 2) has been collected
+// a frame can be stored if the slot being filled is free, or still filling (not yet handed to the detector)
 static bool pipeline_can_submit(const ydst_pipeline* p) {
-    const long long f = p->submitted;
-    return p->collected >= (f / p->B - 1) * p->B;
+    const ydst_pipeline::Slot& sl = p->slot[p->fill % ydst_pipeline::kSlots];
+    return !sl.busy || !sl.launched;
 }
 
 // detector half of one slot, enqueued on sA: Darknet forward over its frames, then per frame NMS, tracker hand-off, small D2H.
@@ -493,15 +504,19 @@ static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) 
     }
     YDST_CUDA(cudaEventRecord(sl.ev_det, p->sA));
     sl.launched = true;
+    ++p->fill;                                                         // the next frame starts a new slot
 }
 
 static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_is_host, bool want_dets, cudaStream_t caller) {
     YDST_CHECK(pipeline_can_submit(p), "the pipeline is full (%lld frames in flight): collect one first", p->submitted - p->collected);
-    ydst_pipeline::Slot& sl = p->slot[(p->submitted / p->B) & 1];
-    const int sub = (int)(p->submitted % p->B);
+    ydst_pipeline::Slot& sl = p->slot[p->fill % ydst_pipeline::kSlots];
+    if (!sl.busy) {
+        sl.busy = true; sl.n_frames = 0; sl.n_collected = 0;
+        sl.launched = false; sl.feat_ready = false; sl.reid_launched = false; sl.want_dets = false;
+    }
+    const int sub = sl.n_frames;
     Detector& det = *p->det;
     const size_t bytes = (size_t)det.H * det.W * 3;
-    if (sub == 0) { sl.n_frames = 0; sl.launched = false; sl.feat_ready = false; sl.want_dets = false; }
     if (frame_is_host) {
         YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, cudaMemcpyHostToDevice, p->sA));
     } else {
@@ -516,40 +531,66 @@ static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_i
     if (sl.n_frames == p->B) pipeline_launch_detector(p, sl);
 }
 
-// tracker half of the oldest submitted frame, on sB: crops + ReID (once per slot, all its frames in one forward), then
-// DeepSort.update with its host lifecycle
-static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {
-    YDST_CHECK(p->collected < p->submitted, "no frame in flight: submit one first");
-    ydst_pipeline::Slot& sl = p->slot[(p->collected / p->B) & 1];
-    const int sub = (int)(p->collected % p->B);
-    ++p->collected;
+// ReID half of one slot on sC: crops of all its frames through one forward.  Needs the detector's counters on the host:
+// blocks for them, or (block == false) only proceeds if the detector half has already finished.
+static void pipeline_launch_reid(ydst_pipeline* p, ydst_pipeline::Slot& sl, bool block) {
+    if (!sl.launched || sl.reid_launched) return;
+    if (block) YDST_CUDA(cudaEventSynchronize(sl.ev_det));
+    else if (cudaEventQuery(sl.ev_det) != cudaSuccess) return;
     Detector& det = *p->det;
     const int md = det.nms_.max_det;
     const size_t bytes = (size_t)det.H * det.W * 3;
+    const uint8_t* frames[8]; const float* boxes[8]; int ms[8];
+    int off = 0;
+    for (int b = 0; b < sl.n_frames; ++b) {
+        YDST_CHECK(sl.h_counts[b * 8 + 2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[b * 8]);
+        frames[b] = sl.frame_dev + b * bytes; boxes[b] = sl.tlwh + (size_t)b * md * 4;
+        ms[b] = sl.h_counts[b * 8 + 1] > 0 ? sl.h_counts[b * 8 + 3] : 0;
+        sl.feat_off[b] = off; off += ms[b];
+    }
+    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sC));
+    p->reid->extract_multi(frames, det.H, det.W, boxes, ms, sl.n_frames, sl.feat, p->sC);
+    YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sC));
+    YDST_CUDA(cudaEventRecord(sl.ev_feat, p->sC));
+    sl.reid_launched = true;
+}
+
+// association half of the oldest submitted frame, on sB: DeepSort.update with its host lifecycle.  While it runs, the ReID half
+// of the NEXT slot is started as soon as that slot's detector half is seen to be complete.
+static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {
+    YDST_CHECK(p->collected < p->submitted, "no frame in flight: submit one first");
+    const int si = (int)(p->drain % ydst_pipeline::kSlots);
+    ydst_pipeline::Slot& sl = p->slot[si];
+    ydst_pipeline::Slot& nxt = p->slot[(si + 1) % ydst_pipeline::kSlots];
+    YDST_CHECK(sl.busy && sl.n_collected < sl.n_frames, "pipeline slot bookkeeping is inconsistent");
+    const int sub = sl.n_collected++;
+    ++p->collected;
+    struct Release {                                                   // the slot is free again once its last frame has been handed back
+        ydst_pipeline* p; ydst_pipeline::Slot& sl;
+        ~Release() { if (sl.n_collected == sl.n_frames && sl.launched) { sl.busy = false; ++p->drain; } }
+    } release{p, sl};
+    Detector& det = *p->det;
+    const int md = det.nms_.max_det;
     if (!sl.launched) pipeline_launch_detector(p, sl);                 // partial batch
+    pipeline_launch_reid(p, sl, true);
     if (!sl.feat_ready) {
-        YDST_CUDA(cudaEventSynchronize(sl.ev_det));
-        const uint8_t* frames[8]; const float* boxes[8]; int ms[8];
-        int off = 0;
-        for (int b = 0; b < sl.n_frames; ++b) {
-            YDST_CHECK(sl.h_counts[b * 8 + 2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[b * 8]);
-            frames[b] = sl.frame_dev + b * bytes; boxes[b] = sl.tlwh + (size_t)b * md * 4;
-            ms[b] = sl.h_counts[b * 8 + 1] > 0 ? sl.h_counts[b * 8 + 3] : 0;
-            sl.feat_off[b] = off; off += ms[b];
-        }
-        YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sB));
-        p->reid->extract_multi(frames, det.H, det.W, boxes, ms, sl.n_frames, p->feat, p->sB);
-        YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sB));
+        YDST_CUDA(cudaStreamWaitEvent(p->sB, sl.ev_feat, 0));          // the tracker's kernels read this slot's features
         sl.feat_ready = true;
     }
+    if (nxt.busy) pipeline_launch_reid(p, nxt, false);
     const int n_dets = sl.h_counts[sub * 8 + 1], m = sl.h_counts[sub * 8 + 3];
     if (n_dets_host) *n_dets_host = n_dets;
     if (dets_host && sl.want_dets) memcpy(dets_host, sl.h_dets + (size_t)sub * md * 6, sizeof(float) * 6 * n_dets);
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
     const float* h_cls = sl.h_cls + (size_t)sub * md;
     for (int i = 0; i < m; ++i) p->h_payload[i] = (int)h_cls[i];
-    p->trk->update(sl.tlwh + (size_t)sub * md * 4, p->feat + (size_t)sl.feat_off[sub] * 512, p->h_payload, nullptr, m, out_host, k_host, p->sB);
-    if (sl.h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    p->trk->update(sl.tlwh + (size_t)sub * md * 4, sl.feat + (size_t)sl.feat_off[sub] * 512, p->h_payload, nullptr, m, out_host, k_host, p->sB);
+    if (nxt.busy) pipeline_launch_reid(p, nxt, false);
+    if (sub == sl.n_frames - 1) {
+        // the crop error flag of this slot's ReID has long landed (the tracker waited for ev_feat on the device; make it host-visible)
+        YDST_CUDA(cudaEventSynchronize(sl.ev_feat));
+        if (sl.h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
+    }
     return 0;
 }
 

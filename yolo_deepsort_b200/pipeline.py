@@ -44,7 +44,7 @@ class FramePipeline:
             else:
                 f = frame.numpy() if isinstance(frame, torch.Tensor) else np.ascontiguousarray(frame)
                 assert f.dtype == np.uint8 and f.shape == (self.model.img_size[0], self.model.img_size[1], 3)
-                self._keep = (getattr(self, '_keep', ()) + (f,))[-4 * self.micro_batch:]   # async H2D copies read them until collected
+                self._keep = (getattr(self, '_keep', ()) + (f,))[-4 * self.micro_batch - 2:]   # async H2D copies read them until collected
                 check(lib().ydst_pipeline_submit(self._h, f.ctypes.data, 1, int(want_dets), stream_ptr()))
 
     def collect(self, want_dets=True):
