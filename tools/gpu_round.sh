@@ -16,15 +16,15 @@ bench)
   tail -3 gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_reference.json; cat gpurun_out/bench.json ;;
 launches)
   # graphs off so that every kernel is a separate stream launch in the list (same kernels, same order)
-  YDST_GRAPH=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/launches_run.log 2>&1
+  YDST_GRAPH=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 500 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/launches_run.log 2>&1
   tail -1 gpurun_out/launches_run.log | cut -c1-200 ;;
 full)
-  # the four representative convolutions of a yolov3-608 frame: 1x1 256->128 @76, 3x3 128->256 @76, 1x1 1024->512 @19, 3x3 512->1024 @19
+  # (micro-batch 1 so that launch indices address single-frame kernels) the four representative convolutions of a yolov3-608 frame: 1x1 256->128 @76, 3x3 128->256 @76, 1x1 1024->512 @19, 3x3 512->1024 @19
   YDST_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 288 -c 2 -o gpurun_out/prof_full_76 -f \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_a.log 2>&1
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --micro-batch 1 > gpurun_out/ncu_full_a.log 2>&1
   YDST_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 322 -c 2 -o gpurun_out/prof_full_19 -f \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_b.log 2>&1
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --micro-batch 1 > gpurun_out/ncu_full_b.log 2>&1
   for f in 76 19; do ncu -i gpurun_out/prof_full_$f.ncu-rep --page raw --csv > gpurun_out/prof_full_$f.csv 2>/dev/null; done
   ls -la gpurun_out/*.ncu-rep ;;
 esac

@@ -18,7 +18,7 @@ for r in data:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[ix["Metric Value"]]) / 1e3
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, f"launches_{tag}.md"), "w") as f:
-    f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 python bench.py --steps 4 --warmup 3` (YDST_GRAPH=0)\n\n")
+    f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 500 python bench.py --steps 8 --warmup 3` (YDST_GRAPH=0, default micro-batch)\n\n")
     f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| {k} | {a[0]} | {a[1]:.1f} | {a[1] / tot:.3f} |\n")
