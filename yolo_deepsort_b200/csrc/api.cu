@@ -2,6 +2,7 @@
 #include <cstring>
 #include <mutex>
 
+#include <algorithm>
 #include "../../include/ydst.h"
 #include "assoc.cuh"
 #include "net.cuh"
@@ -210,15 +211,13 @@ int ydst_conv_tiling(int N, int H, int W, int cin, int cout, int k, int* block_n
     const long long P = (long long)N * (H + 2) * (W + 2);
     const int m_tiles = (int)((P + 127) / 128);
     const int halo = k == 3 ? W + 3 : 0;
-    int a_rows = 128 + 2 * halo;
-    const int boxes = (a_rows + 255) / 256;
-    a_rows = ((a_rows + boxes - 1) / boxes) * boxes;
     const int cout16 = (cout + 15) & ~15;
-    const ConvTiling t = conv_tc_choose_tiling(m_tiles, cout16, k * k, cin / 64, a_rows, (size_t)48 << 20, 8192);
+    const ConvTiling t = conv_tc_choose_tiling(m_tiles, cout16, k * k, cin / 64, halo, (size_t)48 << 20, 8192);
     if (block_n) *block_n = t.bn;
     if (ksplit) *ksplit = t.ksplit;
     if (occupancy) *occupancy = t.occupancy;
-    if (ctas) *ctas = m_tiles * ((cout16 + t.bn - 1) / t.bn) * t.ksplit;
+    if (ctas) *ctas = t.persistent ? std::min(148, ((m_tiles + t.mpair - 1) / t.mpair) * ((cout16 + t.bn - 1) / t.bn))
+                            : ((m_tiles + t.mpair - 1) / t.mpair) * ((cout16 + t.bn - 1) / t.bn) * t.ksplit;
     if (model_us) *model_us = t.model_us;
     YDST_API_END
 }

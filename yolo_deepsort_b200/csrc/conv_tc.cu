@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
 // (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
 // ---------------------------------------------------------------------------------------------
-template <bool kMish, bool kPers>
+template <bool kMish, bool kPers, bool kPair>
 __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -466,7 +466,9 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
 
     const bool k3 = p.R == 3;
     // A stage: 3x3 -> one halo chunk (a_boxes x a_box_rows rows of 128 B); 1x1 -> tpb tiles of 128 rows
-    const uint32_t a_stage_bytes = k3 ? (((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u) : (uint32_t)p.tpb * (kBlockM * 128u);
+    constexpr int mp = kPair ? 2 : 1;                          // 128-row accumulators per tile (compile time: the issue loops unroll)
+    const uint32_t a_tile_bytes = (uint32_t)(kBlockM * mp) * 128u;
+    const uint32_t a_stage_bytes = k3 ? (((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u) : (uint32_t)p.tpb * a_tile_bytes;
     const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
     const uint32_t tmem_slot = bar_tempty + 16u, flag_slot = tmem_slot + 4u;
     float* s_sb = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.block_n * (kPers ? 2 : 1)) tmem_cols <<= 1;
+    while ((int)tmem_cols < p.block_n * mp * (kPers ? 2 : 1)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_stages * nab; ++s) mbar_init(bar_fullA + 8u * s, 1);
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
             uint32_t pha = 1, phb = 1;
             int tm, tn;
             for (int it = 0; tile_at(it, tm, tn); ++it) {
-                const int p0 = tm * kBlockM, n0 = tn * p.block_n;
+                const int p0 = tm * kBlockM * mp, n0 = tn * p.block_n;
                 int jm = 0, js = 0;                            // next weight stage to issue: macro step jm, sub-stage js
                 const int total_b = nmacro * nbs;
                 auto issue_b = [&]() {
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
             int tm, tn;
             for (int it = 0; tile_at(it, tm, tn); ++it) {
                 const int ab = it & 1;                         // accumulator buffer
-                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n * mp);
                 if (kPers) mbar_wait_hot(bar_tempty + 8u * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 uint32_t acc = 0;
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                         uint32_t b_lo = 0;
                         for (int r = 0; r < 3; ++r, a_lo += row_step) {
                             // filter row r reads chunk rows up to r*Wp + 2 + 127
-                            const int need = min(p.a_boxes - 1, (r * p.in_Wp + 129) / p.a_box_rows);
+                            const int need = min(p.a_boxes - 1, (r * p.in_Wp + kBlockM * mp + 1) / p.a_box_rows);
                             while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
                             for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
                                 if (t_in == 0) {
@@ -616,10 +618,14 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                                 }
                                 uint32_t hi_a = hi;
                                 if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
-                                umma_f16_lh(tmem_d, a_lo, b_lo, hi_a, idesc, acc);
-                                umma_f16_lh(tmem_d, a_lo + 2u, b_lo + 2u, hi_a, idesc, 1u);
-                                umma_f16_lh(tmem_d, a_lo + 4u, b_lo + 4u, hi_a, idesc, 1u);
-                                umma_f16_lh(tmem_d, a_lo + 6u, b_lo + 6u, hi_a, idesc, 1u);
+#pragma unroll
+                                for (int h = 0; h < mp; ++h) {         // the M tiles of the pair share this weight tile
+                                    const uint32_t td = tmem_d + (uint32_t)(h * p.block_n), al = a_lo + (uint32_t)h * (kBlockM * 8u);
+                                    umma_f16_lh(td, al, b_lo, hi_a, idesc, acc);
+                                    umma_f16_lh(td, al + 2u, b_lo + 2u, hi_a, idesc, 1u);
+                                    umma_f16_lh(td, al + 4u, b_lo + 4u, hi_a, idesc, 1u);
+                                    umma_f16_lh(td, al + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                                }
                                 acc = 1u;
                                 b_lo += b_tile16;
                                 if (++t_in == p.tpb) {
@@ -635,11 +641,15 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                         if (acc == 0 && it == 0) trace_mark(p, 3);
                         uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
                         const int nsl = min(p.tpb, ncb - i * p.tpb);                  // the last group of a split may be short
-                        for (int t = 0; t < nsl; ++t, a_lo += (kBlockM * 128u) >> 4, b_lo += b_tile16) {
-                            umma_f16_lh(tmem_d, a_lo, b_lo, hi, idesc, acc);
-                            umma_f16_lh(tmem_d, a_lo + 2u, b_lo + 2u, hi, idesc, 1u);
-                            umma_f16_lh(tmem_d, a_lo + 4u, b_lo + 4u, hi, idesc, 1u);
-                            umma_f16_lh(tmem_d, a_lo + 6u, b_lo + 6u, hi, idesc, 1u);
+                        for (int t = 0; t < nsl; ++t, a_lo += a_tile_bytes >> 4, b_lo += b_tile16) {
+#pragma unroll
+                            for (int h = 0; h < mp; ++h) {
+                                const uint32_t td = tmem_d + (uint32_t)(h * p.block_n), al = a_lo + (uint32_t)h * (kBlockM * 8u);
+                                umma_f16_lh(td, al, b_lo, hi, idesc, acc);
+                                umma_f16_lh(td, al + 2u, b_lo + 2u, hi, idesc, 1u);
+                                umma_f16_lh(td, al + 4u, b_lo + 4u, hi, idesc, 1u);
+                                umma_f16_lh(td, al + 6u, b_lo + 6u, hi, idesc, 1u);
+                            }
                             acc = 1u;
                         }
                         umma_commit(bar_emptyB + 8u * sb);
@@ -659,28 +669,30 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
         int stores = 0, staged_tn = -1;
         int tm, tn;
         for (int it = 0; tile_at(it, tm, tn); ++it) {
-            const int p0 = tm * kBlockM, n0 = tn * p.block_n;
+            const int n0 = tn * p.block_n;
             const int ab = it & 1;
-            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n);
             const uint32_t bar_full = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
-            const uint32_t bar_rel = kPers ? bar_tempty + 8u * ab : 0u;
             if (tn != staged_tn) {                             // M runs fastest: the column block (and its scale/bias) rarely changes
                 if (it > 0) epi_bar_sync();                    // everyone is done with the previous tile's scale/bias
                 stage_scale_bias(p, n0, s_sb);
                 staged_tn = tn;
             }
+            if (it == 0) grid_dep_wait();                      // residual / workspace / output buffers belong to earlier kernels
+            for (int h = 0; h < mp; ++h) {                     // the 128-row accumulators of this tile, one after the other
+            const int p0 = (tm * mp + h) * kBlockM;
+            const uint32_t tmem_d = tmem_base + (uint32_t)((ab * mp + h) * p.block_n);
+            const uint32_t bar_rel = (kPers && h == mp - 1) ? bar_tempty + 8u * ab : 0u;
             const long long pp = (long long)p0 + row;
             const int rem = (int)(pp % HpWp);
             const int y = rem / Wp, x = rem - y * Wp;
             const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
-            if (it == 0) grid_dep_wait();                      // residual / workspace / output buffers belong to earlier kernels
             if (p.ksplit == 1) {
-                if (it == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
+                if (it == 0 && h == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
                 if (p.store_tma)
                     epilogue_tile_tma<kMish>(p, &maps.a[1], smem_base, smem_raw + (smem_base - smem_u32(smem_raw)), tmem_d, warp, n0, p0, pp, valid,
                                              s_sb, bar_full, par, bar_rel, stores);
                 else epilogue_tile<kMish>(p, tmem_d, warp, n0, pp, valid, s_sb, bar_full, par, bar_rel);
-                if (it == 0 && threadIdx.x == 0) trace_mark(p, 6);
+                if (it == 0 && h == 0 && threadIdx.x == 0) trace_mark(p, 6);
             } else {
                 const int bn = p.block_n;
                 const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
@@ -739,6 +751,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                     }
                 }
             }
+            }   // h
         }
         if (p.store_tma && threadIdx.x == 0) tma_store_wait_read<0>();    // smem must outlive the bulk reads; writes are complete at grid end
     }
@@ -802,24 +815,37 @@ static int env_int(const char* name, int dflt) {
 //   * tensor time: a 128 x bn x 16 MMA takes ~max(16, bn/2) clocks;
 //   * barrier round trips of the single issuing thread (~150 clocks per stage).
 // Small-M layers may split K over channel blocks (grid.z); the fp32 partials then take a round trip through the workspace.
-ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets) {
+ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets) {
     const int kSms = 148;
     const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 600.0, kClkPerUs = 1900.0;
-    const int chunk_bytes = (a_rows * 128 + 1023) & ~1023;
     const bool tma_store_ok = cout16 % 64 == 0;
     ConvTiling best{};
     best.model_us = 1e30;
     int bn_cap = 32;
     while (bn_cap < cout16 && bn_cap < 256) bn_cap <<= 1;
+    const int force_bn = env_int("YDST_FORCE_BN", 0);          // tuning aid: restrict the N tile (when the layer allows it)
+    // measured on B200: neither M pairs nor the persistent tile loop beat the plain one-tile-per-CTA launch yet
+    // (1163 / 1198 / 1226 frames/s for pair+persistent / persistent / neither at micro-batch 4), so both are opt-in
+    const int allow_pair = env_int("YDST_MPAIR", 0);
+    for (int mp = 1; mp <= 2; ++mp)
     for (int bn = bn_cap; bn >= 32; bn >>= 1) {
+        if (force_bn && bn != std::min(force_bn, bn_cap)) continue;
         const int n_tiles = (cout16 + bn - 1) / bn;
+        // a pair of M tiles per CTA shares every weight stage (half the weight traffic per output); only worth it when there are
+        // tiles to spare, i.e. at least two waves of single tiles
+        if (mp == 2 && (!allow_pair || (long long)m_tiles128 * n_tiles < 2 * kSms || bn > 128)) continue;
+        const int m_tiles = (m_tiles128 + mp - 1) / mp;
+        int a_rows = kBlockM * mp + 2 * halo;
+        { const int boxes = (a_rows + 255) / 256; a_rows = ((a_rows + boxes - 1) / boxes) * boxes; }
+        const int chunk_bytes = (a_rows * 128 + 1023) & ~1023;
+        if (chunk_bytes > 96 * 1024) continue;
         const long long tiles = (long long)m_tiles * n_tiles;
         int last_ks = -1;
         for (int cps = cin_blocks; cps >= 1; --cps) {
             const int ks = (cin_blocks + cps - 1) / cps;
             if (ks == last_ks) continue;
             last_ks = ks;
-            if (ks > 1 && ((size_t)ks * tiles * kBlockM * bn * 4 > ws_bytes || tiles > max_tickets)) continue;
+            if (ks > 1 && ((size_t)ks * tiles * kBlockM * bn * 4 > ws_bytes || tiles > max_tickets || mp > 1)) continue;
             if (ks > 16) continue;
             const long long ctas = tiles * ks;
             const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = 108 * 1024;
@@ -833,7 +859,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                 const int nmacro = taps == 9 ? cps : (cps + tpb - 1) / tpb;
                 const int nbs = taps == 9 ? 9 / tpb : 1;
                 const int total_b = nmacro * nbs;
-                const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * 128;
+                const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * mp * 128;
                 const int b_stage = tpb * bn * 128;
                 const int a_stages = std::min(nmacro, taps == 9 ? 2 : 4);
                 const int fixed = a_stages * a_stage + 4096;
@@ -841,7 +867,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                 // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
                 for (int pass = 0; pass < 3; ++pass) {
                     const bool pers = pass == 2;
-                    if (pers && (ks > 1 || tiles <= kSms || bn > 256 / 1 || !env_int("YDST_PERSISTENT", 1))) continue;
+                    if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !env_int("YDST_PERSISTENT", 0))) continue;
                     const int staging = pers ? 32 * 1024 : 0;
                     const int budget = (pass == 0 ? budget_2 : budget_max) - staging;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
@@ -855,12 +881,12 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                     const int occ = (!pers && smem <= 112 * 1024) ? 2 : 1;
                     const double inflight = (double)a_st * a_stage + (double)b_stages * b_stage;
                     const double rate = std::min(kFill, inflight / kLat);
-                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * 128.0) + (double)taps * bn * 128);
-                    const double mma = (double)cps * taps * 4 * std::max(16.0, bn / 2.0);
+                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + (double)taps * bn * 128);
+                    const double mma = (double)cps * taps * 4 * mp * std::max(16.0, bn / 2.0);
                     const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
                     const double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
                     const bool st = tma_store_ok && bn >= 64 && ks == 1;
-                    const double epi = 700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0);
+                    const double epi = mp * (700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0));
                     const double per_sm = std::ceil((double)ctas / kSms);
                     double t = kSetup + kFirst + per_sm * main_clk + std::ceil(per_sm / occ) * epi;
                     if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, epi) + epi;   // front paid once, epilogues hidden
@@ -870,15 +896,16 @@ ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_bloc
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
+                        best.mpair = mp;
                     }
                 }
             }
         }
     }
     if (getenv("YDST_DEBUG_PLAN"))
-        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d pers %d model %.1f us\n", m_tiles,
+        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d pers %d mpair %d model %.1f us\n", m_tiles128,
                 cout16, taps, cin_blocks, best.bn, best.ksplit, best.cbs_per_split, best.tpb, best.a_stages, best.b_stages, best.smem_bytes,
-                best.occupancy, best.persistent, best.model_us);
+                best.occupancy, best.persistent, best.mpair, best.model_us);
     return best;
 }
 
@@ -917,18 +944,18 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
         p.P_total = out.pixels();
         m_tiles = (int)((p.P_total + kBlockM - 1) / kBlockM);
         const int halo = R == 3 ? in.W + 2 + 1 : 0;
-        const int a_rows = kBlockM + 2 * halo;
-        if (p.block_k == 64 && a_rows * 128 <= 96 * 1024 && env_int("YDST_CONV_V2", 1)) {
+        if (p.block_k == 64 && (kBlockM + 2 * halo) * 128 <= 96 * 1024 && env_int("YDST_CONV_V2", 1)) {
             // ---- halo kernel ----
             p.v2 = 1;
             p.halo = halo;
+            ConvTiling t = conv_tc_choose_tiling(m_tiles, p.cout, R * S, p.cin_blocks, halo, ws ? ws->partial_bytes : 0, ws ? ws->n_tickets : 0);
+            YDST_CHECK(t.bn >= 32, "no feasible tiling for this convolution");
+            p.mpair = t.mpair;
+            const int a_rows = kBlockM * t.mpair + 2 * halo;
             p.a_boxes = (a_rows + 255) / 256;
             p.a_box_rows = (a_rows + p.a_boxes - 1) / p.a_boxes;
-            ConvTiling t = conv_tc_choose_tiling(m_tiles, p.cout, R * S, p.cin_blocks, p.a_box_rows * p.a_boxes, ws ? ws->partial_bytes : 0,
-                                                 ws ? ws->n_tickets : 0);
-            YDST_CHECK(t.bn >= 32, "no feasible tiling for this convolution");
             const int force_cps = env_int("YDST_FORCE_CPS", 0);         // test hook: force a K split of the planner's tile
-            if (force_cps > 0 && ws) {
+            if (force_cps > 0 && ws && t.mpair == 1 && !t.persistent) {
                 const int cps = std::min(force_cps, p.cin_blocks);
                 const int ks = (p.cin_blocks + cps - 1) / cps;
                 const long long tiles = (long long)m_tiles * ((p.cout + t.bn - 1) / t.bn);
@@ -942,7 +969,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             }
             p.block_n = t.bn; p.ksplit = t.ksplit; p.cbs_per_split = t.cbs_per_split; p.a_stages = t.a_stages; p.b_stages = t.b_stages;
             p.tpb = t.tpb;
-            p.m_tiles = m_tiles; p.n_tiles = (p.cout + t.bn - 1) / t.bn;
+            p.m_tiles = (m_tiles + t.mpair - 1) / t.mpair; p.n_tiles = (p.cout + t.bn - 1) / t.bn;
             p.persistent = t.persistent;
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
@@ -961,7 +988,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             } else {
                 cuuint64_t dims[3] = {64, (cuuint64_t)p.P_total, (cuuint64_t)p.cin_blocks};
                 cuuint64_t strides[2] = {(cuuint64_t)in.ctot * 2, 128};
-                cuuint32_t box[3] = {64u, (cuuint32_t)kBlockM, (cuuint32_t)t.tpb};
+                cuuint32_t box[3] = {64u, (cuuint32_t)(kBlockM * t.mpair), (cuuint32_t)t.tpb};
                 encode(&L.tmA[0], in.base + in.coff, 3, dims, strides, box, 128);
                 cuuint64_t bdims[3] = {64, (cuuint64_t)p.cout, (cuuint64_t)p.cin_blocks};
                 cuuint64_t bstrides[2] = {(cuuint64_t)K * 2, 128};
@@ -976,12 +1003,12 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             }
             L.stages = 0;
             L.smem_bytes = t.smem_bytes + 1024;
-            L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + t.bn - 1) / t.bn), (unsigned)t.ksplit);
+            L.grid = dim3((unsigned)p.m_tiles, (unsigned)p.n_tiles, (unsigned)t.ksplit);
             if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
             if (getenv("YDST_DEBUG_PLAN"))
-                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d model %.1fus\n",
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d model %.1fus\n",
                         R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.tpb, t.a_stages, t.b_stages,
-                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, t.model_us);
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, p.mpair, t.model_us);
             return;
         }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1076,8 +1103,10 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         static bool attr2_set = false;
         static int use_pdl = 1;
         if (!attr2_set) {
-            const void* fns[4] = {(const void*)conv_tc2_kernel<false, false>, (const void*)conv_tc2_kernel<false, true>,
-                                  (const void*)conv_tc2_kernel<true, false>, (const void*)conv_tc2_kernel<true, true>};
+            const void* fns[8] = {(const void*)conv_tc2_kernel<false, false, false>, (const void*)conv_tc2_kernel<false, true, false>,
+                                  (const void*)conv_tc2_kernel<true, false, false>,  (const void*)conv_tc2_kernel<true, true, false>,
+                                  (const void*)conv_tc2_kernel<false, false, true>,  (const void*)conv_tc2_kernel<false, true, true>,
+                                  (const void*)conv_tc2_kernel<true, false, true>,   (const void*)conv_tc2_kernel<true, true, true>};
             for (const void* fn : fns) {
                 YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
@@ -1110,11 +1139,17 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-        const bool mish = L.p.act == ACT_MISH, pers = L.p.persistent != 0;
-        if (mish && pers) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true>, maps, prm));
-        else if (mish) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false>, maps, prm));
-        else if (pers) YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true>, maps, prm));
-        else YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false>, maps, prm));
+        const int variant = (L.p.act == ACT_MISH ? 1 : 0) | (L.p.persistent ? 2 : 0) | (L.p.mpair == 2 ? 4 : 0);
+        switch (variant) {
+            case 0: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, false>, maps, prm)); break;
+            case 1: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false, false>, maps, prm)); break;
+            case 2: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true, false>, maps, prm)); break;
+            case 3: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true, false>, maps, prm)); break;
+            case 4: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, true>, maps, prm)); break;
+            case 5: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false, true>, maps, prm)); break;
+            case 6: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true, true>, maps, prm)); break;
+            default: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true, true>, maps, prm)); break;
+        }
         if (trace_on == 1) {
             unsigned long long h[16];
             YDST_CUDA(cudaStreamSynchronize(stream));

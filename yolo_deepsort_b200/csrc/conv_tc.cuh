@@ -38,6 +38,7 @@ struct ConvTcParams {
     int a_stages, b_stages;
     int persistent;       // 1: 1-D grid of at most one CTA per SM, each looping over output tiles with two TMEM accumulators
     int m_tiles, n_tiles;
+    int mpair;            // 128-row accumulators per CTA tile (1 or 2): a pair of M tiles shares every weight stage
     int tpb;              // 64-channel K slices per weight stage (3x3: filter taps, 1 | 3 | 9; 1x1: channel blocks)
     int store_tma;        // 1: epilogue stages 64-column groups in swizzled smem and writes them with TMA bulk stores
     float* ws;            // split-K partials [tile][split][chunk][128][16] fp32
@@ -73,8 +74,8 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                   const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
                   const ConvWorkspace* ws = nullptr);
 // the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
-struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent; double model_us; };
-ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int a_rows, size_t ws_bytes, int max_tickets);
+struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair; double model_us; };
+ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets);
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_trace_dump();   // YDST_CONV_TRACE=2: print the per-launch timeline collected so far (debug aid)
 double conv_tc_flops(const ConvTcLaunch& L);   // useful 2*M*N*K (logical, unpadded)
