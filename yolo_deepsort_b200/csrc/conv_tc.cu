@@ -48,7 +48,7 @@ __device__ __forceinline__ void prefetch_next_weights(const ConvTcParams& p) {
 }
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id = 1) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // The single MMA-issuing thread is the critical path of a batch-1 convolution (hundreds of short k-steps per CTA), so the
 // descriptors are not rebuilt per instruction: the high word (SBO, version, swizzle mode) is loop-invariant and the low word
@@ -189,10 +189,10 @@ __device__ __forceinline__ void load_res_group(const ConvTcParams& p, long long 
 }
 
 // stage this CTA's scale/bias columns in shared memory: s_sb[0..bn) = scale, s_sb[bn..2bn) = bias (epilogue threads only)
-__device__ __forceinline__ void stage_scale_bias(const ConvTcParams& p, int n0, float* s_sb) {
-    for (int i = threadIdx.x; i < 2 * p.block_n; i += 128)
+__device__ __forceinline__ void stage_scale_bias(const ConvTcParams& p, int n0, float* s_sb, int tid = threadIdx.x, int bar = 1) {
+    for (int i = tid; i < 2 * p.block_n; i += 128)
         s_sb[i] = i < p.block_n ? __ldg(p.scale + n0 + i) : __ldg(p.bias + n0 + i - p.block_n);
-    epi_bar_sync();
+    epi_bar_sync(bar);
 }
 
 template <bool kMish>
@@ -246,9 +246,9 @@ template <bool kMish>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const CUtensorMap* out_map, uint32_t stage_smem,
                                                   unsigned char* stage_ptr, uint32_t tmem_base, int warp, int n0, int p0, long long pix,
                                                   bool valid, const float* s_sb, uint32_t bar_tmem, uint32_t parity, uint32_t bar_release,
-                                                  int& stores) {
+                                                  int& stores, int tid = threadIdx.x, int bar = 1) {
     const int ngroups = p.block_n >> 6;
-    const int row = threadIdx.x;                                   // 0..127
+    const int row = tid;                                           // 0..127 within the epilogue warpgroup
     uint4 rcur[8], rnext[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) rcur[q] = rnext[q] = make_uint4(0, 0, 0, 0);
@@ -265,8 +265,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 64 + sub * 16), v[sub]);
         if (g + 1 < ngroups && c0 + 64 < p.cout) load_res_group(p, pix, c0 + 64, 64, valid, rnext);
         if (stores >= 2) {                                         // the buffer about to be refilled was read two stores ago
-            if (threadIdx.x == 0) tma_store_wait_read<1>();
-            epi_bar_sync();
+            if (tid == 0) tma_store_wait_read<1>();
+            epi_bar_sync(bar);
         }
         tcgen05_wait_ld();
         if (bar_release && (g + 1 == ngroups || c0 + 64 >= p.cout)) {   // last read of this accumulator: hand it back to the MMA issuer
@@ -294,9 +294,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
         if (g == 0) trace_mark_epi(p, 12);
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
         if (g == 0) trace_mark_epi(p, 13);
-        epi_bar_sync();
+        epi_bar_sync(bar);
         if (g == 0) trace_mark_epi(p, 14);
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             tma_store_2d(out_map, buf, p.out_coff + c0, p0);
             tma_store_commit();
         }
@@ -457,11 +457,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // any 128-byte row of a 1024-byte-aligned buffer with base_offset = 0 (mode 0, the default).  Setting base_offset to
 // (addr >> 7) & 7 (mode 1) double-applies the shift and produces garbage; the knob stays as a hardware-behaviour probe.
 // ---------------------------------------------------------------------------------------------
+// Persistent instantiations run TWO epilogue warpgroups (warps 0-3 and 4-7): tile i is drained by group i & 1, which also owns
+// accumulator buffer i & 1, so the epilogues of consecutive tiles overlap each other as well as the main loop.
+static constexpr int kThreadsPers = 320;
 template <bool kMish, bool kPers, bool kPair>
-__global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
+__global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
+    constexpr int kEpiGroups = kPers ? 2 : 1;                  // epilogue warpgroups of 4 warps
+    constexpr int kProdWarp = 4 * kEpiGroups, kMmaWarp = kProdWarp + 1;
     if (threadIdx.x == 0) trace_mark(p, 0);
 
     const bool k3 = p.R == 3;
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
     // (they are being refilled for the next tile while the epilogue runs); otherwise the staging aliases the dead stages
-    const uint32_t stage_area = (kPers && p.store_tma) ? 2u * kBlockM * 128u : 0u;
+    const uint32_t stage_area = (kPers && p.store_tma) ? 4u * kBlockM * 128u : 0u;    // two 16 KB buffers per epilogue warpgroup
     const uint32_t a_base = smem_base + stage_area;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
@@ -495,12 +500,12 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 4 && elect_one()) {
+    if (warp == kProdWarp && elect_one()) {
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
         if (p.store_tma) tma_prefetch_desc(&maps.a[1]);
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, tmem_cols);
         tmem_relinquish();
     }
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
         return true;
     };
 
-    if (warp == 4) {
+    if (warp == kProdWarp) {
         if (elect_one()) {
             // ================= TMA producer =================
             int sa = 0, sb = 0;
@@ -581,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
             }
             prefetch_next_weights(p);
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         if (elect_one()) {
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
@@ -664,20 +669,28 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
         }
     } else {
         // ================= epilogue =================
-        const int row = threadIdx.x;
+        const int eg = warp >> 2;                              // epilogue warpgroup (always 0 unless persistent)
+        const int tid = threadIdx.x & 127, ebar = 1 + eg;
+        const int wq = warp & 3;                               // TMEM lane quarter of this warp
+        const int row = tid;
+        float* s_sbg = s_sb + eg * 512;
+        const uint32_t stage_g = smem_base + (uint32_t)eg * (2u * kBlockM * 128u);
         const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
         int stores = 0, staged_tn = -1;
+        bool first = true;
         int tm, tn;
         for (int it = 0; tile_at(it, tm, tn); ++it) {
+            if (kPers && (it & 1) != eg) continue;             // the other warpgroup drains this tile
             const int n0 = tn * p.block_n;
             const int ab = it & 1;
             const uint32_t bar_full = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
             if (tn != staged_tn) {                             // M runs fastest: the column block (and its scale/bias) rarely changes
-                if (it > 0) epi_bar_sync();                    // everyone is done with the previous tile's scale/bias
-                stage_scale_bias(p, n0, s_sb);
+                if (!first) epi_bar_sync(ebar);                // everyone is done with the previous tile's scale/bias
+                stage_scale_bias(p, n0, s_sbg, tid, ebar);
                 staged_tn = tn;
             }
-            if (it == 0) grid_dep_wait();                      // residual / workspace / output buffers belong to earlier kernels
+            if (first) grid_dep_wait();                        // residual / workspace / output buffers belong to earlier kernels
+            first = false;
             for (int h = 0; h < mp; ++h) {                     // the 128-row accumulators of this tile, one after the other
             const int p0 = (tm * mp + h) * kBlockM;
             const uint32_t tmem_d = tmem_base + (uint32_t)((ab * mp + h) * p.block_n);
@@ -689,9 +702,9 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
             if (p.ksplit == 1) {
                 if (it == 0 && h == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
                 if (p.store_tma)
-                    epilogue_tile_tma<kMish>(p, &maps.a[1], smem_base, smem_raw + (smem_base - smem_u32(smem_raw)), tmem_d, warp, n0, p0, pp, valid,
-                                             s_sb, bar_full, par, bar_rel, stores);
-                else epilogue_tile<kMish>(p, tmem_d, warp, n0, pp, valid, s_sb, bar_full, par, bar_rel);
+                    epilogue_tile_tma<kMish>(p, &maps.a[1], stage_g, smem_raw + (stage_g - smem_u32(smem_raw)), tmem_d, wq, n0, p0, pp, valid,
+                                             s_sbg, bar_full, par, bar_rel, stores, tid, ebar);
+                else epilogue_tile<kMish>(p, tmem_d, wq, n0, pp, valid, s_sbg, bar_full, par, bar_rel);
                 if (it == 0 && h == 0 && threadIdx.x == 0) trace_mark(p, 6);
             } else {
                 const int bn = p.block_n;
@@ -704,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                     if (n0 + ch * 16 >= p.cout) break;
                     __syncwarp();
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), v);
+                    tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 16), v);
                     tcgen05_wait_ld();
                     if (!valid) continue;
                     float4* dst = reinterpret_cast<float4*>(mine + ch * 16);
@@ -746,18 +759,18 @@ __global__ void __launch_bounds__(kThreads, kPers ? 1 : 2) conv_tc2_kernel(const
                                     acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
                                 }
                             }
-                            finish16<kMish>(p, acc, c, s_sb + ch * 16, s_sb + bn + ch * 16, r0, r1, pp);
+                            finish16<kMish>(p, acc, c, s_sbg + ch * 16, s_sbg + bn + ch * 16, r0, r1, pp);
                         }
                     }
                 }
             }
             }   // h
         }
-        if (p.store_tma && threadIdx.x == 0) tma_store_wait_read<0>();    // smem must outlive the bulk reads; writes are complete at grid end
+        if (p.store_tma && tid == 0) tma_store_wait_read<0>();    // smem must outlive the bulk reads; writes are complete at grid end
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         __syncwarp();
         tmem_dealloc(tmem_base, tmem_cols);
     }
@@ -862,18 +875,18 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * mp * 128;
                 const int b_stage = tpb * bn * 128;
                 const int a_stages = std::min(nmacro, taps == 9 ? 2 : 4);
-                const int fixed = a_stages * a_stage + 4096;
+                const int fixed = a_stages * a_stage + 6144;
                 // pass 0: leave room for a second CTA on the SM; pass 1: whole SM; pass 2: persistent -- one CTA per SM loops over
                 // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
                 for (int pass = 0; pass < 3; ++pass) {
                     const bool pers = pass == 2;
                     if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !env_int("YDST_PERSISTENT", 0))) continue;
-                    const int staging = pers ? 32 * 1024 : 0;
+                    const int staging = pers ? 64 * 1024 : 0;       // two 16 KB store buffers per epilogue warpgroup
                     const int budget = (pass == 0 ? budget_2 : budget_max) - staging;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
                     // a persistent CTA prefetches the next tile's operands while the current one computes: two stages of each at least
                     const int a_st = pers ? std::max(2, a_stages) : a_stages;
-                    const int fixed_p = a_st * a_stage + 4096;
+                    const int fixed_p = a_st * a_stage + 6144;
                     int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
                     if (b_stages < (pers ? 2 : 1)) continue;
                     int smem = fixed_p + b_stages * b_stage + staging;
@@ -974,7 +987,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
             p.store_tma = (!out_f32 && p.cout % 64 == 0 && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
-            if (t.persistent && !p.store_tma) t.smem_bytes -= 32 * 1024;   // no staging area needed
+            if (t.persistent && !p.store_tma) t.smem_bytes -= 64 * 1024;   // no staging area needed
             const int K = R * S * in.C;
             if (R == 3) {
                 cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1134,7 +1147,7 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
             g_trace_shape[slot] = L.p.Wo * 10000 + L.p.cout;
         }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = L.grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
+        cfg.gridDim = L.grid; cfg.blockDim = dim3(L.p.persistent ? kThreadsPers : kThreads); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
