@@ -205,6 +205,14 @@ int ydst_pipeline_step(ydst_pipeline* p, const uint8_t* frame_host, int32_t* out
  * may reuse its buffer.  want_dets: also bring the post-NMS detections back for _collect's dets_host.                              */
 int ydst_pipeline_submit(ydst_pipeline* p, const uint8_t* frame, int frame_is_host, int want_dets, void* stream);
 int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host);
+/* _submit for a frame of ANY size and channel order (the first "next" row of the scope table): the reader thread's BGR->RGB
+ * (yolo3/detect/video_detect.py:33-36) and ImageDetector's cv2.resize to the network size (yolo3/detect/img_detect.py:70) run on
+ * the device with OpenCV's fixed-point INTER_LINEAR arithmetic; detections are scaled back to the captured size (resize_boxes,
+ * yolo3/utils/model_build.py:12-19) and the ReID crops are cut from the captured frame, as DeepSort._get_features does.        */
+int ydst_pipeline_submit_frame(ydst_pipeline* p, const uint8_t* frame, int height, int width, int frame_is_host, int is_bgr, int want_dets,
+                               void* stream);
+/* the ingest kernel alone: cv2.resize(src, (dst_w, dst_h), INTER_LINEAR) on uint8 HxWx3, optionally swapping R and B; synchronises */
+int ydst_resize_u8(const uint8_t* src_dev, int src_h, int src_w, uint8_t* dst_dev, int dst_h, int dst_w, int swap_rb, void* stream);
 int ydst_pipeline_in_flight(const ydst_pipeline* p);
 /* A detector handle created with batch B > 1 makes B the pipeline's MICRO-BATCH: B consecutive frames of the stream share one
  * Darknet forward (and one ReID forward), which amortises the per-layer launch latency that bounds a batch-1 frame; up to 2B

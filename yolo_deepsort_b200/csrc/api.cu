@@ -30,6 +30,11 @@ struct ydst_pipeline {
     // batch k+1 (sC) and DeepSort.update of batch k (sB, with its host lifecycle).  Frame f lives in slot (f / B) % 3, position f % B.
     static constexpr int kSlots = 3;
     struct Slot {
+        uint8_t* orig_dev = nullptr;  // [B][orig_cap] the frames as captured (RGB), when they do not have the network size
+        uint8_t* raw_dev = nullptr;   // [orig_cap] staging for a BGR / host frame before the colour swap
+        size_t orig_cap = 0;          // bytes per frame in orig_dev
+        int fh[8] = {0}, fw[8] = {0}; // captured size of each frame
+        bool resized[8] = {false};
         float* feat = nullptr;        // [B * max_det][512]
         cudaEvent_t ev_feat = nullptr;
         bool reid_launched = false;
@@ -464,6 +469,7 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
         if (p->sC) cudaStreamSynchronize(p->sC);
         for (auto& sl : p->slot) {
             cudaFree(sl.frame_dev); cudaFree(sl.tlwh); cudaFree(sl.confd); cudaFree(sl.cls); cudaFree(sl.feat);
+            cudaFree(sl.orig_dev); cudaFree(sl.raw_dev);
             cudaFreeHost(sl.h_counts); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_cls);
             if (sl.ev_det) cudaEventDestroy(sl.ev_det);
             if (sl.ev_feat) cudaEventDestroy(sl.ev_feat);
@@ -493,8 +499,9 @@ static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) 
     det.forward_u8(sl.frame_dev, nullptr, p->sA);
     for (int b = 0; b < sl.n_frames; ++b) {
         det.nms_.run(det.pred + (size_t)b * det.rows * det.fields, det.rows, det.fields, p->conf, p->iou, p->sA);
-        // frame == network size, so resize_boxes' ratios are exactly 1 (yolo3/utils/model_build.py:12-19)
-        det.nms_.to_tracker_inputs(1.f, 1.f, p->mask_dev, p->n_mask, sl.tlwh + (size_t)b * md * 4, sl.confd + (size_t)b * md, sl.cls + (size_t)b * md, p->sA);
+            // resize_boxes: x *= w / W, y *= h / H with python-float ratios applied to fp32 boxes (yolo3/utils/model_build.py:12-19)
+        const float rw = (float)((double)sl.fw[b] / (double)det.W), rh = (float)((double)sl.fh[b] / (double)det.H);
+        det.nms_.to_tracker_inputs(rw, rh, p->mask_dev, p->n_mask, sl.tlwh + (size_t)b * md * 4, sl.confd + (size_t)b * md, sl.cls + (size_t)b * md, p->sA);
         YDST_CUDA(cudaMemcpyAsync(sl.h_counts + b * 8, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->sA));
         if (sl.want_dets)
             YDST_CUDA(cudaMemcpyAsync(sl.h_dets + (size_t)b * md * 6, det.nms_.dets, sizeof(float) * 6 * md, cudaMemcpyDeviceToHost, p->sA));
@@ -506,7 +513,8 @@ static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) 
     ++p->fill;                                                         // the next frame starts a new slot
 }
 
-static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_is_host, bool want_dets, cudaStream_t caller) {
+static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_is_host, bool want_dets, cudaStream_t caller, int fh = 0,
+                            int fw = 0, bool is_bgr = false) {
     YDST_CHECK(pipeline_can_submit(p), "the pipeline is full (%lld frames in flight): collect one first", p->submitted - p->collected);
     ydst_pipeline::Slot& sl = p->slot[p->fill % ydst_pipeline::kSlots];
     if (!sl.busy) {
@@ -516,13 +524,38 @@ static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_i
     const int sub = sl.n_frames;
     Detector& det = *p->det;
     const size_t bytes = (size_t)det.H * det.W * 3;
-    if (frame_is_host) {
-        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, cudaMemcpyHostToDevice, p->sA));
-    } else {
+    if (fh <= 0 || fw <= 0) { fh = det.H; fw = det.W; }
+    const bool plain = fh == det.H && fw == det.W && !is_bgr;            // already what the network eats
+    sl.fh[sub] = fh; sl.fw[sub] = fw; sl.resized[sub] = !plain;
+    if (!frame_is_host) {
         // the caller's frame was produced on the caller's stream and must stay readable until this frame is collected: keep a copy
         YDST_CUDA(cudaEventRecord(p->ev_in, caller));
         YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
-        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, cudaMemcpyDeviceToDevice, p->sA));
+    }
+    const cudaMemcpyKind kind = frame_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (plain) {
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, p->sA));
+    } else {
+        // ingest on the device: (BGR ->) RGB copy of the captured frame for the ReID crops, cv2-exact resize to the network size
+        const size_t fbytes = (size_t)fh * fw * 3;
+        if (fbytes > sl.orig_cap) {
+            YDST_CHECK(sub == 0, "frames of one micro-batch must not grow in size");
+            YDST_CUDA(cudaStreamSynchronize(p->sA));
+            cudaFree(sl.orig_dev); cudaFree(sl.raw_dev);
+            sl.orig_cap = fbytes;
+            YDST_CUDA(cudaMalloc(&sl.orig_dev, sl.orig_cap * p->B));
+            YDST_CUDA(cudaMalloc(&sl.raw_dev, sl.orig_cap));
+        }
+        uint8_t* orig = sl.orig_dev + (size_t)sub * sl.orig_cap;
+        if (is_bgr) {
+            YDST_CUDA(cudaMemcpyAsync(sl.raw_dev, frame, fbytes, kind, p->sA));
+            launch_resize_u8(sl.raw_dev, fh, fw, orig, fh, fw, 1, p->sA);        // same size: a channel-swapping copy
+            count_launch();
+        } else {
+            YDST_CUDA(cudaMemcpyAsync(orig, frame, fbytes, kind, p->sA));
+        }
+        launch_resize_u8(orig, fh, fw, sl.frame_dev + sub * bytes, det.H, det.W, 0, p->sA);
+        count_launch();
     }
     sl.want_dets = sl.want_dets || want_dets;
     sl.n_frames = sub + 1;
@@ -539,16 +572,19 @@ static void pipeline_launch_reid(ydst_pipeline* p, ydst_pipeline::Slot& sl, bool
     Detector& det = *p->det;
     const int md = det.nms_.max_det;
     const size_t bytes = (size_t)det.H * det.W * 3;
-    const uint8_t* frames[8]; const float* boxes[8]; int ms[8];
+    const uint8_t* frames[8]; const float* boxes[8]; int ms[8], hs[8], ws[8];
     int off = 0;
     for (int b = 0; b < sl.n_frames; ++b) {
         YDST_CHECK(sl.h_counts[b * 8 + 2] == 0, "NMS candidate capacity exceeded (%d candidates)", sl.h_counts[b * 8]);
-        frames[b] = sl.frame_dev + b * bytes; boxes[b] = sl.tlwh + (size_t)b * md * 4;
+        // crops come from the frame as captured (deep_sort/deep_sort.py:133-141 slices ori_img), boxes are already in its pixels
+        frames[b] = sl.resized[b] ? sl.orig_dev + (size_t)b * sl.orig_cap : sl.frame_dev + b * bytes;
+        hs[b] = sl.fh[b]; ws[b] = sl.fw[b];
+        boxes[b] = sl.tlwh + (size_t)b * md * 4;
         ms[b] = sl.h_counts[b * 8 + 1] > 0 ? sl.h_counts[b * 8 + 3] : 0;
         sl.feat_off[b] = off; off += ms[b];
     }
     YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sC));
-    p->reid->extract_multi(frames, det.H, det.W, boxes, ms, sl.n_frames, sl.feat, p->sC);
+    p->reid->extract_multi(frames, hs, ws, boxes, ms, sl.n_frames, sl.feat, p->sC);
     YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sC));
     YDST_CUDA(cudaEventRecord(sl.ev_feat, p->sC));
     sl.reid_launched = true;
@@ -579,7 +615,16 @@ static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, fl
     if (nxt.busy) pipeline_launch_reid(p, nxt, false);
     const int n_dets = sl.h_counts[sub * 8 + 1], m = sl.h_counts[sub * 8 + 3];
     if (n_dets_host) *n_dets_host = n_dets;
-    if (dets_host && sl.want_dets) memcpy(dets_host, sl.h_dets + (size_t)sub * md * 6, sizeof(float) * 6 * n_dets);
+    if (dets_host && sl.want_dets) {
+        memcpy(dets_host, sl.h_dets + (size_t)sub * md * 6, sizeof(float) * 6 * n_dets);
+        if (sl.resized[sub]) {                                       // resize_boxes (yolo3/utils/model_build.py:12-19), same fp32 products
+            const float rw = (float)((double)sl.fw[sub] / (double)det.W), rh = (float)((double)sl.fh[sub] / (double)det.H);
+            for (int i = 0; i < n_dets; ++i) {
+                float* d = dets_host + (size_t)i * 6;
+                d[0] *= rw; d[1] *= rh; d[2] *= rw; d[3] *= rh;
+            }
+        }
+    }
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
     const float* h_cls = sl.h_cls + (size_t)sub * md;
     for (int i = 0; i < m; ++i) p->h_payload[i] = (int)h_cls[i];
@@ -597,6 +642,21 @@ int ydst_pipeline_submit(ydst_pipeline* p, const uint8_t* frame, int frame_is_ho
     YDST_API_BEGIN
     YDST_CHECK(p && frame, "null argument");
     pipeline_submit(p, frame, frame_is_host != 0, want_dets != 0, S(stream));
+    YDST_API_END
+}
+int ydst_pipeline_submit_frame(ydst_pipeline* p, const uint8_t* frame, int height, int width, int frame_is_host, int is_bgr, int want_dets,
+                               void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && frame && height > 0 && width > 0, "bad argument");
+    pipeline_submit(p, frame, frame_is_host != 0, want_dets != 0, S(stream), height, width, is_bgr != 0);
+    YDST_API_END
+}
+int ydst_resize_u8(const uint8_t* src_dev, int src_h, int src_w, uint8_t* dst_dev, int dst_h, int dst_w, int swap_rb, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(src_dev && dst_dev, "null argument");
+    launch_resize_u8(src_dev, src_h, src_w, dst_dev, dst_h, dst_w, swap_rb, S(stream));
+    count_launch();
+    YDST_CUDA(cudaStreamSynchronize(S(stream)));
     YDST_API_END
 }
 int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {

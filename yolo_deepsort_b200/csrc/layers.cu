@@ -370,6 +370,41 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c] = ((float)v[c] / 255.f - mean[c]) / stdv[c];
 }
+// Whole-frame ingest (next to the hot path): the reader thread's BGR->RGB (yolo3/detect/video_detect.py:33-36) and
+// ImageDetector's cv2.resize(img, (W, H), INTER_LINEAR) (yolo3/detect/img_detect.py:70) on the device, with the same
+// fixed-point arithmetic as the crop kernel above (bit-exact against cv2 on every size tried, tests/test_gpu_ingest.py).
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh,
+                                                        int dw, int swap_rb) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)dh * dw) return;
+    const int dx = (int)(idx % dw), dy = (int)(idx / dw);
+    int v[3];
+    if (sh == dh && sw == dw) {
+        const uint8_t* s = src + idx * 3;
+        v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+    } else {
+        int xa, xb, a0, a1, ya, yb, b0, b1;
+        axis_coeff(dx, dw, sw, true, xa, xb, a0, a1);
+        axis_coeff(dy, dh, sh, false, ya, yb, b0, b1);
+        const uint8_t* r0 = src + (long long)ya * sw * 3;
+        const uint8_t* r1 = src + (long long)yb * sw * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = (int)r0[xa * 3 + c] * a0 + (int)r0[xb * 3 + c] * a1;
+            const int h1 = (int)r1[xa * 3 + c] * a0 + (int)r1[xb * 3 + c] * a1;
+            const int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v[c] = min(max(r, 0), 255);
+        }
+    }
+    uint8_t* o = dst + idx * 3;
+    o[0] = (uint8_t)(swap_rb ? v[2] : v[0]); o[1] = (uint8_t)v[1]; o[2] = (uint8_t)(swap_rb ? v[0] : v[2]);
+}
+void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st) {
+    YDST_CHECK(sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad resize geometry");
+    resize_u8_kernel<<<cdiv((long long)dh * dw, 256), 256, 0, st>>>(src, sh, sw, dst, dh, dw, swap_rb);
+    YDST_CUDA(cudaGetLastError());
+}
+
 void launch_crop_resize(const uint8_t* frame, int H, int W, const float* tlwh, int m, float* out, int* err_flag, cudaStream_t st) {
     if (m == 0) return;
     crop_resize_kernel<<<cdiv((long long)m * 128 * 64, 256), 256, 0, st>>>(frame, H, W, tlwh, m, out, err_flag);

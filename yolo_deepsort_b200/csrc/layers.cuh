@@ -40,6 +40,8 @@ void launch_avgpool_l2(const Act& in, float* out, cudaStream_t st);
 // Crop + cv2-exact fixed-point bilinear resize to 128x64 + /255 + ImageNet mean/std (deep_sort/deep_sort.py:116-141,
 // deep_sort/deep/feature_extractor.py:34-51).  frame: u8 HWC RGB; boxes: tlwh fp32 [m][4]; out fp32 NHWC [m][128][64][3].
 // err_flag (device int) is set to 1 if a box yields an empty crop (the reference raises there).
+// cv2.resize(u8 HWC, INTER_LINEAR) of a whole frame, optionally swapping R and B (BGR capture -> RGB); same size = (swapping) copy
+void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st);
 void launch_crop_resize(const uint8_t* frame, int H, int W, const float* tlwh, int m, float* out, int* err_flag, cudaStream_t st);
 
 }  // namespace ydst

@@ -518,7 +518,7 @@ void Reid::forward(const float* x_dev, int m, float* feat_out, cudaStream_t st) 
         YDST_CUDA(cudaMemcpyAsync(feat_out, feat_, (size_t)m * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
 
-void Reid::extract_multi(const uint8_t* const* frames_dev, int H, int W, const float* const* tlwh_dev, const int* m, int nb,
+void Reid::extract_multi(const uint8_t* const* frames_dev, const int* H, const int* W, const float* const* tlwh_dev, const int* m, int nb,
                          float* feat_out, cudaStream_t st) {
     int total = 0;
     for (int b = 0; b < nb; ++b) total += m[b];
@@ -527,7 +527,7 @@ void Reid::extract_multi(const uint8_t* const* frames_dev, int H, int W, const f
     int off = 0;
     for (int b = 0; b < nb; ++b) {
         if (m[b] == 0) continue;
-        launch_crop_resize(frames_dev[b], H, W, tlwh_dev[b], m[b], in_f32_ + (size_t)off * 128 * 64 * 3, err_flag, st);
+        launch_crop_resize(frames_dev[b], H[b], W[b], tlwh_dev[b], m[b], in_f32_ + (size_t)off * 128 * 64 * 3, err_flag, st);
         count_launch();
         off += m[b];
     }

@@ -94,8 +94,8 @@ public:
     void extract(const uint8_t* frame_dev, int H, int W, const float* tlwh_dev, int m, float* feat_out, cudaStream_t st);
     void forward(const float* x_dev, int m, float* feat_out, cudaStream_t st);
     // crops of several frames through ONE forward: frame b contributes m[b] boxes (tlwh[b]); features are written frame after frame
-    void extract_multi(const uint8_t* const* frames_dev, int H, int W, const float* const* tlwh_dev, const int* m, int nb, float* feat_out,
-                       cudaStream_t st);
+    void extract_multi(const uint8_t* const* frames_dev, const int* H, const int* W, const float* const* tlwh_dev, const int* m, int nb,
+                       float* feat_out, cudaStream_t st);
     int max_batch;
     int* err_flag = nullptr;     // device
 private:

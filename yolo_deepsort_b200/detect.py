@@ -71,9 +71,9 @@ class VideoDetector:
     def _track(self, frame):
         """One detection step; returns `hold_detections` exactly as the reference loop would set it
         (yolo3/detect/video_detect.py:134-157)."""
-        H, W = self.image_detector.model.img_size
-        if self._pipeline is not None and frame.shape[:2] == (H, W):
-            tracks, dets = self._pipeline.step(frame, want_dets=False)
+        if self._pipeline is not None:
+            self._pipeline.submit(frame, want_dets=False)        # any frame size: the resize runs on the device
+            tracks, dets = self._pipeline.collect(want_dets=False)
             return tracks
         detections = self.image_detector.detect(frame)
         if detections is not None and self.tracker is not None:
@@ -137,7 +137,7 @@ class VideoDetector:
         try:
             while nxt is not None:
                 frame, nxt = nxt, read_rgb()
-                if lookahead and frame.shape[:2] == (H, W) and (nxt is None or nxt.shape[:2] == (H, W)):
+                if lookahead:
                     if not submitted:
                         self._pipeline.submit(frame, want_dets=False)
                     submitted = nxt is not None

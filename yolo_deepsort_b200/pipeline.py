@@ -36,14 +36,23 @@ class FramePipeline:
             pass
 
     # ---- software-pipelined form: the detector half of frame t+1 runs under the ReID + association half of frame t ----
-    def submit(self, frame, want_dets=True):
-        """Enqueue the detector half of `frame` and return at once (at most two frames may be in flight)."""
+    def submit(self, frame, want_dets=True, bgr=False):
+        """Enqueue the detector half of `frame` and return at once (up to 3 micro-batches may be in flight).  `frame` is
+        (h,w,3) uint8, RGB (or BGR with bgr=True), of ANY size: colour swap and the cv2-exact resize to the network size run
+        on the device, detections come back in the frame's own pixels and the ReID crops are cut from the frame itself."""
         with torch.cuda.device(self.device):
             if isinstance(frame, torch.Tensor) and frame.is_cuda:
-                check(lib().ydst_pipeline_submit(self._h, ptr(frame), 0, int(want_dets), stream_ptr()))
+                assert frame.dtype == torch.uint8 and frame.dim() == 3 and frame.shape[2] == 3 and frame.is_contiguous()
+                check(lib().ydst_pipeline_submit_frame(self._h, ptr(frame), int(frame.shape[0]), int(frame.shape[1]), 0, int(bgr),
+                                                       int(want_dets), stream_ptr()))
             else:
                 f = frame.numpy() if isinstance(frame, torch.Tensor) else np.ascontiguousarray(frame)
-                assert f.dtype == np.uint8 and f.shape == (self.model.img_size[0], self.model.img_size[1], 3)
+                assert f.dtype == np.uint8 and f.ndim == 3 and f.shape[2] == 3
+                if f.shape[:2] != tuple(self.model.img_size) or bgr:
+                    self._keep = (getattr(self, '_keep', ()) + (f,))[-4 * self.micro_batch - 2:]
+                    check(lib().ydst_pipeline_submit_frame(self._h, f.ctypes.data, int(f.shape[0]), int(f.shape[1]), 1, int(bgr),
+                                                           int(want_dets), stream_ptr()))
+                    return
                 self._keep = (getattr(self, '_keep', ()) + (f,))[-4 * self.micro_batch - 2:]   # async H2D copies read them until collected
                 check(lib().ydst_pipeline_submit(self._h, f.ctypes.data, 1, int(want_dets), stream_ptr()))
 
