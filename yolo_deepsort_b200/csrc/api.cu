@@ -497,17 +497,20 @@ static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) 
     Detector& det = *p->det;
     const int md = det.nms_.max_det;
     det.forward_u8(sl.frame_dev, nullptr, p->sA);
+    // one set of NMS launches for the whole micro-batch (image = blockIdx.y), then one D2H per result array
+    det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, p->sA, sl.n_frames);
+    NmsRatios ratios{};
     for (int b = 0; b < sl.n_frames; ++b) {
-        det.nms_.run(det.pred + (size_t)b * det.rows * det.fields, det.rows, det.fields, p->conf, p->iou, p->sA);
-            // resize_boxes: x *= w / W, y *= h / H with python-float ratios applied to fp32 boxes (yolo3/utils/model_build.py:12-19)
-        const float rw = (float)((double)sl.fw[b] / (double)det.W), rh = (float)((double)sl.fh[b] / (double)det.H);
-        det.nms_.to_tracker_inputs(rw, rh, p->mask_dev, p->n_mask, sl.tlwh + (size_t)b * md * 4, sl.confd + (size_t)b * md, sl.cls + (size_t)b * md, p->sA);
-        YDST_CUDA(cudaMemcpyAsync(sl.h_counts + b * 8, det.nms_.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, p->sA));
-        if (sl.want_dets)
-            YDST_CUDA(cudaMemcpyAsync(sl.h_dets + (size_t)b * md * 6, det.nms_.dets, sizeof(float) * 6 * md, cudaMemcpyDeviceToHost, p->sA));
-        // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
-        YDST_CUDA(cudaMemcpyAsync(sl.h_cls + (size_t)b * md, sl.cls + (size_t)b * md, sizeof(float) * md, cudaMemcpyDeviceToHost, p->sA));
+        // resize_boxes: x *= w / W, y *= h / H with python-float ratios applied to fp32 boxes (yolo3/utils/model_build.py:12-19)
+        ratios.rw[b] = (float)((double)sl.fw[b] / (double)det.W);
+        ratios.rh[b] = (float)((double)sl.fh[b] / (double)det.H);
     }
+    det.nms_.to_tracker_inputs_batch(ratios, sl.n_frames, p->mask_dev, p->n_mask, sl.tlwh, sl.confd, sl.cls, p->sA);
+    YDST_CUDA(cudaMemcpyAsync(sl.h_counts, det.nms_.counters, sizeof(int) * 8 * sl.n_frames, cudaMemcpyDeviceToHost, p->sA));
+    if (sl.want_dets)
+        YDST_CUDA(cudaMemcpyAsync(sl.h_dets, det.nms_.dets, sizeof(float) * 6 * md * sl.n_frames, cudaMemcpyDeviceToHost, p->sA));
+    // class ids of the tracker inputs ride along with the counters (saves the tracker a kernel + a synchronisation)
+    YDST_CUDA(cudaMemcpyAsync(sl.h_cls, sl.cls, sizeof(float) * md * sl.n_frames, cudaMemcpyDeviceToHost, p->sA));
     YDST_CUDA(cudaEventRecord(sl.ev_det, p->sA));
     sl.launched = true;
     ++p->fill;                                                         // the next frame starts a new slot

@@ -11,6 +11,7 @@
 // reader is the following shortcut adds the residual in its epilogue; head convs write fp32 for the decode.
 #include "net.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -183,7 +184,7 @@ Detector::Detector(const ydst_layer_desc* layers, int n, const float* weights, s
     : H(H_), W(W_), batch(batch_) {
     YDST_CHECK(batch >= 1 && H > 0 && W > 0, "bad detector geometry");
     build(layers, n, weights, n_weights);
-    nms_.init(4096, 300);
+    nms_.init(4096, 300, std::min(batch, 8));
 }
 
 void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size_t n_weights) {

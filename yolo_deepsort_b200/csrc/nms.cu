@@ -13,7 +13,9 @@ __global__ void nms_collect_kernel(const float* __restrict__ pred, int rows, int
                                    int cap, int* __restrict__ count) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
-    const float* p = pred + (long long)row * nf;
+    const int img = blockIdx.y;
+    cand += (long long)img * cap; count += img * 8;
+    const float* p = pred + ((long long)img * rows + row) * nf;
     const float obj = p[4];
     if (!(obj > conf)) return;
     const float cx = p[0], cy = p[1], w = p[2], h = p[3];
@@ -36,6 +38,8 @@ __global__ void nms_collect_kernel(const float* __restrict__ pred, int rows, int
 
 // ---- 2. stable descending order by counting: rank(i) = #{j : s_j > s_i or (s_j == s_i and key_j < key_i)} ----
 __global__ void nms_rank_kernel(const NmsCand* __restrict__ cand, const int* __restrict__ count, int cap, NmsCand* __restrict__ sorted) {
+    const int img = blockIdx.y;
+    cand += (long long)img * cap; sorted += (long long)img * cap; count += img * 8;
     const int n = min(*count, cap);
     __shared__ float ss[256];
     __shared__ int sk[256];
@@ -60,6 +64,8 @@ __global__ void nms_rank_kernel(const NmsCand* __restrict__ cand, const int* __r
 // ---- 3. suppression bitmask on class-offset boxes (boxes + cls*4096 in fp32, as the reference does) ----
 __global__ void nms_mask_kernel(const NmsCand* __restrict__ sorted, const int* __restrict__ count, int cap, float iou_thr,
                                 unsigned long long* __restrict__ mask, int words) {
+    const int img = blockIdx.y;
+    sorted += (long long)img * cap; count += img * 8; mask += (long long)img * cap * words;
     const int n = min(*count, cap);
     const int i = blockIdx.x;                 // row
     if (i >= n) return;
@@ -97,6 +103,9 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
                                                         float* __restrict__ dets, int* __restrict__ n_out, int* __restrict__ overflow) {
     extern __shared__ unsigned long long smask[];
     __shared__ int s_kept[1024];               // max_det <= 1024 (Nms::init)
+    const int img = blockIdx.x;
+    sorted += (long long)img * cap; count += img * 8; mask += (long long)img * cap * words;
+    dets += (long long)img * max_det * 6; n_out += img * 8; overflow += img * 8;
     const int total = *count;
     const int n = min(total, cap);
     const int nw = (n + 63) >> 6;
@@ -138,11 +147,15 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
 }
 
 // ---- 5. hand-off: resize_boxes, xyxy -> tlwh, class mask; order preserved (one block, ballot scan) ----
-__global__ void __launch_bounds__(1024) dets_to_tracks_kernel(const float* __restrict__ dets, const int* __restrict__ n_dets, float rw,
-                                                              float rh, const int* __restrict__ class_mask, int n_mask,
+__global__ void __launch_bounds__(1024) dets_to_tracks_kernel(const float* __restrict__ dets, const int* __restrict__ n_dets, NmsRatios ratios,
+                                                              int max_det, const int* __restrict__ class_mask, int n_mask,
                                                               float* __restrict__ tlwh, float* __restrict__ conf,
                                                               float* __restrict__ cls, int* __restrict__ m_out) {
     __shared__ int warp_cnt[32];
+    const int img = blockIdx.x;
+    const float rw = ratios.rw[img], rh = ratios.rh[img];
+    dets += (long long)img * max_det * 6; n_dets += img * 8; m_out += img * 8;
+    tlwh += (long long)img * max_det * 4; conf += (long long)img * max_det; cls += (long long)img * max_det;
     const int n = *n_dets;
     const int i = threadIdx.x, lane = i & 31, wid = i >> 5;
     bool keep = false;
@@ -166,41 +179,49 @@ __global__ void __launch_bounds__(1024) dets_to_tracks_kernel(const float* __res
     if (i == 0) *m_out = total;
 }
 
-void Nms::init(int cap_, int max_det_) {
-    cap = cap_; max_det = max_det_;
+void Nms::init(int cap_, int max_det_, int batch_) {
+    cap = cap_; max_det = max_det_; batch = batch_;
+    YDST_CHECK(batch >= 1 && batch <= 8, "nms batch 1..8");
     YDST_CHECK(cap % 64 == 0 && cap <= 8192, "nms candidate capacity must be a multiple of 64, <= 8192");
     YDST_CHECK(max_det <= 1024, "max_det <= 1024");
     words = cap / 64;
-    YDST_CUDA(cudaMalloc(&cand, sizeof(NmsCand) * cap));
-    YDST_CUDA(cudaMalloc(&sorted, sizeof(NmsCand) * cap));
-    YDST_CUDA(cudaMalloc(&mask, sizeof(unsigned long long) * (size_t)cap * words));
-    YDST_CUDA(cudaMalloc(&counters, sizeof(int) * 8));
-    YDST_CUDA(cudaMalloc(&dets, sizeof(float) * 6 * max_det));
+    YDST_CUDA(cudaMalloc(&cand, sizeof(NmsCand) * cap * batch));
+    YDST_CUDA(cudaMalloc(&sorted, sizeof(NmsCand) * cap * batch));
+    YDST_CUDA(cudaMalloc(&mask, sizeof(unsigned long long) * (size_t)cap * words * batch));
+    YDST_CUDA(cudaMalloc(&counters, sizeof(int) * 8 * batch));
+    YDST_CUDA(cudaMalloc(&dets, sizeof(float) * 6 * max_det * batch));
 }
 void Nms::destroy() {
     cudaFree(cand); cudaFree(sorted); cudaFree(mask); cudaFree(counters); cudaFree(dets);
     cand = sorted = nullptr; mask = nullptr; counters = nullptr; dets = nullptr;
 }
-// counters: [0] candidate count, [1] n_out, [2] overflow flag, [3] m (tracker inputs)
-void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaStream_t st) {
-    YDST_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 4, st));
-    nms_collect_kernel<<<(rows + 255) / 256, 256, 0, st>>>(pred, rows, nf, conf, cand, cap, counters);
-    nms_rank_kernel<<<cap / 256 > 0 ? cap / 256 : 1, 256, 0, st>>>(cand, counters, cap, sorted);
-    nms_mask_kernel<<<cap, 64, 0, st>>>(sorted, counters, cap, iou, mask, words);
+// counters (per image, stride 8): [0] candidate count, [1] n_out, [2] overflow flag, [3] m (tracker inputs)
+void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaStream_t st, int nb) {
+    YDST_CHECK(nb >= 1 && nb <= batch, "nms over %d images, capacity %d", nb, batch);
+    YDST_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 8 * nb, st));
+    nms_collect_kernel<<<dim3((rows + 255) / 256, nb), 256, 0, st>>>(pred, rows, nf, conf, cand, cap, counters);
+    nms_rank_kernel<<<dim3(cap / 256 > 0 ? cap / 256 : 1, nb), 256, 0, st>>>(cand, counters, cap, sorted);
+    nms_mask_kernel<<<dim3(cap, nb), 64, 0, st>>>(sorted, counters, cap, iou, mask, words);
     static bool attr_set = false;
     const int sweep_smem = kSweepSmemRows * (kSweepSmemRows / 64) * (int)sizeof(unsigned long long);
     if (!attr_set) {
         YDST_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
         attr_set = true;
     }
-    nms_sweep_kernel<<<1, 256, sweep_smem, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
+    nms_sweep_kernel<<<nb, 256, sweep_smem, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
     YDST_CUDA(cudaGetLastError());
     count_launch(4);
 }
-void Nms::to_tracker_inputs(float rw, float rh, const int* class_mask_dev, int n_mask, float* tlwh, float* conf, float* cls, cudaStream_t st) {
-    dets_to_tracks_kernel<<<1, 1024, 0, st>>>(dets, counters + 1, rw, rh, class_mask_dev, n_mask, tlwh, conf, cls, counters + 3);
+void Nms::to_tracker_inputs_batch(const NmsRatios& r, int nb, const int* class_mask_dev, int n_mask, float* tlwh, float* conf, float* cls,
+                                  cudaStream_t st) {
+    dets_to_tracks_kernel<<<nb, 1024, 0, st>>>(dets, counters + 1, r, max_det, class_mask_dev, n_mask, tlwh, conf, cls, counters + 3);
     YDST_CUDA(cudaGetLastError());
     count_launch();
+}
+void Nms::to_tracker_inputs(float rw, float rh, const int* class_mask_dev, int n_mask, float* tlwh, float* conf, float* cls, cudaStream_t st) {
+    NmsRatios r{};
+    r.rw[0] = rw; r.rh[0] = rh;
+    to_tracker_inputs_batch(r, 1, class_mask_dev, n_mask, tlwh, conf, cls, st);
 }
 
 }  // namespace ydst
