@@ -251,19 +251,18 @@ void launch_unpack_f32(const float* padded, int cstride, int N, int H, int W, in
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void yolo_decode_kernel(const float* __restrict__ head, int cstride, int N, int gy, int gx, int na, float aw0, float ah0,
-                                   float aw1, float ah1, float aw2, float ah2, int nc, float s0, float s1, float* __restrict__ pred,
-                                   int rows_total, int row0) {
+// grid: x over (gx * nf) elements of one grid row, y = (n * na + a) * gy + y  -> one integer division per thread
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ head, int cstride, int N, int gy, int gx, int na, float aw0,
+                                                          float ah0, float aw1, float ah1, float aw2, float ah2, int nc, float s0, float s1,
+                                                          float* __restrict__ pred, int rows_total, int row0) {
     const int nf = nc + 5;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)N * na * gy * gx * nf;
-    if (idx >= total) return;
-    const int k = (int)(idx % nf);
-    long long t = idx / nf;
-    const int x = (int)(t % gx); t /= gx;
-    const int y = (int)(t % gy); t /= gy;
-    const int a = (int)(t % na);
-    const int n = (int)(t / na);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= gx * nf) return;
+    const int x = e / nf, k = e - x * nf;
+    int t = blockIdx.y;
+    const int y = t % gy; t /= gy;                         // block-uniform
+    const int a = t % na;
+    const int n = t / na;
     const long long pix = ((long long)n * (gy + 2) + y + 1) * (gx + 2) + x + 1;
     const float v = __ldg(head + pix * cstride + a * nf + k);
     const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2), ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
@@ -281,10 +280,10 @@ __global__ void yolo_decode_kernel(const float* __restrict__ head, int cstride, 
 void launch_yolo_decode(const float* head, int cstride, int N, int gy, int gx, int na, const float* anchors_wh, int nc, int img_h,
                         int img_w, float* pred, int rows_total, int row0, cudaStream_t st) {
     YDST_CHECK(na == 3, "yolo layer with %d anchors (3 supported)", na);
-    const long long total = (long long)N * na * gy * gx * (nc + 5);
     const float s0 = (float)((double)img_h / gy), s1 = (float)((double)img_w / gx);
-    yolo_decode_kernel<<<cdiv(total, 256), 256, 0, st>>>(head, cstride, N, gy, gx, na, anchors_wh[0], anchors_wh[1], anchors_wh[2],
-                                                        anchors_wh[3], anchors_wh[4], anchors_wh[5], nc, s0, s1, pred, rows_total, row0);
+    const dim3 grid(cdiv((long long)gx * (nc + 5), 256), (unsigned)(N * na * gy));
+    yolo_decode_kernel<<<grid, 256, 0, st>>>(head, cstride, N, gy, gx, na, anchors_wh[0], anchors_wh[1], anchors_wh[2], anchors_wh[3],
+                                             anchors_wh[4], anchors_wh[5], nc, s0, s1, pred, rows_total, row0);
     YDST_CUDA(cudaGetLastError());
 }
 
