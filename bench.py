@@ -315,7 +315,7 @@ def run_ours(args):
     conv_flops = float(flops[conv].sum()) / nprof
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM, fp16 in / fp32 accumulate)", "bound": "tensor",
+    roof = {"kernel": "conv_tc2_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convolutions, fp16 in / fp32 accumulate)", "bound": "tensor",
             "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); kernel timed inside a long step",
             "traffic": ncu_traffic(),
