@@ -184,7 +184,7 @@ int ydst_conv2d(const void* x_dev, int N, int H, int W, int cin, const float* w_
     if (cin == 3) {
         YDST_CHECK(!y_is_f32 && !res_dev, "first-layer path: fp16 output, no residual");
         Act out = make_act(arena, N, Ho, Wo, cout);
-        launch_conv_first((const float*)x_dev, N, H, W, cw->w32, cw->scale, cw->bias, cout, stride, act, out, st);
+        launch_conv_first((const float*)x_dev, N, H, W, cw->w32, cw->w_hilo, cw->scale, cw->bias, cout, stride, act, out, st);
         launch_unpack(out, (__half*)y_dev, st);
     } else {
         Act in = make_act(arena, N, H, W, cin);

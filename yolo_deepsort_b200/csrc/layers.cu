@@ -3,6 +3,8 @@
 // moves 16 bytes (8 channels) per thread per access and writes interior pixels only.
 #include "layers.cuh"
 
+#include <cstdlib>
+
 namespace ydst {
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -108,10 +110,119 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
         }
     }
 }
-void launch_conv_first(const float* in, int N, int H, int W, const float* w, const float* scale, const float* bias, int cout,
-                       int stride, int act, const Act& out, cudaStream_t st) {
+// Tensor-core first layer (stride 1).  K = 3*3*3 = 27 is padded to 32 and the im2col tile of 128 consecutive output pixels is
+// built in shared memory by the CTA's 128 threads (one row each, 64-byte rows in the SWIZZLE_64B layout the UMMA descriptor
+// names).  Inputs and weights are fp32 in the reference and this layer sets the scale of everything behind it, so both are
+// split into hi + lo fp16 parts and three products (hi*hi + lo*hi + hi*lo) accumulate in fp32 TMEM: ~22 significant bits.
+__global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restrict__ in, int N, int H, int W, const __half* __restrict__ w_hilo,
+                                                            const float* __restrict__ scale, const float* __restrict__ bias, int cout, int act,
+                                                            Act out) {
+    __shared__ __align__(1024) uint8_t sm[2 * 8192 + 2 * 4096];
+    __shared__ __align__(8) unsigned long long bar_storage;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const uint32_t sA_hi = smem_u32(sm), sA_lo = sA_hi + 8192u, sB_hi = sA_lo + 8192u, sB_lo = sB_hi + 4096u;
+    const uint32_t bar = smem_u32(&bar_storage);
+    const uint32_t tmem_cols = cout <= 32 ? 32u : 64u;
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), tmem_cols); tmem_relinquish(); }
+    // ---- this thread's im2col row ----
+    const long long total = (long long)N * H * W;
+    const long long idx = (long long)blockIdx.x * 128 + t;
+    const bool live = idx < total;
+    int xo = 0, yo = 0, n = 0;
+    if (live) { xo = (int)(idx % W); const long long q = idx / W; yo = (int)(q % H); n = (int)(q / H); }
+    float v[32];
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int y = yo - 1 + r, x = xo - 1 + s;
+            const bool ok = live && y >= 0 && y < H && x >= 0 && x < W;
+            const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+        }
+    const uint32_t sw = (uint32_t)((t >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 hi4, lo4;
+        __half2* hh = reinterpret_cast<__half2*>(&hi4);
+        __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = v[c * 8 + 2 * q], b = v[c * 8 + 2 * q + 1];
+            const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+            hh[q] = __halves2half2(ah, bh);
+            ll[q] = __halves2half2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
+        }
+        const uint32_t off = (uint32_t)t * 64u + ((((uint32_t)c) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(sm + off) = hi4;
+        *reinterpret_cast<uint4*>(sm + 8192 + off) = lo4;
+    }
+    // ---- weights: [2][cout][32] fp16 -> two swizzled [cout][64 B] tiles ----
+    for (int e = t; e < 2 * cout * 4; e += 128) {
+        const int part = e / (cout * 4), rem = e - part * cout * 4;
+        const int row = rem >> 2, c = rem & 3;
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(w_hilo + ((size_t)part * cout + row) * 32 + c * 8));
+        *reinterpret_cast<uint4*>(sm + 16384 + part * 4096 + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = w4;
+    }
+    fence_proxy_async();                                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = make_idesc_f16(128, cout);
+        const uint32_t a_of[3] = {sA_hi, sA_lo, sA_hi}, b_of[3] = {sB_hi, sB_hi, sB_lo};
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                umma_f16(tmem_base, make_smem_desc(a_of[pr] + 32u * k, 64), make_smem_desc(b_of[pr] + 32u * k, 64), idesc, (uint32_t)((pr | k) != 0));
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tcgen05_fence_after();
+    const long long pix = ((long long)n * out.Hp() + yo + 1) * out.Wp() + xo + 1;
+    __half* op = out.base + pix * out.ctot + out.coff;
+    for (int ch = 0; ch < (cout >> 4); ++ch) {
+        __syncwarp();
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), acc);
+        tcgen05_wait_ld();
+        if (!live) continue;
+        uint4 w0, w1;
+        __half2* g0 = reinterpret_cast<__half2*>(&w0);
+        __half2* g1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int c0 = ch * 16 + 2 * q;
+            const float a = apply_act(fmaf(__uint_as_float(acc[2 * q]), __ldg(scale + c0), __ldg(bias + c0)), act);
+            const float b = apply_act(fmaf(__uint_as_float(acc[2 * q + 1]), __ldg(scale + c0 + 1), __ldg(bias + c0 + 1)), act);
+            (q < 4 ? g0[q] : g1[q - 4]) = __floats2half2_rn(a, b);
+        }
+        reinterpret_cast<uint4*>(op + ch * 16)[0] = w0;
+        reinterpret_cast<uint4*>(op + ch * 16)[1] = w1;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+void launch_conv_first(const float* in, int N, int H, int W, const float* w, const __half* w_hilo, const float* scale, const float* bias,
+                       int cout, int stride, int act, const Act& out, cudaStream_t st) {
     YDST_CHECK(cout % 8 == 0 && cout <= 64, "first-layer conv supports cout in {8..64}, multiple of 8 (got %d)", cout);
     YDST_CHECK(stride == 1 || stride == 2, "first-layer conv supports stride 1 and 2");
+    static const bool tc_ok = !(getenv("YDST_STEM_TC") && atoi(getenv("YDST_STEM_TC")) == 0);
+    if (tc_ok && w_hilo && stride == 1 && cout % 16 == 0 && act != ACT_MISH) {
+        const long long tot = (long long)N * H * W;
+        conv_first_tc_kernel<<<cdiv(tot, 128), 128, 0, st>>>(in, N, H, W, w_hilo, scale, bias, cout, act, out);
+        YDST_CUDA(cudaGetLastError());
+        return;
+    }
     const long long total = (long long)N * out.H * ((out.W + 1) / 2);
     const int smem = (27 * cout + 2 * cout) * (int)sizeof(float);
     if (stride == 1) conv_first_kernel<1><<<cdiv(total, 128), 128, smem, st>>>(in, N, H, W, w, scale, bias, cout, act, out);

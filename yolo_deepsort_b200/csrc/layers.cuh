@@ -11,7 +11,9 @@ void launch_nchw_to_nhwc(const void* src, int src_is_half, float* dst, int N, in
 
 // First-layer direct convolution: fp32 NHWC input with 3 channels (unpadded), 3x3 pad 1, stride 1|2,
 // fused scale/bias/activation, fp16 padded-NHWC output.  w is fp32 [27][cout] (tap-major, then cin).
-void launch_conv_first(const float* in, int N, int H, int W, const float* w, const float* scale, const float* bias,
+// w_hilo (optional): [2][cout][32] fp16 hi/lo split of the same weights; with it, stride 1 and cout in {16,32,48,64} the layer runs
+// on the tensor cores (three tcgen05 products hi*hi + lo*hi + hi*lo of a [128 x 32] im2col tile built in shared memory).
+void launch_conv_first(const float* in, int N, int H, int W, const float* w, const __half* w_hilo, const float* scale, const float* bias,
                        int cout, int stride, int act, const Act& out, cudaStream_t st);
 
 // MaxPool2d(k, s, padding=(k-1)//2) with -inf padding; zero_pad_br=1 reproduces the reference's

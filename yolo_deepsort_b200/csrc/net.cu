@@ -77,6 +77,17 @@ std::unique_ptr<ConvWeights> pack_conv(DeviceArena& arena, const float* w, int c
                     for (int s = 0; s < 3; ++s) p[(size_t)((r * 3 + s) * 3 + c) * cout + o] = w[((o * 3 + c) * 3 + r) * 3 + s];
         cw->w32 = (float*)arena.alloc(p.size() * sizeof(float));
         YDST_CUDA(cudaMemcpy(cw->w32, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // tensor-core variant: the fp32 weight as a sum of two fp16 numbers (the products then carry ~22 significant bits)
+        std::vector<__half> hl((size_t)2 * cout * 32, __float2half(0.f));
+        for (int o = 0; o < cout; ++o)
+            for (int k = 0; k < 27; ++k) {
+                const float v = p[(size_t)k * cout + o];
+                const __half hi = __float2half_rn(v);
+                hl[(size_t)o * 32 + k] = hi;
+                hl[(size_t)(cout + o) * 32 + k] = __float2half_rn(v - __half2float(hi));
+            }
+        cw->w_hilo = (__half*)arena.alloc(hl.size() * sizeof(__half));
+        YDST_CUDA(cudaMemcpy(cw->w_hilo, hl.data(), hl.size() * sizeof(__half), cudaMemcpyHostToDevice));
     } else {
         const size_t K = (size_t)taps * cin;
         std::vector<__half> p((size_t)cw->cout16 * K, __float2half(0.f));
@@ -161,7 +172,7 @@ static void run_ops(const Plan& plan, cudaStream_t st) {
         switch (op.kind) {
             case OP_CONV_TC: conv_tc_run(op.conv, st); break;
             case OP_CONV_FIRST:
-                launch_conv_first(op.fsrc, op.out.N, op.i0, op.i1, op.w->w32, op.w->scale, op.w->bias, op.w->cout, op.i2, op.i3, op.out, st);
+                launch_conv_first(op.fsrc, op.out.N, op.i0, op.i1, op.w->w32, op.w->w_hilo, op.w->scale, op.w->bias, op.w->cout, op.i2, op.i3, op.out, st);
                 break;
             case OP_MAXPOOL: launch_maxpool(op.a, op.out, op.i0, op.i1, op.i2, st); break;
             case OP_UPSAMPLE: launch_upsample(op.a, op.out, op.i0, st); break;

@@ -14,7 +14,8 @@ namespace ydst {
 struct ConvWeights {
     int cin = 0, cout = 0, k = 0, cout16 = 0;
     __half* w16 = nullptr;    // [cout16][k*k*cin]  (tensor-core path)
-    float* w32 = nullptr;     // [27][cout]         (first-layer path)
+    float* w32 = nullptr;     // [27][cout]         (first-layer path, CUDA cores)
+    __half* w_hilo = nullptr; // [2][cout][32] fp16: hi = fp16(w), lo = fp16(w - hi), K = 27 padded to 32 (first-layer path, tensor cores)
     float* scale = nullptr;   // [cout rounded up to 256]
     float* bias = nullptr;
 };
