@@ -92,3 +92,28 @@ def test_features_vs_oracle_batches(extractor, m):
         crops = [frame[y1:y2, x1:x2] for (x1, y1, x2, y2) in (crop_box(b, 608, 608) for b in tlwh)]
         got2 = ex(crops).cpu().numpy()
         np.testing.assert_array_equal(got2, got)
+
+
+def test_features_batch_4096_config4():
+    """BASELINE configs[3]: the Extractor alone on 4096 crops in one forward.  Features are independent per crop, so the
+    result is checked against the oracle on a sample of the batch (first / middle / last crops), and against the same
+    crops pushed through in small batches (different tiling, same numbers to fp16 rounding)."""
+    from oracle import reid_ref as R
+    from oracle.synth import make_frame, reid_state_dict
+    sd = reid_state_dict(seed=0)
+    ex = Extractor(sd, use_cuda=True, max_batch=4096, device=DEV)
+    frame = make_frame(608, 608, seed=11)
+    rng = np.random.default_rng(4096)
+    m = 4096
+    tlwh = np.stack([rng.uniform(0, 500, m), rng.uniform(0, 440, m), rng.uniform(25, 90, m), rng.uniform(50, 160, m)], 1).astype(np.float32)
+    fd = torch.from_numpy(frame).to(DEV)
+    got = ex.extract(fd, torch.from_numpy(tlwh).to(DEV)).cpu().numpy()
+    assert got.shape == (m, 512) and np.isfinite(got).all()
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    sample = np.r_[0:24, 2036:2060, 4072:4096]
+    ref = R.extract(sd, frame, tlwh[sample]).numpy()
+    rel = np.linalg.norm(got[sample] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 5e-3, rel.max()
+    small = torch.cat([ex.extract(fd, torch.from_numpy(tlwh[i:i + 32]).to(DEV)) for i in (0, 2048, 4064)]).cpu().numpy()
+    big = np.concatenate([got[0:32], got[2048:2080], got[4064:4096]])
+    assert np.abs(small - big).max() < 2e-3
