@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
     if (warp == kProdWarp) {
         if (elect_one()) {
             // ================= TMA producer =================
-            int sa = 0, sb = 0;
+            int sa = 0, sb = 0, loaded_tn = -1;
             uint32_t pha = 1, phb = 1;
             int tm, tn;
             for (int it = 0; tile_at(it, tm, tn); ++it) {
@@ -569,6 +569,15 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
                     if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
                 };
                 int issued = 0;
+                if (kPers && p.b_resident) {
+                    // weight-stationary: the N tile's whole weight slab (total_b stages == b_stages) is fetched when the column block
+                    // changes and then serves every M tile this CTA processes; only the activation chunks stream
+                    if (tn != loaded_tn) {
+                        for (; issued < total_b; ++issued) issue_b();      // waits for the previous slab's last readers (emptyB)
+                        loaded_tn = tn;
+                    }
+                    issued = total_b;
+                }
                 if (it == 0) {
                     // weights never depend on the previous kernel: queue them before waiting on the grid dependency, so that
                     // under programmatic dependent launch they stream in while the producer of our input is still draining
@@ -592,10 +601,21 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
             const uint32_t hi = desc_hi(128);
             const uint32_t b_tile16 = b_tile_bytes >> 4;
-            int sa = 0, sb = 0;
+            int sa = 0, sb = 0, prev_tn = -1;
             uint32_t pha = 0, phb = 0;
+            const bool resident = kPers && p.b_resident;
             int tm, tn;
             for (int it = 0; tile_at(it, tm, tn); ++it) {
+                // weight-stationary tiles: wait for the slab only on its first use, release it only after its last use; the ring
+                // index restarts at 0 every tile (the slab occupies the whole ring) and the phase flips once per slab, not per tile
+                bool first_use = true, last_use = true;
+                if (resident) {
+                    int tm2, tn2;
+                    first_use = tn != prev_tn;
+                    last_use = !tile_at(it + 1, tm2, tn2) || tn2 != tn;
+                    prev_tn = tn;
+                    sb = 0;
+                }
                 const int ab = it & 1;                         // accumulator buffer
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n * mp);
                 if (kPers) mbar_wait_hot(bar_tempty + 8u * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
@@ -616,7 +636,7 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
                             while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
                             for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
                                 if (t_in == 0) {
-                                    mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                                    if (first_use) mbar_wait_hot(bar_fullB + 8u * sb, phb);
                                     tcgen05_fence_after();
                                     if (acc == 0 && it == 0) trace_mark(p, 3);
                                     b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
@@ -635,13 +655,13 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
                                 b_lo += b_tile16;
                                 if (++t_in == p.tpb) {
                                     t_in = 0;
-                                    umma_commit(bar_emptyB + 8u * sb);
-                                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                                    if (last_use) umma_commit(bar_emptyB + 8u * sb);
+                                    if (++sb == p.b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                                 }
                             }
                         }
                     } else {
-                        mbar_wait_hot(bar_fullB + 8u * sb, phb);
+                        if (first_use) mbar_wait_hot(bar_fullB + 8u * sb, phb);
                         tcgen05_fence_after();
                         if (acc == 0 && it == 0) trace_mark(p, 3);
                         uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
@@ -657,13 +677,14 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
                             }
                             acc = 1u;
                         }
-                        umma_commit(bar_emptyB + 8u * sb);
-                        if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                        if (last_use) umma_commit(bar_emptyB + 8u * sb);
+                        if (++sb == p.b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                     }
                     umma_commit(bar_emptyA + 8u * sa);
                     if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
                 }
                 umma_commit(bar_tfull + 8u * ab);
+                if (resident && last_use) phb ^= 1u;           // the next slab lands in the next phase of every weight barrier
                 if (it == 0) trace_mark(p, 4);
             }
         }
@@ -889,12 +910,18 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const int fixed_p = a_st * a_stage + 6144;
                     int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
                     if (b_stages < (pers ? 2 : 1)) continue;
+                    // weight-stationary persistent tiles: the N tile's whole weight slab fits and is fetched once per column block
+                    const bool resident = pers && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
+                                          env_int("YDST_B_RESIDENT", 1);
+                    if (resident) b_stages = total_b;
                     int smem = fixed_p + b_stages * b_stage + staging;
                     smem = std::max(smem, 36 * 1024);             // the TMA-store epilogue stages two 16 KB groups at the start of smem
                     const int occ = (!pers && smem <= 112 * 1024) ? 2 : 1;
                     const double inflight = (double)a_st * a_stage + (double)b_stages * b_stage;
                     const double rate = std::min(kFill, inflight / kLat);
-                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + (double)taps * bn * 128);
+                    const double tiles_per_cta = std::ceil((double)ctas / kSms);
+                    const double b_share = resident ? 1.0 / std::max(1.0, std::min(tiles_per_cta, (double)m_tiles)) : 1.0;   // slab amortised over the CTA's M tiles
+                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * bn * 128);
                     const double mma = (double)cps * taps * 4 * mp * std::max(16.0, bn / 2.0);
                     const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
                     const double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
@@ -909,7 +936,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
-                        best.mpair = mp;
+                        best.mpair = mp; best.b_resident = resident ? 1 : 0;
                     }
                 }
             }
@@ -984,6 +1011,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             p.tpb = t.tpb;
             p.m_tiles = (m_tiles + t.mpair - 1) / t.mpair; p.n_tiles = (p.cout + t.bn - 1) / t.bn;
             p.persistent = t.persistent;
+            p.b_resident = t.b_resident;
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
             p.store_tma = (!out_f32 && p.cout % 64 == 0 && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
@@ -1019,9 +1047,9 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             L.grid = dim3((unsigned)p.m_tiles, (unsigned)p.n_tiles, (unsigned)t.ksplit);
             if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
             if (getenv("YDST_DEBUG_PLAN"))
-                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d model %.1fus\n",
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d res %d model %.1fus\n",
                         R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.tpb, t.a_stages, t.b_stages,
-                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, p.mpair, t.model_us);
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, p.mpair, p.b_resident, t.model_us);
             return;
         }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};

@@ -36,6 +36,7 @@ struct ConvTcParams {
     int halo;             // chunk rows before the tile's first pixel (3x3: Wp + 1, 1x1: 0)
     int a_box_rows, a_boxes;   // the chunk is fetched as a_boxes TMA boxes of a_box_rows rows
     int a_stages, b_stages;
+    int b_resident;       // persistent only: all weight stages of an N tile fit in shared memory and stay there across its M tiles
     int persistent;       // 1: 1-D grid of at most one CTA per SM, each looping over output tiles with two TMEM accumulators
     int m_tiles, n_tiles;
     int mpair;            // 128-row accumulators per CTA tile (1 or 2): a pair of M tiles shares every weight stage
@@ -74,7 +75,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                   const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
                   const ConvWorkspace* ws = nullptr);
 // the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
-struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair; double model_us; };
+struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair, b_resident; double model_us; };
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets);
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_trace_dump();   // YDST_CONV_TRACE=2: print the per-launch timeline collected so far (debug aid)
