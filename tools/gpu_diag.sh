@@ -1,3 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dropin.py tests/test_gpu_pipeline.py -q -m gpu --tb=short 2>&1 | tail -12
+run() { name=$1; shift
+  env "$@" timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/bench_$name.err
+}
+run default YDST_GRAPH=1
+timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline --micro-batch 1 > gpurun_out/bench_mb1.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/bench_mb1.json')); print('mb1', d['value'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])"

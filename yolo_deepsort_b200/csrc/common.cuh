@@ -122,10 +122,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+// Used by the epilogue warps, which wait for the whole main loop: they back off with nanosleep so that their polling does not
+// take issue slots from the single MMA-issuing / TMA-issuing threads that share their scheduler.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        __nanosleep(spins < 64 ? 100 : 400);
+        if (++spins > (1u << 24)) {
             printf("ydst: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }
