@@ -25,7 +25,10 @@ full)
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --micro-batch 1 > gpurun_out/ncu_full_a.log 2>&1
   YDST_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 322 -c 2 -o gpurun_out/prof_full_19 -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --micro-batch 1 > gpurun_out/ncu_full_b.log 2>&1
-  for f in 76 19; do ncu -i gpurun_out/prof_full_$f.ncu-rep --page raw --csv > gpurun_out/prof_full_$f.csv 2>/dev/null; done
+  # the same 3x3 128->256 @76x76 layer at the bench's default micro-batch (what roofline.traffic quotes)
+  YDST_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 289 -c 1 -o gpurun_out/prof_full_mb -f \
+      python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_c.log 2>&1
+  for f in 76 19 mb; do ncu -i gpurun_out/prof_full_$f.ncu-rep --page raw --csv > gpurun_out/prof_full_$f.csv 2>/dev/null; done
   ls -la gpurun_out/*.ncu-rep ;;
 esac
 done

@@ -35,7 +35,8 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
         "launch__occupancy_limit_registers", "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
 full = []
-for name, what in (("76", ["1x1 256->128 @76x76", "3x3 128->256 @76x76"]), ("19", ["1x1 1024->512 @19x19", "3x3 512->1024 @19x19"])):
+for name, what in (("76", ["1x1 256->128 @76x76", "3x3 128->256 @76x76"]), ("19", ["1x1 1024->512 @19x19", "3x3 512->1024 @19x19"]),
+                   ("mb", ["3x3 128->256 @76x76, default micro-batch"])):
     path = os.path.join(G, f"prof_full_{name}.csv")
     if not os.path.exists(path):
         continue
@@ -57,7 +58,7 @@ if full:
     def num(s):
         v, u = s.split()[0], (s.split() + [""])[1]
         return float(v.replace(",", "")) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1}.get(u, 1)
-    for d in full:
+    for d in sorted(full, key=lambda d: "micro-batch" in d["layer"]):        # the micro-batch capture wins when present
         if d["layer"].startswith("3x3 128->256"):
             t = num(d["dram__bytes_read.sum"]) + num(d["dram__bytes_write.sum"])
             json.dump({"layer": d["layer"], "dram_bytes_per_launch": t, "source": f"profiles/conv_full_{tag}.json"}, open(os.path.join(P, "conv_tc_traffic.json"), "w"))
