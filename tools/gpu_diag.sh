@@ -5,5 +5,5 @@ run() { name=$1; shift
   python -c "
 import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/bench_$name.err
 }
-run default YDST_GRAPH=1
-timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline --micro-batch 1 > gpurun_out/bench_mb1.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/bench_mb1.json')); print('mb1', d['value'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])"
+run smem_model YDST_MODEL_SMEM=1
+run old_model YDST_MODEL_SMEM=0

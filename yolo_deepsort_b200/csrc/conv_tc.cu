@@ -922,7 +922,10 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const double tiles_per_cta = std::ceil((double)ctas / kSms);
                     const double b_share = resident ? 1.0 / std::max(1.0, std::min(tiles_per_cta, (double)m_tiles)) : 1.0;   // slab amortised over the CTA's M tiles
                     const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * bn * 128);
-                    const double mma = (double)cps * taps * 4 * mp * std::max(16.0, bn / 2.0);
+                    // one 128 x bn x 16 MMA takes bn/2 tensor clocks but also reads 4 KB of A and 32*bn B of B from shared memory
+                    // (128 B/clk): narrow N tiles are shared-memory-bound (bn = 32: 40 clk instead of 16, bn = 64: 48 instead of 32)
+                    const double mma_step = std::max(bn / 2.0, (4096.0 + 32.0 * bn) / 128.0);
+                    const double mma = (double)cps * taps * 4 * mp * mma_step;
                     const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
                     const double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
                     const bool st = tma_store_ok && bn >= 64 && ks == 1;
