@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { name=$1; shift
-  env "$@" timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  env "$@" timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline --dump-ops gpurun_out/ops_$name.csv > gpurun_out/bench_$name.json 2> gpurun_out/plan_$name.txt
   python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/bench_$name.err
+import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/plan_$name.txt
 }
-run smem_model YDST_MODEL_SMEM=1
-run old_model YDST_MODEL_SMEM=0
+run bn256 YDST_PREFER_BN256=1 YDST_DEBUG_PLAN=1
+run base YDST_DEBUG_PLAN=1
