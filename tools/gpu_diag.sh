@@ -5,5 +5,6 @@ run() { name=$1; shift
   python -c "
 import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/plan_$name.txt
 }
-run bn256 YDST_PREFER_BN256=1 YDST_DEBUG_PLAN=1
-run base YDST_DEBUG_PLAN=1
+run bn256_96 YDST_DEBUG_PLAN=1
+run bn256_96_tpb1 YDST_TPB1_BN128=1 YDST_DEBUG_PLAN=1
+run bn256_48 YDST_BN256_MIN_CTAS=48 YDST_DEBUG_PLAN=1

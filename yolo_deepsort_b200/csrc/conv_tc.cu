@@ -886,7 +886,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
             // weight-stage granularity: one TMA instruction costs the producer thread ~200 clocks to issue, so boxes below
             // ~16 KB make the PRODUCER the bottleneck (measured: tpb = 1 everywhere cost 15 % end to end); the step term below
             // steers towards multi-slice stages, the first-stage term keeps them from growing without bound
-            const int tpb_opts3[3] = {9, 3, 1}, tpb_opts1[3] = {8, 4, 2};
+            // N = 256 tiles: one tap is already 32 KB of weights and 512 tensor clocks, so single-tap stages pipeline best
+            const bool fine = bn == 256;
+            const int tpb_opts3[3] = {fine ? 1 : 9, fine ? 1 : 3, 1}, tpb_opts1[3] = {8, 4, 2};
             for (int oi = 0; oi < 3; ++oi) {
                 const int tpb = taps == 9 ? tpb_opts3[oi] : std::min(tpb_opts1[oi], cps);
                 if (taps == 1 && oi > 0 && tpb == std::min(tpb_opts1[oi - 1], cps)) continue;     // same as the previous option
@@ -936,6 +938,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     else if (per_sm > 1) t += (per_sm - 1) / occ * (kSetup + kFirst);          // every further wave pays the front again
                     if (ks > 1) t += 1500.0 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / 30.0;
                     t /= kClkPerUs;
+                    // measured: where an N = 256 tile still leaves >= 96 CTAs it beats the model's pick -- the 128 x 256 MMA is
+                    // the only shape whose operand reads fit the shared-memory bandwidth -- so it gets a bonus the clock model lacks
+                    if (env_int("YDST_PREFER_BN256", 1) && bn == 256 && ctas >= 96 && ks == 1) t *= 0.5;
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
