@@ -75,6 +75,8 @@ __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 28)) __trap();          // a protocol bug must abort the launch, never hang the GPU
 }
 
+__device__ __forceinline__ bool env_res_early(const ConvTcParams& p) { return !(p.bo_mode & 2); }   // YDST_BO_MODE=2: tuning switch
+
 __device__ __forceinline__ void trace_mark_epi(const ConvTcParams& p, int slot) {      // thread 100: a row that is valid in CTA 0
     if (p.trace && threadIdx.x == 100 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = (unsigned long long)clock64();
 }
@@ -290,6 +292,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
             const int x = row & 7;
             rbase[(2 * sub) ^ x] = w0;
             rbase[(2 * sub + 1) ^ x] = w1;
+            if (g == 0 && sub == 0) trace_mark_epi(p, 15);
         }
         if (g == 0) trace_mark_epi(p, 12);
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -302,6 +305,147 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvTcParams& p, const C
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+    }
+}
+
+// Eight-warp variant of the TMA-store epilogue (one-tile-per-CTA launches of the halo kernel).  Warps w and w+4 share TMEM lane
+// quarter w & 3: for every 64-column group, warpgroup `half` handles columns [32*half, 32*half+32) of each row, so two warps per
+// scheduler cover each other's latencies and the per-thread work halves.  Every group has its own 16 KB staging buffer (no reuse,
+// no waits on earlier stores).  The residual tile is not fetched thread-per-row (32 cache lines per warp instruction) but by TMA
+// into the same swizzled staging buffer the result is written to: a thread reads its residual chunks, then overwrites them.
+// The arithmetic is the bound here (measured: tcgen05.ld delivers > 300 B/clk/SM, tools/micro/tmem_read.cu), so the activation
+// and residual mode are compile-time (no per-block uniform branches / parameter loads) and the fp32 work uses the packed
+// FFMA2 / FMUL2 / FADD2 forms, which round exactly like their scalar counterparts.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// y = acc*scale + bias, residual before (kRes 2) or after (kRes 1) the activation, fp16 pack: the compile-time twin of compute16 + pack16
+template <int kAct, int kRes>
+__device__ __forceinline__ void finish16_static(const uint32_t (&v)[16], const float* s_scale, const float* s_bias, const uint4& r0, const uint4& r1,
+                                                uint4& w0, uint4& w1) {
+    const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+    const float4* bi4 = reinterpret_cast<const float4*>(s_bias);
+    float o[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 sc = sc4[q], bi = bi4[q];
+        ffma2(o[4 * q + 0], o[4 * q + 1], __uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1]), sc.x, sc.y, bi.x, bi.y);
+        ffma2(o[4 * q + 2], o[4 * q + 3], __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]), sc.z, sc.w, bi.z, bi.w);
+    }
+    float rs[16];
+    if (kRes) {
+        const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+        const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
+            rs[2 * q] = f0.x; rs[2 * q + 1] = f0.y;
+            rs[8 + 2 * q] = f1.x; rs[8 + 2 * q + 1] = f1.y;
+        }
+    }
+    if (kRes == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) fadd2(o[j], o[j + 1], o[j], o[j + 1], rs[j], rs[j + 1]);
+    }
+    if (kAct == ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            float t0, t1;
+            fmul2(t0, t1, o[j], o[j + 1], 0.1f, 0.1f);
+            o[j] = fmaxf(o[j], t0);                                 // == (x > 0 ? x : 0.1x) for every finite x
+            o[j + 1] = fmaxf(o[j + 1], t1);
+        }
+    } else if (kAct == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (kAct == ACT_MISH) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = apply_act(o[j], ACT_MISH);
+    }
+    if (kRes == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) fadd2(o[j], o[j + 1], o[j], o[j + 1], rs[j], rs[j + 1]);
+    }
+    pack16(o, w0, w1);
+}
+
+// kAct / kRes < 0: activation and residual mode read from the parameters at run time (the rare combinations)
+template <bool kMish, int kAct, int kRes>
+__device__ __forceinline__ void epilogue_tile_wide(const ConvTcParams& p, const CUtensorMap* out_map, const CUtensorMap* res_map,
+                                                   const uint32_t (&gaddr)[4], unsigned char* smem_generic, uint32_t smem_generic_u32,
+                                                   uint32_t tmem_base, int wq, int half, int row, int n0, int p0, bool valid,
+                                                   const float* s_sb, uint32_t bar_tmem, uint32_t bar_res, bool res_issued) {
+    const int ngroups = p.block_n >> 6, bn = p.block_n;
+    const bool has_res = kRes < 0 ? p.res_mode != 0 : kRes != 0;
+    mbar_wait(bar_tmem, 0);
+    tcgen05_fence_after();
+    if (has_res && !res_issued && threadIdx.x == 0) {             // the operand stages are dead: fetch every group's residual tile
+        for (int g = 0; g < ngroups && n0 + g * 64 < p.cout; ++g) {
+            mbar_arrive_expect_tx(bar_res + 8u * g, kBlockM * 128u);
+            tma_load_2d(gaddr[g], res_map, bar_res + 8u * g, p.res_coff + n0 + g * 64, p0);
+        }
+    }
+    const int x = row & 7;
+    const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 32);
+    const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;               // border pixels are stored as zeros (branch-free)
+    // one 16-column block: scale/bias/activation/residual, fp16 pack, and the two 16-byte chunks of this row in the swizzled tile
+    auto process = [&](const uint32_t (&v)[16], int g, int sub, uint4* rbase) {
+        const int ch = 4 * half + 2 * sub;
+        const int cl = g * 64 + half * 32 + sub * 16;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, w0, w1;
+        if (has_res) { r0 = rbase[ch ^ x]; r1 = rbase[(ch + 1) ^ x]; }
+        if (kAct >= 0) {
+            finish16_static<kAct, kRes>(v, s_sb + cl, s_sb + bn + cl, r0, r1, w0, w1);
+        } else {
+            float acc[16], o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+            compute16<kMish>(p, acc, s_sb + cl, s_sb + bn + cl, r0, r1, o);
+            pack16(o, w0, w1);
+        }
+        w0.x &= keep; w0.y &= keep; w0.z &= keep; w0.w &= keep;
+        w1.x &= keep; w1.y &= keep; w1.z &= keep; w1.w &= keep;
+        rbase[ch ^ x] = w0;
+        rbase[(ch + 1) ^ x] = w1;
+    };
+    // the TMEM load of block i+1 is in flight while block i is computed; tcgen05.wait::ld waits for every outstanding load, so the
+    // next one is issued right after the wait
+    uint32_t va[16], vb[16];
+    __syncwarp();
+    tmem_ld_32x32b_x16(tbase, va);
+#pragma unroll 1
+    for (int g = 0; g < ngroups; ++g) {
+        const int c0 = n0 + g * 64;
+        if (c0 >= p.cout) break;
+        uint4* rbase = reinterpret_cast<uint4*>(smem_generic + (gaddr[g] - smem_generic_u32) + (size_t)row * 128u);
+        tcgen05_wait_ld();
+        __syncwarp();
+        tmem_ld_32x32b_x16(tbase + (uint32_t)(g * 64 + 16), vb);
+        if (has_res) mbar_wait(bar_res + 8u * g, 0);
+        process(va, g, 0, rbase);
+        tcgen05_wait_ld();
+        if (g + 1 < ngroups && c0 + 64 < p.cout) {
+            __syncwarp();
+            tmem_ld_32x32b_x16(tbase + (uint32_t)((g + 1) * 64), va);
+        }
+        process(vb, g, 1, rbase);
+        fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+            tma_store_2d(out_map, gaddr[g], p.out_coff + c0, p0);
+            tma_store_commit();
+        }
     }
 }
 
@@ -459,13 +603,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // Persistent instantiations run TWO epilogue warpgroups (warps 0-3 and 4-7): tile i is drained by group i & 1, which also owns
 // accumulator buffer i & 1, so the epilogues of consecutive tiles overlap each other as well as the main loop.
-static constexpr int kThreadsPers = 320;
+static constexpr int kThreads2 = 320;   // warps 0-7: epilogue (two per TMEM lane quarter), warp 8: TMA producer, warp 9: MMA issuer + TMEM owner
 template <bool kMish, bool kPers, bool kPair>
-__global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
+__global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
-    constexpr int kEpiGroups = kPers ? 2 : 1;                  // epilogue warpgroups of 4 warps
+    constexpr int kEpiGroups = 2;                              // epilogue warpgroups of 4 warps
     constexpr int kProdWarp = 4 * kEpiGroups, kMmaWarp = kProdWarp + 1;
     if (threadIdx.x == 0) trace_mark(p, 0);
 
@@ -481,13 +625,32 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
     const uint32_t stage_area = (kPers && p.store_tma) ? 4u * kBlockM * 128u : 0u;    // two 16 KB buffers per epilogue warpgroup
     const uint32_t a_base = smem_base + stage_area;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
-    const uint32_t bar_base = b_base + (uint32_t)p.b_stages * b_stage_bytes;
+    // the wide epilogue stages one 16 KB buffer per 64-column group over the (then dead) operand stages: keep the barriers clear of it
+    const bool wide = !kPers && !kPair && p.store_tma;         // (the planner only sets store_tma on unsplit launches)
+    const uint32_t stage_need = wide ? (uint32_t)(p.block_n >> 6) * (kBlockM * 128u) : (p.store_tma ? 2u * kBlockM * 128u : 0u);
+    const uint32_t bar_base = max(b_base + (uint32_t)p.b_stages * b_stage_bytes, smem_base + stage_need);
     const int nab = k3 ? p.a_boxes : 1;                        // "full" barriers per A stage: one per TMA box of the halo chunk
     const uint32_t bar_fullA = bar_base, bar_emptyA = bar_fullA + 8u * p.a_stages * nab;
     const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
     const uint32_t bar_tfull = bar_emptyB + 8u * p.b_stages;   // [2] accumulator complete
     const uint32_t bar_tempty = bar_tfull + 16u;               // [2] accumulator drained by the epilogue (128 arrivals)
-    const uint32_t tmem_slot = bar_tempty + 16u, flag_slot = tmem_slot + 4u;
+    const uint32_t bar_res = bar_tempty + 16u;                 // [4] residual tile of a 64-column group has landed (wide epilogue)
+    // Wide epilogue with a residual: the tiles are fetched by the PRODUCER into the weight stages as the last MMAs release them
+    // (up to b_stages - 1 taps before the accumulator is complete), and the results are staged in place.  Group g lives in the
+    // (g / gps)-th stage to be released after the last weight load, gps = 16 KB tiles per stage.
+    const uint32_t gps = b_stage_bytes / (kBlockM * 128u);
+    const bool res_early = wide && p.res_mode && gps >= 1u && (uint32_t)(p.block_n >> 6) <= gps * (uint32_t)p.b_stages && env_res_early(p);
+    // (every role that needs the group addresses computes them itself: the divisions stay off the common prologue)
+    auto group_addrs = [&](uint32_t (&ga)[4], int first_stage) {
+        int st = first_stage;
+        uint32_t k = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            ga[g] = res_early ? b_base + (uint32_t)st * b_stage_bytes + k * (kBlockM * 128u) : smem_base + (uint32_t)g * (kBlockM * 128u);
+            if (++k == gps) { k = 0; if (++st == p.b_stages) st = 0; }
+        }
+    };
+    const uint32_t tmem_slot = bar_res + 32u, flag_slot = tmem_slot + 4u;
     float* s_sb = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.block_n * mp * (kPers ? 2 : 1)) tmem_cols <<= 1;
@@ -497,6 +660,7 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
         for (int s = 0; s < p.a_stages; ++s) mbar_init(bar_emptyA + 8u * s, 1);
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, 128); }
+        for (int s = 0; s < 4; ++s) mbar_init(bar_res + 8u * s, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -504,6 +668,7 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
         if (p.store_tma) tma_prefetch_desc(&maps.a[1]);
+        if (wide && p.res_mode) tma_prefetch_desc(&maps.a[2]);
     }
     if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, tmem_cols);
@@ -591,6 +756,20 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
                     if (p.a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
                     for (; issued < (i + 1) * nbs; ++issued) issue_b();
                     if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
+                }
+            }
+            if (res_early) {
+                // sb / phb point at the next stage the ring would refill, i.e. the next one the MMAs release
+                const int ngroups = p.block_n >> 6, n0 = (int)blockIdx.y * p.block_n, p0 = (int)blockIdx.x * kBlockM;
+                uint32_t gaddr[4];
+                group_addrs(gaddr, sb);
+                for (int g = 0; g < ngroups && n0 + g * 64 < p.cout; ++g) {
+                    if (g % (int)gps == 0) {
+                        if (g) { if (++sb == p.b_stages) { sb = 0; phb ^= 1u; } }
+                        mbar_wait_hot(bar_emptyB + 8u * sb, phb);
+                    }
+                    mbar_arrive_expect_tx(bar_res + 8u * g, kBlockM * 128u);
+                    tma_load_2d(gaddr[g], &maps.a[2], bar_res + 8u * g, p.res_coff + n0 + g * 64, p0);
                 }
             }
             prefetch_next_weights(p);
@@ -690,7 +869,8 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
         }
     } else {
         // ================= epilogue =================
-        const int eg = warp >> 2;                              // epilogue warpgroup (always 0 unless persistent)
+        const int eg = kPers ? warp >> 2 : 0;                  // persistent: the warpgroups alternate tiles
+        const int half = kPers ? 0 : warp >> 2;                // otherwise: both work on the one tile (wide epilogue), or the second idles
         const int tid = threadIdx.x & 127, ebar = 1 + eg;
         const int wq = warp & 3;                               // TMEM lane quarter of this warp
         const int row = tid;
@@ -699,13 +879,23 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
         const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
         int stores = 0, staged_tn = -1;
         bool first = true;
+        uint32_t gaddr[4];
+        {
+            const int total_b = nmacro * nbs;                  // weight stages issued per tile: the ring position after the last one
+            group_addrs(gaddr, res_early ? total_b % p.b_stages : 0);
+        }
         int tm, tn;
         for (int it = 0; tile_at(it, tm, tn); ++it) {
             if (kPers && (it & 1) != eg) continue;             // the other warpgroup drains this tile
+            if (!kPers && !wide && half) break;                // direct-store and split-K epilogues use one warpgroup
             const int n0 = tn * p.block_n;
             const int ab = it & 1;
             const uint32_t bar_full = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
-            if (tn != staged_tn) {                             // M runs fastest: the column block (and its scale/bias) rarely changes
+            if (wide) {
+                for (int i = threadIdx.x; i < 2 * p.block_n; i += 256)
+                    s_sbg[i] = i < p.block_n ? __ldg(p.scale + n0 + i) : __ldg(p.bias + n0 + i - p.block_n);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            } else if (tn != staged_tn) {                      // M runs fastest: the column block (and its scale/bias) rarely changes
                 if (!first) epi_bar_sync(ebar);                // everyone is done with the previous tile's scale/bias
                 stage_scale_bias(p, n0, s_sbg, tid, ebar);
                 staged_tn = tn;
@@ -722,7 +912,27 @@ __global__ void __launch_bounds__(kPers ? kThreadsPers : kThreads, kPers ? 1 : 2
             const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
             if (p.ksplit == 1) {
                 if (it == 0 && h == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
-                if (p.store_tma)
+                if constexpr (!kPers && !kPair) {
+                    if (wide) {
+#define YDST_WIDE(A, R) epilogue_tile_wide<kMish, A, R>(p, &maps.a[1], &maps.a[2], gaddr, smem_raw, smem_u32(smem_raw), tmem_d, wq, half, row, n0, p0, \
+                                                        valid, s_sbg, bar_full, bar_res, res_early)
+                        const int key = p.act * 4 + p.res_mode;    // warp-uniform: one specialised epilogue per common combination
+                        if (kMish) {
+                            if (key == ACT_MISH * 4 + 0) YDST_WIDE(ACT_MISH, 0);
+                            else if (key == ACT_MISH * 4 + 1) YDST_WIDE(ACT_MISH, 1);
+                            else YDST_WIDE(-1, -1);
+                        } else {
+                            if (key == ACT_LEAKY * 4 + 0) YDST_WIDE(ACT_LEAKY, 0);
+                            else if (key == ACT_LEAKY * 4 + 1) YDST_WIDE(ACT_LEAKY, 1);
+                            else if (key == ACT_RELU * 4 + 0) YDST_WIDE(ACT_RELU, 0);
+                            else if (key == ACT_RELU * 4 + 2) YDST_WIDE(ACT_RELU, 2);
+                            else if (key == ACT_LINEAR * 4 + 0) YDST_WIDE(ACT_LINEAR, 0);
+                            else YDST_WIDE(-1, -1);
+                        }
+#undef YDST_WIDE
+                    }
+                    else epilogue_tile<kMish>(p, tmem_d, wq, n0, pp, valid, s_sbg, bar_full, par, bar_rel);
+                } else if (p.store_tma)
                     epilogue_tile_tma<kMish>(p, &maps.a[1], stage_g, smem_raw + (stage_g - smem_u32(smem_raw)), tmem_d, wq, n0, p0, pp, valid,
                                              s_sbg, bar_full, par, bar_rel, stores, tid, ebar);
                 else epilogue_tile<kMish>(p, tmem_d, wq, n0, pp, valid, s_sbg, bar_full, par, bar_rel);
@@ -882,7 +1092,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
             if (ks > 1 && ((size_t)ks * tiles * kBlockM * bn * 4 > ws_bytes || tiles > max_tickets || mp > 1)) continue;
             if (ks > 16) continue;
             const long long ctas = tiles * ks;
-            const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = 108 * 1024;
+            // two CTAs per SM: 227 KB of shared memory less 1 KB of system use per CTA -> 113 KB each
+            const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = env_int("YDST_SMEM_BUDGET2_KB", 113) * 1024;
+            const int co_model = env_int("YDST_CO_MODEL", 2);
             // weight-stage granularity: one TMA instruction costs the producer thread ~200 clocks to issue, so boxes below
             // ~16 KB make the PRODUCER the bottleneck (measured: tpb = 1 everywhere cost 15 % end to end); the step term below
             // steers towards multi-slice stages, the first-stage term keeps them from growing without bound
@@ -897,11 +1109,12 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 const int total_b = nmacro * nbs;
                 const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * mp * 128;
                 const int b_stage = tpb * bn * 128;
-                const int a_stages = std::min(nmacro, taps == 9 ? 2 : 4);
-                const int fixed = a_stages * a_stage + 6144;
+                const int a_stages_max = std::min(nmacro, taps == 9 ? 2 : 4);
                 // pass 0: leave room for a second CTA on the SM; pass 1: whole SM; pass 2: persistent -- one CTA per SM loops over
                 // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
-                for (int pass = 0; pass < 3; ++pass) {
+                for (int pass = 0; pass < 3; ++pass)
+                for (int a_stages = a_stages_max; a_stages >= 1; --a_stages) {
+                    if (a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
                     const bool pers = pass == 2;
                     if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !env_int("YDST_PERSISTENT", 0))) continue;
                     const int staging = pers ? 64 * 1024 : 0;       // two 16 KB store buffers per epilogue warpgroup
@@ -917,11 +1130,16 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                                           env_int("YDST_B_RESIDENT", 1);
                     if (resident) b_stages = total_b;
                     int smem = fixed_p + b_stages * b_stage + staging;
-                    smem = std::max(smem, 36 * 1024);             // the TMA-store epilogue stages two 16 KB groups at the start of smem
-                    const int occ = (!pers && smem <= 112 * 1024) ? 2 : 1;
+                    // the TMA-store epilogue stages 16 KB per 64-column group (two buffers in persistent / pair mode) at the start of smem
+                    smem = std::max(smem, std::max(2, bn / 64) * 16 * 1024 + 6144);
+                    const int occ = (!pers && smem <= budget_2) ? 2 : 1;
                     const double inflight = (double)a_st * a_stage + (double)b_stages * b_stage;
-                    const double rate = std::min(kFill, inflight / kLat);
                     const double tiles_per_cta = std::ceil((double)ctas / kSms);
+                    // CTAs sharing an SM fill it together: the bytes in flight are those of all co-resident CTAs
+                    const double co = co_model ? std::min((double)occ, tiles_per_cta) : 1.0;
+                    const double rate = std::min(kFill, co * inflight / kLat);
+                    // the two operand streams are pipelined separately: each is also bound by its own bytes in flight
+                    const double rate_a = co * (double)a_st * a_stage / kLat, rate_b = co * (double)b_stages * b_stage / kLat;
                     const double b_share = resident ? 1.0 / std::max(1.0, std::min(tiles_per_cta, (double)m_tiles)) : 1.0;   // slab amortised over the CTA's M tiles
                     const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * bn * 128);
                     // one 128 x bn x 16 MMA takes bn/2 tensor clocks but also reads 4 KB of A and 32*bn B of B from shared memory
@@ -929,7 +1147,11 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const double mma_step = std::max(bn / 2.0, (4096.0 + 32.0 * bn) / 128.0);
                     const double mma = (double)cps * taps * 4 * mp * mma_step;
                     const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
-                    const double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
+                    double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
+                    if (co_model >= 2) {
+                        const double bytes_a = (double)cps * (taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0);
+                        main_clk = std::max(main_clk, std::max(bytes_a / rate_a, (bytes - bytes_a) / rate_b));
+                    }
                     const bool st = tma_store_ok && bn >= 64 && ks == 1;
                     const double epi = mp * (700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0));
                     const double per_sm = std::ceil((double)ctas / kSms);
@@ -1049,6 +1271,11 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 cuuint64_t strides[1] = {(cuuint64_t)out.ctot * 2};
                 cuuint32_t box[2] = {64u, (cuuint32_t)kBlockM};
                 encode(&L.tmA[1], out.base, 2, dims, strides, box, 128);
+                if (res_mode) {                                  // the wide epilogue fetches the residual tile by TMA
+                    cuuint64_t rdims[2] = {(cuuint64_t)res->ctot, (cuuint64_t)p.P_total};
+                    cuuint64_t rstrides[1] = {(cuuint64_t)res->ctot * 2};
+                    encode(&L.tmA[2], res->base, 2, rdims, rstrides, box, 128);
+                }
             }
             L.stages = 0;
             L.smem_bytes = t.smem_bytes + 1024;
@@ -1183,7 +1410,7 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
             g_trace_shape[slot] = L.p.Wo * 10000 + L.p.cout;
         }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = L.grid; cfg.blockDim = dim3(L.p.persistent ? kThreadsPers : kThreads); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
+        cfg.gridDim = L.grid; cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1208,6 +1435,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
                             "acc_ready %lld epilogue_done %lld exit %lld clk | cta0 %.2f us, last CTA started +%.2f us\n",
                     L.p.R, L.p.cin, L.p.cout, L.p.N, L.p.Ho, L.p.Wo, L.grid.x, L.grid.y, L.grid.z, L.p.block_n, d(0, 1), d(0, 2), d(0, 3), d(0, 4),
                     d(0, 5), d(0, 6), d(0, 7), (h[9] - h[8]) * 1e-3, ((long long)h[10] - (long long)h[8]) * 1e-3);
+            if (h[11]) fprintf(stderr, "    epilogue thread 100, group 0: acc_ready %lld | 16 cols in registers +%lld, computed +%lld, staged +%lld, next 16 cols in registers +%lld, "
+                               "group staged and barrier passed +%lld (res_mode %d)\n", d(0, 5), d(5, 11), d(11, 15), d(15, 12), d(12, 13), d(13, 14), L.p.res_mode);
         }
         return;
     }
