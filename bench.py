@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 METRIC = "end-to-end FPS (608x608, ~50 dets/frame)"
 UNIT = "frames/s"
 CFG, SIZE = "yolov3", 608
-MICRO_BATCH = 4
+MICRO_BATCH = 8          # consecutive frames per Darknet / ReID forward (3 slots in flight: 24 frames of look-ahead)
 
 
 def env_int(name, default):

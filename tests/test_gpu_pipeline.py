@@ -136,9 +136,10 @@ def test_lookahead_pipeline_equals_synchronous_steps():
     assert pipe2.in_flight() == 0
     with pytest.raises(Exception):
         pipe2.collect()                     # nothing in flight
-    # micro-batches of 2 and 3 consecutive frames per Darknet / ReID forward (12 frames: 3 leaves no remainder, 5 does)
+    # micro-batches of 2, 3, 5 and 8 consecutive frames per Darknet / ReID forward (12 frames: 3 leaves no remainder, 5 and 8 do;
+    # 8 is the bench default and the largest the batched NMS takes)
     from yolo_deepsort_b200 import DeepSort, FramePipeline
-    for mb in (2, 3, 5):
+    for mb in (2, 3, 5, 8):
         ds_mb = DeepSort(sd, max_dist=0.3, min_confidence=1, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30, use_cuda=True, device=DEV)
         pipe_mb = FramePipeline(model, ds_mb, thres=0.5, nms_thres=0.4, class_mask=[0, 2, 4], micro_batch=mb)
         out_mb = list(pipe_mb.run(frames_dev if mb != 3 else clip))

@@ -117,3 +117,19 @@ def test_features_batch_4096_config4():
     small = torch.cat([ex.extract(fd, torch.from_numpy(tlwh[i:i + 32]).to(DEV)) for i in (0, 2048, 4064)]).cpu().numpy()
     big = np.concatenate([got[0:32], got[2048:2080], got[4064:4096]])
     assert np.abs(small - big).max() < 2e-3
+
+
+def test_fused_stem_matches_unfused(monkeypatch):
+    """The first layer + MaxPool2d(3,2,1) kernel keeps the 128x64x64 activation on chip; rounding to fp16 is monotone, so its
+    features must be BIT-identical to the default two-kernel stem for every crop."""
+    from oracle.synth import make_frame, reid_state_dict
+    sd = reid_state_dict(seed=0)
+    frame = torch.from_numpy(make_frame(608, 608, seed=5)).to(DEV)
+    rng = np.random.default_rng(77)
+    m = 61
+    tlwh = np.stack([rng.uniform(-20, 560, m), rng.uniform(-20, 520, m), rng.uniform(25, 90, m), rng.uniform(50, 160, m)], 1).astype(np.float32)
+    monkeypatch.setenv("YDST_STEM_FUSED", "1")               # opt-in (not faster yet, DESIGN.md 5)
+    fused = Extractor(sd, use_cuda=True, max_batch=64, device=DEV).extract(frame, torch.from_numpy(tlwh).to(DEV)).cpu().numpy()
+    monkeypatch.setenv("YDST_STEM_FUSED", "0")
+    plain = Extractor(sd, use_cuda=True, max_batch=64, device=DEV).extract(frame, torch.from_numpy(tlwh).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(fused, plain)

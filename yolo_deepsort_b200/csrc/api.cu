@@ -50,8 +50,9 @@ struct ydst_pipeline {
         int n_collected = 0;
         int feat_off[8] = {0};        // first feature row of each frame
     } slot[kSlots];
-    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr;
-    cudaEvent_t ev_in = nullptr;
+    cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sH = nullptr;   // detector | association | crops+ReID | host-frame uploads
+    cudaEvent_t ev_in = nullptr, ev_h2d = nullptr;
+    bool h2d_pending = false;
     long long submitted = 0, collected = 0;
     long long fill = 0, drain = 0;    // slot sequence numbers: slot[fill % kSlots] accepts frames, slot[drain % kSlots] is collected from
     int* h_payload = nullptr;
@@ -453,10 +454,20 @@ int ydst_pipeline_create(ydst_detector* det, ydst_reid* reid, ydst_tracker* trk,
     }
     YDST_CUDA(cudaMalloc(&p->mask_dev, sizeof(int) * (n_mask > 0 ? n_mask : 1)));
     if (n_mask > 0) YDST_CUDA(cudaMemcpy(p->mask_dev, class_mask_host, sizeof(int) * n_mask, cudaMemcpyHostToDevice));
-    YDST_CUDA(cudaStreamCreateWithFlags(&p->sA, cudaStreamNonBlocking));
-    YDST_CUDA(cudaStreamCreateWithFlags(&p->sB, cudaStreamNonBlocking));
-    YDST_CUDA(cudaStreamCreateWithFlags(&p->sC, cudaStreamNonBlocking));
+    // oldest work first: the association of frame t (many small kernels, host in the loop) must not queue behind the CTAs of the
+    // ReID forward of t+1 and the detector forward of t+2, which each fill the GPU on their own
+    int prio_least = 0, prio_greatest = 0;
+    YDST_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const char* pe = getenv("YDST_STREAM_PRIO");
+    const int prio_mode = pe ? atoi(pe) : 2;                           // 0: off, 1: association > ReID > detector, 2: association only (measured best)
+    const bool use_prio = prio_mode != 0;
+    const int prio_mid = (prio_mode == 1 && prio_greatest < prio_least) ? prio_greatest + 1 : prio_least;
+    YDST_CUDA(cudaStreamCreateWithPriority(&p->sA, cudaStreamNonBlocking, prio_least));
+    YDST_CUDA(cudaStreamCreateWithPriority(&p->sB, cudaStreamNonBlocking, use_prio ? prio_greatest : prio_least));
+    YDST_CUDA(cudaStreamCreateWithPriority(&p->sC, cudaStreamNonBlocking, use_prio ? prio_mid : prio_least));
+    YDST_CUDA(cudaStreamCreateWithPriority(&p->sH, cudaStreamNonBlocking, prio_least));
     YDST_CUDA(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    YDST_CUDA(cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
     p->h_payload = new int[md];
     *out = p;
     YDST_API_END
@@ -467,6 +478,7 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
         if (p->sA) cudaStreamSynchronize(p->sA);
         if (p->sB) cudaStreamSynchronize(p->sB);
         if (p->sC) cudaStreamSynchronize(p->sC);
+        if (p->sH) cudaStreamSynchronize(p->sH);
         for (auto& sl : p->slot) {
             cudaFree(sl.frame_dev); cudaFree(sl.tlwh); cudaFree(sl.confd); cudaFree(sl.cls); cudaFree(sl.feat);
             cudaFree(sl.orig_dev); cudaFree(sl.raw_dev);
@@ -478,7 +490,9 @@ int ydst_pipeline_destroy(ydst_pipeline* p) {
         if (p->sA) cudaStreamDestroy(p->sA);
         if (p->sB) cudaStreamDestroy(p->sB);
         if (p->sC) cudaStreamDestroy(p->sC);
+        if (p->sH) cudaStreamDestroy(p->sH);
         if (p->ev_in) cudaEventDestroy(p->ev_in);
+        if (p->ev_h2d) cudaEventDestroy(p->ev_h2d);
         delete[] p->h_payload;
         delete p;
     }
@@ -496,6 +510,11 @@ static bool pipeline_can_submit(const ydst_pipeline* p) {
 static void pipeline_launch_detector(ydst_pipeline* p, ydst_pipeline::Slot& sl) {
     Detector& det = *p->det;
     const int md = det.nms_.max_det;
+    if (p->h2d_pending) {                                              // host frames of this slot were uploaded on their own stream
+        YDST_CUDA(cudaEventRecord(p->ev_h2d, p->sH));
+        YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_h2d, 0));
+        p->h2d_pending = false;
+    }
     det.forward_u8(sl.frame_dev, nullptr, p->sA);
     // one set of NMS launches for the whole micro-batch (image = blockIdx.y), then one D2H per result array
     det.nms_.run(det.pred, det.rows, det.fields, p->conf, p->iou, p->sA, sl.n_frames);
@@ -536,7 +555,12 @@ static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_i
         YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
     }
     const cudaMemcpyKind kind = frame_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    if (plain) {
+    if (plain && frame_is_host) {
+        // a free slot has no reader left (its last collect waited for the ReID half), so the upload need not queue behind the
+        // detector forward of the previous slot on sA: it runs on the copy stream, under that forward
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, p->sH));
+        p->h2d_pending = true;
+    } else if (plain) {
         YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, p->sA));
     } else {
         // ingest on the device: (BGR ->) RGB copy of the captured frame for the ReID crops, cv2-exact resize to the network size

@@ -575,6 +575,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             pix = ((long long)img * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
         }
         grid_dep_wait();
+        // (measured: staging the rows in shared memory for coalesced 16-byte stores is SLOWER here than the thread-per-row stores --
+        //  +5..10 % per layer from the two extra barriers per group -- unlike the TMA bulk stores of the halo kernel)
         epilogue_tile<kMish>(p, tmem_base, warp, n0, pix, valid, s_sb, bar_tmem);
     }
     tcgen05_fence_before();

@@ -120,96 +120,309 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
     __shared__ __align__(1024) uint8_t sm[2 * 8192 + 2 * 4096];
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ uint32_t tmem_slot;
+    __shared__ long long rowpix[128];
+    __shared__ float s_sb[128];
     const int t = threadIdx.x, warp = t >> 5;
     const uint32_t sA_hi = smem_u32(sm), sA_lo = sA_hi + 8192u, sB_hi = sA_lo + 8192u, sB_lo = sB_hi + 4096u;
     const uint32_t bar = smem_u32(&bar_storage);
     const uint32_t tmem_cols = cout <= 32 ? 32u : 64u;
+    // ---- once per CTA: barrier, TMEM, weights, scale/bias (the CTA then strides over the 128-pixel tiles) ----
     if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), tmem_cols); tmem_relinquish(); }
-    // ---- this thread's im2col row ----
-    const long long total = (long long)N * H * W;
-    const long long idx = (long long)blockIdx.x * 128 + t;
-    const bool live = idx < total;
-    int xo = 0, yo = 0, n = 0;
-    if (live) { xo = (int)(idx % W); const long long q = idx / W; yo = (int)(q % H); n = (int)(q / H); }
-    float v[32];
-#pragma unroll
-    for (int k = 27; k < 32; ++k) v[k] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int y = yo - 1 + r, x = xo - 1 + s;
-            const bool ok = live && y >= 0 && y < H && x >= 0 && x < W;
-            const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
-        }
-    const uint32_t sw = (uint32_t)((t >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 hi4, lo4;
-        __half2* hh = reinterpret_cast<__half2*>(&hi4);
-        __half2* ll = reinterpret_cast<__half2*>(&lo4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float a = v[c * 8 + 2 * q], b = v[c * 8 + 2 * q + 1];
-            const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-            hh[q] = __halves2half2(ah, bh);
-            ll[q] = __halves2half2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
-        }
-        const uint32_t off = (uint32_t)t * 64u + ((((uint32_t)c) ^ sw) << 4);
-        *reinterpret_cast<uint4*>(sm + off) = hi4;
-        *reinterpret_cast<uint4*>(sm + 8192 + off) = lo4;
-    }
-    // ---- weights: [2][cout][32] fp16 -> two swizzled [cout][64 B] tiles ----
+    // weights: [2][cout][32] fp16 -> two swizzled [cout][64 B] tiles
     for (int e = t; e < 2 * cout * 4; e += 128) {
         const int part = e / (cout * 4), rem = e - part * cout * 4;
         const int row = rem >> 2, c = rem & 3;
         const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(w_hilo + ((size_t)part * cout + row) * 32 + c * 8));
         *reinterpret_cast<uint4*>(sm + 16384 + part * 4096 + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = w4;
     }
-    fence_proxy_async();                                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    if (t < cout) { s_sb[t] = __ldg(scale + t); s_sb[64 + t] = __ldg(bias + t); }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    if (warp == 0 && elect_one()) {
-        const uint32_t idesc = make_idesc_f16(128, cout);
-        const uint32_t a_of[3] = {sA_hi, sA_lo, sA_hi}, b_of[3] = {sB_hi, sB_hi, sB_lo};
+    const uint32_t idesc = make_idesc_f16(128, cout);
+    const long long total = (long long)N * H * W;
+    const long long ntiles = (total + 127) / 128;
+    const uint32_t sw = (uint32_t)((t >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3
+    const int chunks = cout >> 3;
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1u) {
+        // ---- this thread's im2col row ----
+        const long long idx = tile * 128 + t;
+        const bool live = idx < total;
+        int xo = 0, yo = 0, n = 0;
+        if (live) { xo = (int)(idx % W); const long long q = idx / W; yo = (int)(q % H); n = (int)(q / H); }
+        float v[32];
 #pragma unroll
-        for (int pr = 0; pr < 3; ++pr)
+        for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-                umma_f16(tmem_base, make_smem_desc(a_of[pr] + 32u * k, 64), make_smem_desc(b_of[pr] + 32u * k, 64), idesc, (uint32_t)((pr | k) != 0));
-        umma_commit(bar);
-    }
-    mbar_wait(bar, 0);
-    tcgen05_fence_after();
-    const long long pix = ((long long)n * out.Hp() + yo + 1) * out.Wp() + xo + 1;
-    __half* op = out.base + pix * out.ctot + out.coff;
-    for (int ch = 0; ch < (cout >> 4); ++ch) {
-        __syncwarp();
-        uint32_t acc[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), acc);
-        tcgen05_wait_ld();
-        if (!live) continue;
-        uint4 w0, w1;
-        __half2* g0 = reinterpret_cast<__half2*>(&w0);
-        __half2* g1 = reinterpret_cast<__half2*>(&w1);
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int c0 = ch * 16 + 2 * q;
-            const float a = apply_act(fmaf(__uint_as_float(acc[2 * q]), __ldg(scale + c0), __ldg(bias + c0)), act);
-            const float b = apply_act(fmaf(__uint_as_float(acc[2 * q + 1]), __ldg(scale + c0 + 1), __ldg(bias + c0 + 1)), act);
-            (q < 4 ? g0[q] : g1[q - 4]) = __floats2half2_rn(a, b);
+            for (int s = 0; s < 3; ++s) {
+                const int y = yo - 1 + r, x = xo - 1 + s;
+                const bool ok = live && y >= 0 && y < H && x >= 0 && x < W;
+                const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+            }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 hi4, lo4;
+            __half2* hh = reinterpret_cast<__half2*>(&hi4);
+            __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = v[c * 8 + 2 * q], b = v[c * 8 + 2 * q + 1];
+                const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+                hh[q] = __halves2half2(ah, bh);
+                ll[q] = __halves2half2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
+            }
+            const uint32_t off = (uint32_t)t * 64u + ((((uint32_t)c) ^ sw) << 4);
+            *reinterpret_cast<uint4*>(sm + off) = hi4;
+            *reinterpret_cast<uint4*>(sm + 8192 + off) = lo4;
         }
-        reinterpret_cast<uint4*>(op + ch * 16)[0] = w0;
-        reinterpret_cast<uint4*>(op + ch * 16)[1] = w1;
+        rowpix[t] = live ? ((long long)n * out.Hp() + yo + 1) * out.Wp() + xo + 1 : -1;
+        fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+        if (warp == 0 && elect_one()) {
+            const uint32_t a_of[3] = {sA_hi, sA_lo, sA_hi}, b_of[3] = {sB_hi, sB_hi, sB_lo};
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_f16(tmem_base, make_smem_desc(a_of[pr] + 32u * k, 64), make_smem_desc(b_of[pr] + 32u * k, 64), idesc, (uint32_t)((pr | k) != 0));
+            umma_commit(bar);
+        }
+        mbar_wait(bar, parity);
+        tcgen05_fence_after();
+        // Epilogue through shared memory: a thread owns one output pixel (TMEM lane), but a thread-per-row global store touches 32
+        // cache lines per warp instruction.  The fp16 rows go to a swizzled [128][128 B] tile over the dead im2col tiles, and the
+        // CTA then writes them out 16 bytes per thread with 8 (cout = 64) or 4 (cout = 32) consecutive threads per pixel.
+        {
+            uint4* rbase = reinterpret_cast<uint4*>(sm + (size_t)t * 128u);
+            const int x7 = t & 7;
+            for (int ch = 0; ch < (cout >> 4); ++ch) {
+                __syncwarp();
+                uint32_t acc[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 16), acc);
+                tcgen05_wait_ld();
+                uint4 w0, w1;
+                __half2* g0 = reinterpret_cast<__half2*>(&w0);
+                __half2* g1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c0 = ch * 16 + 2 * q;
+                    const float a = apply_act(fmaf(__uint_as_float(acc[2 * q]), s_sb[c0], s_sb[64 + c0]), act);
+                    const float b = apply_act(fmaf(__uint_as_float(acc[2 * q + 1]), s_sb[c0 + 1], s_sb[64 + c0 + 1]), act);
+                    (q < 4 ? g0[q] : g1[q - 4]) = __floats2half2_rn(a, b);
+                }
+                rbase[(2 * ch) ^ x7] = w0;
+                rbase[(2 * ch + 1) ^ x7] = w1;
+            }
+        }
+        tcgen05_fence_before();                            // the accumulator has been read: the next tile's MMAs may overwrite it
+        __syncthreads();
+        for (int item = t; item < 128 * chunks; item += 128) {
+            const int row = item / chunks, c = item - row * chunks;
+            const long long pix = rowpix[row];
+            if (pix < 0) continue;
+            const uint4 v4 = *reinterpret_cast<const uint4*>(sm + (size_t)row * 128u + (size_t)((c ^ (row & 7)) << 4));
+            *reinterpret_cast<uint4*>(out.base + pix * out.ctot + out.coff + c * 8) = v4;
+        }
+        __syncthreads();                                   // the staging tile is the next im2col tile
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+__device__ __forceinline__ uint4* act_ptr_w(const Act& a, int n, int y, int x, int c);
+// First layer + MaxPool2d(3, 2, 1) in one kernel (the ReID stem, deep_sort/deep/model.py:47-53): the full-resolution activation
+// (128x64x64 fp16 per crop, 1 MB) never goes to HBM.  A CTA owns a 4 x 16 tile of POOLED pixels: it stages the 11 x 35 x 3 input
+// patch, builds the im2col rows of the 9 x 33 convolution outputs the tile's windows cover (three 128-row MMA tiles, hi/lo split as
+// above), rounds them to fp16 into a swizzled staging tile and takes the 3x3 / stride-2 maxima from there.  The results are
+// bit-identical to conv_first_tc_kernel followed by maxpool_kernel (max commutes with the monotone fp16 rounding).
+static constexpr int kPoolTH = 4, kPoolTW = 16, kConvRH = 2 * kPoolTH + 1, kConvRW = 2 * kPoolTW + 1;      // 9 x 33 conv outputs
+static constexpr int kPatchH = kConvRH + 2, kPatchW = kConvRW + 2;                                       // 11 x 35 input pixels
+static constexpr int kStemPoolSmem = 3 * 16384 + 8192 + ((kPatchH * kPatchW * 3 * 4 + 15) & ~15) + 128 * 4 + 64 + 1024;
+__global__ void __launch_bounds__(128) conv_first_pool_kernel(const float* __restrict__ in, int N, int H, int W, const __half* __restrict__ w_hilo,
+                                                              const float* __restrict__ scale, const float* __restrict__ bias, int cout, int act,
+                                                              Act out) {
+    extern __shared__ uint8_t sm_raw[];
+    uint8_t* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+    const uint32_t sm_u = smem_u32(sm);
+    uint8_t* sB = sm + 3 * 16384;                                          // hi tile, lo tile (4 KB each)
+    float* patch = reinterpret_cast<float*>(sB + 8192);
+    float* s_sb = patch + ((kPatchH * kPatchW * 3 + 3) & ~3);               // scale[64], bias[64]
+    unsigned long long* bar_ptr = reinterpret_cast<unsigned long long*>(s_sb + 128);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + 1);
+    const uint32_t bar = smem_u32(bar_ptr);
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 256u); tmem_relinquish(); }
+    const int tiles_x = out.W / kPoolTW, tiles_y = out.H / kPoolTH;
+    int b = blockIdx.x;
+    const int tx = b % tiles_x; b /= tiles_x;
+    const int ty = b % tiles_y;
+    const int n = b / tiles_y;
+    const int py0 = ty * kPoolTH, px0 = tx * kPoolTW;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;                         // first conv output of the region (may be -1: pool padding)
+    // ---- input patch (zero outside the image = the convolution's padding) ----
+    for (int e = t; e < kPatchH * kPatchW * 3; e += 128) {
+        const int r = e / (kPatchW * 3), rem = e - r * (kPatchW * 3);
+        const int c = rem / 3, ch = rem - c * 3;
+        const int y = cy0 - 1 + r, x = cx0 - 1 + c;
+        patch[e] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(in + (((long long)n * H + y) * W + x) * 3 + ch) : 0.f;
+    }
+    if (t < cout) { s_sb[t] = __ldg(scale + t); s_sb[64 + t] = __ldg(bias + t); }
+    // ---- weights: [2][cout][32] fp16 -> two swizzled [cout][64 B] tiles ----
+    for (int e = t; e < 2 * cout * 4; e += 128) {
+        const int part = e / (cout * 4), rem = e - part * cout * 4;
+        const int row = rem >> 2, c = rem & 3;
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(w_hilo + ((size_t)part * cout + row) * 32 + c * 8));
+        *reinterpret_cast<uint4*>(sB + part * 4096 + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = w4;
+    }
+    __syncthreads();
+    // ---- im2col rows of the three MMA tiles (row = conv output r = i*128 + t of the 9 x 33 region) ----
+    const uint32_t sw = (uint32_t)((t >> 1) & 3);
+    bool inside[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int r = i * 128 + t;
+        const bool live = r < kConvRH * kConvRW;
+        const int ry = live ? r / kConvRW : 0, rx = live ? r - ry * kConvRW : 0;
+        inside[i] = live && cy0 + ry >= 0 && cy0 + ry < H && cx0 + rx >= 0 && cx0 + rx < W;
+        float v[32];
+#pragma unroll
+        for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+            for (int ds = 0; ds < 3; ++ds) {
+                const float* px = patch + ((ry + dr) * kPatchW + rx + ds) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(dr * 3 + ds) * 3 + c] = live ? px[c] : 0.f;
+            }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 hi4, lo4;
+            __half2* hh = reinterpret_cast<__half2*>(&hi4);
+            __half2* ll = reinterpret_cast<__half2*>(&lo4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a = v[c * 8 + 2 * q], bb = v[c * 8 + 2 * q + 1];
+                const __half ah = __float2half_rn(a), bh = __float2half_rn(bb);
+                hh[q] = __halves2half2(ah, bh);
+                ll[q] = __halves2half2(__float2half_rn(a - __half2float(ah)), __float2half_rn(bb - __half2float(bh)));
+            }
+            const uint32_t off = (uint32_t)i * 16384u + (uint32_t)t * 64u + ((((uint32_t)c) ^ sw) << 4);
+            *reinterpret_cast<uint4*>(sm + off) = hi4;
+            *reinterpret_cast<uint4*>(sm + 8192 + off) = lo4;
+        }
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = make_idesc_f16(128, cout);
+        const uint32_t bh = sm_u + 3 * 16384, bl = bh + 4096;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint32_t ah = sm_u + (uint32_t)i * 16384u, al = ah + 8192u;
+            const uint32_t a_of[3] = {ah, al, ah}, b_of[3] = {bh, bh, bl};
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_f16(tmem_base + (uint32_t)(i * 64), make_smem_desc(a_of[pr] + 32u * k, 64), make_smem_desc(b_of[pr] + 32u * k, 64), idesc,
+                             (uint32_t)((pr | k) != 0));
+        }
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tcgen05_fence_after();
+    // ---- BN + activation, fp16, into the staging tile [384 rows][128 B] over the (now dead) im2col tiles ----
+    const uint32_t ninf2 = 0xFC00FC00u;
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        const int r = i * 128 + t;
+        uint4* rbase = reinterpret_cast<uint4*>(sm + (size_t)r * 128u);
+        const int x7 = r & 7;
+        for (int ch = 0; ch < (cout >> 4); ++ch) {
+            __syncwarp();
+            uint32_t acc[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * 64 + ch * 16), acc);
+            tcgen05_wait_ld();
+            uint4 w0 = make_uint4(ninf2, ninf2, ninf2, ninf2), w1 = w0;
+            if (inside[i]) {
+                __half2* g0 = reinterpret_cast<__half2*>(&w0);
+                __half2* g1 = reinterpret_cast<__half2*>(&w1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c0 = ch * 16 + 2 * q;
+                    const float a = apply_act(fmaf(__uint_as_float(acc[2 * q]), s_sb[c0], s_sb[64 + c0]), act);
+                    const float bb = apply_act(fmaf(__uint_as_float(acc[2 * q + 1]), s_sb[c0 + 1], s_sb[64 + c0 + 1]), act);
+                    (q < 4 ? g0[q] : g1[q - 4]) = __floats2half2_rn(a, bb);
+                }
+            }
+            rbase[(2 * ch) ^ x7] = w0;
+            rbase[(2 * ch + 1) ^ x7] = w1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256u); }
+    // ---- 3x3 / stride-2 maxima: 64 pooled pixels x (cout / 8) 16-byte channel chunks ----
+    const int chunks = cout >> 3;
+    for (int item = t; item < kPoolTH * kPoolTW * chunks; item += 128) {
+        const int pp = item / chunks, ch = item - pp * chunks;
+        const int ply = pp / kPoolTW, plx = pp - ply * kPoolTW;
+        const __half2 ninf = __float2half2_rn(-INFINITY);
+        __half2 m[4] = {ninf, ninf, ninf, ninf};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int r = (2 * ply + dy) * kConvRW + 2 * plx + dx;
+                const uint4 v = *reinterpret_cast<const uint4*>(sm + (size_t)r * 128u + (size_t)((ch ^ (r & 7)) << 4));
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], h[q]);
+            }
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ho[q] = m[q];
+        const int py = py0 + ply, px = px0 + plx;
+        if (py < out.H && px < out.W) *act_ptr_w(out, n, py, px, ch * 8) = o;
+    }
+}
+
+bool conv_first_pool_supported(int H, int W, int cout, int stride, int act, const __half* w_hilo) {
+    // (read per plan, not cached: the parity test builds one extractor with the fused stem and one without)
+    // opt-in: measured SLOWER than the two kernels (ReID forward of 416 crops 2.48 ms against 2.35 ms) -- three 128-row tiles per
+    // CTA need 192 TMEM columns, so only two 128-thread CTAs fit an SM and their serial phases are latency-bound
+    const bool on = (getenv("YDST_STEM_FUSED") && atoi(getenv("YDST_STEM_FUSED")) != 0) &&
+                    !(getenv("YDST_STEM_TC") && atoi(getenv("YDST_STEM_TC")) == 0);
+    return on && w_hilo && stride == 1 && cout == 64 && act != ACT_MISH && H % (2 * kPoolTH) == 0 && W % (2 * kPoolTW) == 0;
+}
+void launch_conv_first_pool(const float* in, int N, int H, int W, const __half* w_hilo, const float* scale, const float* bias, int cout, int act,
+                            const Act& out, cudaStream_t st) {
+    YDST_CHECK(conv_first_pool_supported(H, W, cout, 1, act, w_hilo) && out.H == H / 2 && out.W == W / 2 && out.C == cout,
+               "fused first layer + maxpool: unsupported shape");
+    static bool attr = false;
+    if (!attr) {
+        YDST_CUDA(cudaFuncSetAttribute(conv_first_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemPoolSmem));
+        attr = true;
+    }
+    const long long ctas = (long long)N * (out.H / kPoolTH) * (out.W / kPoolTW);
+    conv_first_pool_kernel<<<(unsigned)ctas, 128, kStemPoolSmem, st>>>(in, N, H, W, w_hilo, scale, bias, cout, act, out);
+    YDST_CUDA(cudaGetLastError());
 }
 
 void launch_conv_first(const float* in, int N, int H, int W, const float* w, const __half* w_hilo, const float* scale, const float* bias,
@@ -219,7 +432,10 @@ void launch_conv_first(const float* in, int N, int H, int W, const float* w, con
     static const bool tc_ok = !(getenv("YDST_STEM_TC") && atoi(getenv("YDST_STEM_TC")) == 0);
     if (tc_ok && w_hilo && stride == 1 && cout % 16 == 0 && act != ACT_MISH) {
         const long long tot = (long long)N * H * W;
-        conv_first_tc_kernel<<<cdiv(tot, 128), 128, 0, st>>>(in, N, H, W, w_hilo, scale, bias, cout, act, out);
+        // persistent: 8 CTAs per SM (26 KB of shared memory, <= 64 TMEM columns each) stride over the tiles
+        static const int per_sm = getenv("YDST_STEM_CTAS_PER_SM") ? atoi(getenv("YDST_STEM_CTAS_PER_SM")) : 8;
+        const long long ntiles = cdiv(tot, 128), cap = 148LL * (per_sm > 0 ? per_sm : 8);
+        conv_first_tc_kernel<<<(unsigned)(per_sm > 0 ? std::min(ntiles, cap) : ntiles), 128, 0, st>>>(in, N, H, W, w_hilo, scale, bias, cout, act, out);
         YDST_CUDA(cudaGetLastError());
         return;
     }

@@ -19,6 +19,10 @@ void launch_conv_first(const float* in, int N, int H, int W, const float* w, con
 // MaxPool2d(k, s, padding=(k-1)//2) with -inf padding; zero_pad_br=1 reproduces the reference's
 // ZeroPad2d((0,1,0,1)) + MaxPool2d(2,1) (yolo3/models/models.py:58-64).
 void launch_maxpool(const Act& in, const Act& out, int k, int stride, int zero_pad_br, cudaStream_t st);
+// first layer (Cin = 3, stride 1, tensor cores) fused with MaxPool2d(3, 2, 1): the ReID stem without the full-resolution round trip
+bool conv_first_pool_supported(int H, int W, int cout, int stride, int act, const __half* w_hilo);
+void launch_conv_first_pool(const float* in, int N, int H, int W, const __half* w_hilo, const float* scale, const float* bias, int cout, int act,
+                            const Act& out, cudaStream_t st);
 // nearest-neighbour upsample by `s` (UpsampleExpand, yolo3/models/models.py:118-133)
 void launch_upsample(const Act& in, const Act& out, int s, cudaStream_t st);
 // out = a + b (unfused shortcut, yolo3/models/models.py:304-306)

@@ -174,6 +174,9 @@ static void run_ops(const Plan& plan, cudaStream_t st) {
             case OP_CONV_FIRST:
                 launch_conv_first(op.fsrc, op.out.N, op.i0, op.i1, op.w->w32, op.w->w_hilo, op.w->scale, op.w->bias, op.w->cout, op.i2, op.i3, op.out, st);
                 break;
+            case OP_CONV_FIRST_POOL:
+                launch_conv_first_pool(op.fsrc, op.out.N, op.i0, op.i1, op.w->w_hilo, op.w->scale, op.w->bias, op.w->cout, op.i3, op.out, st);
+                break;
             case OP_MAXPOOL: launch_maxpool(op.a, op.out, op.i0, op.i1, op.i2, st); break;
             case OP_UPSAMPLE: launch_upsample(op.a, op.out, op.i0, st); break;
             case OP_ADD: launch_add(op.a, op.b, op.out, st); break;
@@ -473,14 +476,20 @@ const Plan& Reid::plan_for(int m) {
     Plan plan;
     auto view = [&](int i) { Act a = bufs_[i]; a.N = m; return a; };
     size_t wi = 0;
-    {
-        Op op; op.kind = OP_CONV_FIRST; op.fsrc = in_f32_; op.out = view(0); op.w = weights_[wi++].get();
+    Act x = view(1);                                                    // stage-1 buffer A
+    if (conv_first_pool_supported(128, 64, weights_[wi]->cout, 1, ACT_RELU, weights_[wi]->w_hilo)) {
+        // conv 3->64 + BN + ReLU + MaxPool2d(3,2,1) in one kernel: the 128x64x64 activation stays on chip
+        Op op; op.kind = OP_CONV_FIRST_POOL; op.fsrc = in_f32_; op.out = x; op.w = weights_[wi++].get();
         op.i0 = 128; op.i1 = 64; op.i2 = 1; op.i3 = ACT_RELU;
         plan.ops.push_back(op);
         plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
-    }
-    Act x = view(1);                                                    // stage-1 buffer A
-    {
+    } else {
+        {
+            Op op; op.kind = OP_CONV_FIRST; op.fsrc = in_f32_; op.out = view(0); op.w = weights_[wi++].get();
+            op.i0 = 128; op.i1 = 64; op.i2 = 1; op.i3 = ACT_RELU;
+            plan.ops.push_back(op);
+            plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
+        }
         Op op; op.kind = OP_MAXPOOL; op.a = view(0); op.out = x; op.i0 = 3; op.i1 = 2; op.i2 = 0;
         plan.ops.push_back(op);
     }

@@ -20,7 +20,7 @@ struct ConvWeights {
     float* bias = nullptr;
 };
 
-enum OpKind { OP_CONV_TC, OP_CONV_FIRST, OP_MAXPOOL, OP_UPSAMPLE, OP_ADD, OP_COPY, OP_YOLO, OP_AVGPOOL_L2 };
+enum OpKind { OP_CONV_TC, OP_CONV_FIRST, OP_MAXPOOL, OP_UPSAMPLE, OP_ADD, OP_COPY, OP_YOLO, OP_AVGPOOL_L2, OP_CONV_FIRST_POOL };
 
 struct Op {
     OpKind kind;
