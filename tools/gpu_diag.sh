@@ -1,9 +1,9 @@
 #!/bin/bash
-# final artefacts of a round: bench line (with per-op dump), planner choices, in-kernel timeline
 mkdir -p gpurun_out
-timeout 900 python bench.py --dump-ops gpurun_out/ops.csv > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -2 gpurun_out/bench.err; cut -c1-200 gpurun_out/bench.json
-YDST_DEBUG_PLAN=1 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "^conv_plan" | awk '!seen[$0]++' > gpurun_out/plan.txt
-YDST_CONV_TRACE=2 timeout 600 python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2> gpurun_out/timeline.txt > /dev/null
-grep "^conv_timeline" gpurun_out/timeline.txt | tail -130 > gpurun_out/timeline_tail.txt
-wc -l gpurun_out/plan.txt gpurun_out/timeline_tail.txt gpurun_out/ops.csv
+timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_detector.py -x -q 2>&1 | tail -4
+run() { name=$1; extra=$2; shift; shift
+  env "$@" timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline $extra --dump-ops gpurun_out/ops_$name.csv > gpurun_out/bench_$name.json 2> gpurun_out/plan_$name.txt
+  python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/plan_$name.txt
+}
+run narrow "" YDST_X=0

@@ -1064,11 +1064,14 @@ static int env_int(const char* name, int dflt) {
 ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets) {
     const int kSms = 148;
     const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 600.0, kClkPerUs = 1900.0;
-    const bool tma_store_ok = cout16 % 64 == 0;
+    // narrow layers (cout < 64) may use a 64-wide N tile: the weight rows past cout are zero-filled by TMA and the store is clipped
+    // at the end of the layer's channel slice, so they too get the eight-warp TMA-store epilogue instead of thread-per-row stores
+    const bool tma_store_ok = cout16 % 64 == 0 || cout16 < 64;
     ConvTiling best{};
     best.model_us = 1e30;
     int bn_cap = 32;
     while (bn_cap < cout16 && bn_cap < 256) bn_cap <<= 1;
+    if (cout16 < 64 && env_int("YDST_NARROW_TMA", 1)) bn_cap = 64;
     const int force_bn = env_int("YDST_FORCE_BN", 0);          // tuning aid: restrict the N tile (when the layer allows it)
     // measured on B200: neither M pairs nor the persistent tile loop beat the plain one-tile-per-CTA launch yet
     // (1163 / 1198 / 1226 frames/s for pair+persistent / persistent / neither at micro-batch 4), so both are opt-in
@@ -1246,7 +1249,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             p.b_resident = t.b_resident;
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
-            p.store_tma = (!out_f32 && p.cout % 64 == 0 && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
+            p.store_tma = (!out_f32 && (p.cout % 64 == 0 || p.cout < 64) && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
             if (t.persistent && !p.store_tma) t.smem_bytes -= 64 * 1024;   // no staging area needed
             const int K = R * S * in.C;
             if (R == 3) {
@@ -1269,12 +1272,13 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 encode(&L.tmB, w_packed, 3, bdims, bstrides, bbox, 128);
             }
             if (p.store_tma) {
-                cuuint64_t dims[2] = {(cuuint64_t)out.ctot, (cuuint64_t)p.P_total};
+                // the logical width ends with this layer's channel slice: a 64-column box never spills into a neighbouring slice
+                cuuint64_t dims[2] = {(cuuint64_t)(out.coff + cout_real), (cuuint64_t)p.P_total};
                 cuuint64_t strides[1] = {(cuuint64_t)out.ctot * 2};
                 cuuint32_t box[2] = {64u, (cuuint32_t)kBlockM};
                 encode(&L.tmA[1], out.base, 2, dims, strides, box, 128);
                 if (res_mode) {                                  // the wide epilogue fetches the residual tile by TMA
-                    cuuint64_t rdims[2] = {(cuuint64_t)res->ctot, (cuuint64_t)p.P_total};
+                    cuuint64_t rdims[2] = {(cuuint64_t)(res->coff + cout_real), (cuuint64_t)p.P_total};
                     cuuint64_t rstrides[1] = {(cuuint64_t)res->ctot * 2};
                     encode(&L.tmA[2], res->base, 2, rdims, rstrides, box, 128);
                 }
