@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
     __shared__ __align__(8) unsigned long long bar_storage;
     __shared__ uint32_t tmem_slot;
     __shared__ long long rowpix[128];
-    __shared__ float s_sb[128];
+    __shared__ __align__(16) float s_sb[128];
     const int t = threadIdx.x, warp = t >> 5;
     const uint32_t sA_hi = smem_u32(sm), sA_lo = sA_hi + 8192u, sB_hi = sA_lo + 8192u, sB_lo = sB_hi + 4096u;
     const uint32_t bar = smem_u32(&bar_storage);
@@ -157,15 +157,19 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
 #pragma unroll
         for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        {
+            const bool rok[3] = {live && yo >= 1, live, live && yo + 1 < H}, cok[3] = {xo >= 1, true, xo + 1 < W};
+            const float* ctr = in + (((long long)n * H + yo) * W + xo) * 3;      // never dereferenced unless the tap is inside
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int y = yo - 1 + r, x = xo - 1 + s;
-                const bool ok = live && y >= 0 && y < H && x >= 0 && x < W;
-                const float* px = in + (((long long)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 3;
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
-            }
+                for (int s = 0; s < 3; ++s) {
+                    const bool ok = rok[r] && cok[s];
+                    const float* px = ctr + ((r - 1) * W + (s - 1)) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = ok ? __ldg(px + c) : 0.f;
+                }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint4 hi4, lo4;
@@ -174,9 +178,10 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float a = v[c * 8 + 2 * q], b = v[c * 8 + 2 * q + 1];
-                const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-                hh[q] = __halves2half2(ah, bh);
-                ll[q] = __halves2half2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
+                const __half2 h2 = __floats2half2_rn(a, b);
+                const float2 back = __half22float2(h2);
+                hh[q] = h2;
+                ll[q] = __floats2half2_rn(a - back.x, b - back.y);
             }
             const uint32_t off = (uint32_t)t * 64u + ((((uint32_t)c) ^ sw) << 4);
             *reinterpret_cast<uint4*>(sm + off) = hi4;
@@ -212,12 +217,32 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
                 uint4 w0, w1;
                 __half2* g0 = reinterpret_cast<__half2*>(&w0);
                 __half2* g1 = reinterpret_cast<__half2*>(&w1);
+                // (the kernel is instruction-bound: the activation kind is tested once per 16 columns, not once per element)
+                float o[16];
+                const float4* sc4 = reinterpret_cast<const float4*>(s_sb + ch * 16);
+                const float4* bi4 = reinterpret_cast<const float4*>(s_sb + 64 + ch * 16);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c0 = ch * 16 + 2 * q;
-                    const float a = apply_act(fmaf(__uint_as_float(acc[2 * q]), s_sb[c0], s_sb[64 + c0]), act);
-                    const float b = apply_act(fmaf(__uint_as_float(acc[2 * q + 1]), s_sb[c0 + 1], s_sb[64 + c0 + 1]), act);
-                    (q < 4 ? g0[q] : g1[q - 4]) = __floats2half2_rn(a, b);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 sc = sc4[q], bi = bi4[q];
+                    o[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), sc.x, bi.x);
+                    o[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), sc.y, bi.y);
+                    o[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), sc.z, bi.z);
+                    o[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), sc.w, bi.w);
+                }
+                if (act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+                } else if (act == ACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.1f * o[j]);          // == (x > 0 ? x : 0.1x) for every finite x
+                } else if (act != ACT_LINEAR) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = apply_act(o[j], act);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    g0[q] = __floats2half2_rn(o[2 * q], o[2 * q + 1]);
+                    g1[q] = __floats2half2_rn(o[8 + 2 * q], o[8 + 2 * q + 1]);
                 }
                 rbase[(2 * ch) ^ x7] = w0;
                 rbase[(2 * ch + 1) ^ x7] = w1;
@@ -578,38 +603,43 @@ void launch_unpack_f32(const float* padded, int cstride, int N, int H, int W, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid: x over (gx * nf) elements of one grid row, y = (n * na + a) * gy + y  -> one integer division per thread
+// block = 32 lanes over the fields of a box x 8 grid cells; grid.x over the cells of one grid row, grid.y = (n * na + a) * gy + y.
+// The kernel is instruction-bound (12 M outputs of a 76x76 head at micro-batch 8), so the index arithmetic is per block row,
+// not per element: no division by the field count, three fields per thread, 32 consecutive floats per warp load and store.
 __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ head, int cstride, int N, int gy, int gx, int na, float aw0,
                                                           float ah0, float aw1, float ah1, float aw2, float ah2, int nc, float s0, float s1,
                                                           float* __restrict__ pred, int rows_total, int row0) {
     const int nf = nc + 5;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= gx * nf) return;
-    const int x = e / nf, k = e - x * nf;
+    const int x = blockIdx.x * 8 + threadIdx.y;
+    if (x >= gx) return;
     int t = blockIdx.y;
     const int y = t % gy; t /= gy;                         // block-uniform
     const int a = t % na;
     const int n = t / na;
     const long long pix = ((long long)n * (gy + 2) + y + 1) * (gx + 2) + x + 1;
-    const float v = __ldg(head + pix * cstride + a * nf + k);
-    const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2), ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
-    float o;
-    // (sigmoid(t)+grid) * scale, exp(t) * (anchor/scale) * scale with scale = (H/gy, W/gx, H/gy, W/gx):
-    // x and w use the HEIGHT stride, y and h the WIDTH stride -- the reference's own quirk.
-    if (k == 0) o = (1.f / (1.f + expf(-v)) + (float)x) * s0;
-    else if (k == 1) o = (1.f / (1.f + expf(-v)) + (float)y) * s1;
-    else if (k == 2) o = (expf(v) * (aw / s0)) * s0;
-    else if (k == 3) o = (expf(v) * (ah / s1)) * s1;
-    else o = 1.f / (1.f + expf(-v));
+    const float* src = head + pix * cstride + a * nf;
     const long long row = row0 + ((long long)a * gy + y) * gx + x;
-    pred[((long long)n * rows_total + row) * nf + k] = o;
+    float* dst = pred + ((long long)n * rows_total + row) * nf;
+    const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2), ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
+    for (int k = threadIdx.x; k < nf; k += 32) {
+        const float v = __ldg(src + k);
+        float o;
+        // (sigmoid(t)+grid) * scale, exp(t) * (anchor/scale) * scale with scale = (H/gy, W/gx, H/gy, W/gx):
+        // x and w use the HEIGHT stride, y and h the WIDTH stride -- the reference's own quirk.
+        if (k == 0) o = (1.f / (1.f + expf(-v)) + (float)x) * s0;
+        else if (k == 1) o = (1.f / (1.f + expf(-v)) + (float)y) * s1;
+        else if (k == 2) o = (expf(v) * (aw / s0)) * s0;
+        else if (k == 3) o = (expf(v) * (ah / s1)) * s1;
+        else o = 1.f / (1.f + expf(-v));
+        dst[k] = o;
+    }
 }
 void launch_yolo_decode(const float* head, int cstride, int N, int gy, int gx, int na, const float* anchors_wh, int nc, int img_h,
                         int img_w, float* pred, int rows_total, int row0, cudaStream_t st) {
     YDST_CHECK(na == 3, "yolo layer with %d anchors (3 supported)", na);
     const float s0 = (float)((double)img_h / gy), s1 = (float)((double)img_w / gx);
-    const dim3 grid(cdiv((long long)gx * (nc + 5), 256), (unsigned)(N * na * gy));
-    yolo_decode_kernel<<<grid, 256, 0, st>>>(head, cstride, N, gy, gx, na, anchors_wh[0], anchors_wh[1], anchors_wh[2], anchors_wh[3],
+    const dim3 grid((unsigned)cdiv(gx, 8), (unsigned)(N * na * gy));
+    yolo_decode_kernel<<<grid, dim3(32, 8), 0, st>>>(head, cstride, N, gy, gx, na, anchors_wh[0], anchors_wh[1], anchors_wh[2], anchors_wh[3],
                                              anchors_wh[4], anchors_wh[5], nc, s0, s1, pred, rows_total, row0);
     YDST_CUDA(cudaGetLastError());
 }
