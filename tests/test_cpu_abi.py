@@ -79,3 +79,13 @@ def test_planner_choices(cdll, shape):
     if m_tiles < 148:                      # batch-1 detector layers: do not leave most of the 148 SMs idle
         assert ctas >= 16
     assert cdll.ydst_conv_tiling(1, 19, 19, 48, 64, 3, None, None, None, None, None) != 0     # Cin must be a multiple of 64
+
+
+def test_planner_micro_batch_choices(cdll):
+    """Choices the measurements in DESIGN.md 4.1 (7-8) rest on: a layer with more tiles than SMs but fewer than two per SM is
+    planned as ONE resident wave of 128 x 256 tiles (two CTAs per SM), and a narrow layer takes a 64-wide N tile so that it gets
+    the TMA-store epilogue."""
+    bn, ks, occ, ctas, _ = tiling(cdll, 4, 76, 76, 128, 256, 3)          # 191 tiles on 148 SMs
+    assert (bn, ks, occ, ctas) == (256, 1, 2, 191)
+    bn, ks, occ, ctas, _ = tiling(cdll, 8, 304, 304, 64, 32, 1)          # cout 32: zero-filled weight rows, clipped store
+    assert (bn, ks) == (64, 1) and ctas == (8 * 306 * 306 + 127) // 128
