@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_detector.py tests/test_gpu_reid.py -x -q 2>&1 | tail -4
-run() { name=$1; extra=$2; shift; shift
-  env "$@" timeout 600 python bench.py --steps 256 --warmup 16 --no-cpu-baseline $extra --dump-ops gpurun_out/ops_$name.csv > gpurun_out/bench_$name.json 2> gpurun_out/plan_$name.txt
-  python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'])" || tail -3 gpurun_out/plan_$name.txt
-}
-run decode "" YDST_X=0
+timeout 900 python -m pytest tests/test_gpu_reid.py tests/test_gpu_pipeline.py -x -q 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_bucket.json 2> gpurun_out/bench_bucket.err; tail -2 gpurun_out/bench_bucket.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_bucket.json')); print(d['value'], d['e2e']['value'], d['stage_ms'])"
+timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 3 | cut -c1-160

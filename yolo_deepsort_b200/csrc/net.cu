@@ -534,7 +534,11 @@ void Reid::forward(const float* x_dev, int m, float* feat_out, cudaStream_t st) 
     YDST_CHECK(m <= max_batch, "ReID batch %d exceeds max_batch %d", m, max_batch);
     if (x_dev != in_f32_)
         YDST_CUDA(cudaMemcpyAsync(in_f32_, x_dev, (size_t)m * 128 * 64 * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    run_plan(plan_for(m), st);
+    // plans (tensor maps, tilings, CUDA graph) are cached per crop count; a stream's count changes by a few from one micro-batch
+    // to the next, so large counts are rounded up to a multiple of 16: the padding rows hold zeros or stale crops, every crop is
+    // computed independently of its neighbours, and only the first m feature rows are handed out
+    const int m_plan = m <= 32 ? m : std::min(max_batch, (m + 15) & ~15);
+    run_plan(plan_for(m_plan), st);
     if (feat_out && feat_out != feat_)
         YDST_CUDA(cudaMemcpyAsync(feat_out, feat_, (size_t)m * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
