@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit: parity tests, bench line (both arms), ncu launch list of a bench run, ncu --set full of representative convs.
-# usage: bash tools/gpu_round.sh [tests] [bench] [launches] [full]        (outputs under gpurun_out/, kept < 64 MiB)
+# usage: bash tools/gpu_round.sh [tests] [bench] [launches] [full] [artefacts]        (outputs under gpurun_out/, kept < 64 MiB)
 mkdir -p gpurun_out
 what="${@:-tests bench launches full}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
@@ -30,5 +30,12 @@ full)
       python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_c.log 2>&1
   for f in 76 19 mb; do ncu -i gpurun_out/prof_full_$f.ncu-rep --page raw --csv > gpurun_out/prof_full_$f.csv 2>/dev/null; done
   ls -la gpurun_out/*.ncu-rep ;;
+artefacts)
+  # per-op CUDA-event table, the planner's choices and the in-kernel timelines that tools/summarise_profiles.py files under profiles/
+  timeout 600 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --dump-ops gpurun_out/ops.csv > /dev/null 2> gpurun_out/ops.err
+  YDST_DEBUG_PLAN=1 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "^conv_plan" | awk '!seen[$0]++' > gpurun_out/plan.txt
+  YDST_CONV_TRACE=2 timeout 600 python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2> gpurun_out/timeline.txt > /dev/null
+  grep "^conv_timeline" gpurun_out/timeline.txt | tail -130 > gpurun_out/timeline_tail.txt
+  wc -l gpurun_out/plan.txt gpurun_out/timeline_tail.txt gpurun_out/ops.csv ;;
 esac
 done
