@@ -340,7 +340,7 @@ def run_ours(args):
            "dtype": "fp16", "data": "synthetic",
            "config": {"workload": f"{CFG} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream per GPU, {args.micro_batch} consecutive frames per forward",
                       "dets_per_frame": round(float(np.mean(n_dets)), 1), "track_rows_per_frame": round(float(np.mean(n_trk)), 1),
-                      "clip": f"{W.N_SCENES} synthetic scenes x {W.HOLD} frames, cycled; random-init weights, calibrated BN/head bias",
+                      "clip": f"{W.N_SCENES} synthetic scenes held per workload.SCHEDULE ({W.CLIP_LEN}-frame cycle); seeded random weights, BN statistics and head rows calibrated with decision margins",
                       "tracker": W.TRACKER_KW, "detector": W.DETECT_KW,
                       "l2": "per-step working set (124 MB fp16 weights + ~340 MB activations) exceeds the 126 MB L2; no explicit flush",
                       "pipelining": f"look-ahead: the detector half of the next {args.micro_batch} frame(s) of the stream (one forward) overlaps the "
@@ -418,7 +418,7 @@ def run_reference(args):
            "data": "synthetic",
            "config": {"workload": f"{CFG} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream, batch 1, CPU",
                       "dets_per_frame": b["dets_per_frame"], "tracker": W.TRACKER_KW, "detector": W.DETECT_KW,
-                      "clip": f"{W.N_SCENES} synthetic scenes x {W.HOLD} frames, cycled; same frames and weights as the CUDA arm"},
+                      "clip": f"{W.N_SCENES} synthetic scenes held per workload.SCHEDULE ({W.CLIP_LEN}-frame cycle); same frames and weights as the CUDA arm"},
            "cpu_baseline": b,
            "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}

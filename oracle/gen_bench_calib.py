@@ -17,53 +17,37 @@ import workload as W
 from . import darknet_ref as D
 from . import reid_ref as R
 from .cv_resize_ref import crops_to_batch
-from .synth import frame_to_input
+from .synth import calibrate_heads, frame_to_input
 
 
-def calibrate_darknet(cfg_name, size, seed=0, target=56, n_pool=12):
+def calibrate_darknet(cfg_name, size, seed=0, want_dets=50):
     blocks = D.parse_cfg(os.path.join(W.ROOT, "config", cfg_name + ".cfg"))
     defs = blocks[1:]
     ws = W.shape_heads(W.init_darknet_weights(defs, seed))
-    pool = list(range(n_pool))
-    frames = W.scenes(size, size, seeds=pool)
+    frames = W.scenes(size, size)
     xs = torch.cat([frame_to_input(f) for f in frames], 0)
-    D.forward(blocks, ws, xs, calibrate_bn=True)                    # BN statistics over the whole candidate pool
-    obj = W.head_rows()[0]
-    heads = [i for i, e in enumerate(ws) if "b" in e]
-    _, outs = D.forward(blocks, ws, xs, return_layers=True)
-    per_frame = []
-    for n in range(len(frames)):
-        per = [outs[li - 1][n][obj].reshape(-1).numpy() for li, b in enumerate(defs) if b["type"] == "yolo"]
-        per_frame.append(np.concatenate(per))
-    # provisional cut: the median candidate scene passes `target` rows; keep the N_SCENES scenes closest to the target,
-    # then place the final cut in the widest logit gap of the kept scenes' pooled logits
-    cut0 = float(np.median([np.sort(l)[::-1][target] for l in per_frame]))
-    counts = np.array([int((l > cut0).sum()) for l in per_frame])
-    keep = np.argsort(np.abs(counts - target), kind="stable")[:W.N_SCENES]
-    keep = np.sort(keep)
-    print("candidate counts", counts.tolist(), "-> scenes", keep.tolist())
-    frames = [frames[i] for i in keep]
-    per_frame = [per_frame[i] for i in keep]
-    pooled = np.sort(np.concatenate(per_frame))[::-1]
-    want = target * len(frames)
-    lo, hi = int(want * 0.93), int(want * 1.07)
-    gaps = pooled[lo - 1:hi - 1] - pooled[lo:hi]
-    k = int(np.argmax(gaps)) + lo
-    cut = 0.5 * (float(pooled[k - 1]) + float(pooled[k]))
-    for hi_ in heads:
-        ws[hi_]["b"][obj] = np.float32(-cut)                         # sigmoid(t - cut) > 0.5  <=>  t > cut
-    out = {"scene_seeds": np.asarray([pool[i] for i in keep], np.int32)}
+    D.forward(blocks, ws, xs, calibrate_bn=True)                    # BN statistics over all scenes of the clip
+    # objectness rows with threshold / score-order / NMS margins on every scene (so that fp16-vs-fp32 rounding noise cannot
+    # flip a decision and the track ids of both arms are comparable bit for bit)
+    ws, info = calibrate_heads(blocks, ws, frames, want_dets=want_dets, conf_thres=W.DETECT_KW["thres"],
+                               iou_thres=W.DETECT_KW["nms_thres"], verbose=True)
+    box_obj = W.head_box_obj_rows()
+    out = {}
     for i, e in enumerate(ws):
         if "bn" in e:
             out[f"bn_mean_{i}"], out[f"bn_var_{i}"] = e["bn"][2].astype(np.float32), e["bn"][3].astype(np.float32)
         else:
             out[f"head_bias_{i}"] = e["b"].astype(np.float32)
+            out[f"head_rows_w_{i}"] = e["w"][box_obj, :, 0, 0].astype(np.float32)
     dets = [D.detect(blocks, ws, f, (size, size), W.DETECT_KW["thres"], W.DETECT_KW["nms_thres"]) for f in frames]
-    info = dict(cut=cut, gap=float(gaps.max()), n_pass=[int((l > cut).sum()) for l in per_frame],
-                n_dets=[0 if d is None else len(d) for d in dets], logit_std=float(np.std(pooled)))
     print(cfg_name, size, info)
     os.makedirs(W.DATA, exist_ok=True)
     np.savez_compressed(os.path.join(W.DATA, f"{cfg_name}_{size}_seed{seed}.npz"), **out)
+    # the fixture must reproduce the calibrated model through workload.py alone
+    _, ws2 = W.darknet_workload(cfg_name, size, seed)
+    for a, b in zip(ws, ws2):
+        for k in a:
+            assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k])) if k == "bn" else np.array_equal(a[k], b[k]), k
     return frames, dets
 
 
@@ -109,7 +93,8 @@ def main():
     size = int(sys.argv[2]) if len(sys.argv) > 2 else 608
     torch.set_num_threads(os.cpu_count())
     frames, dets = calibrate_darknet(cfg, size)
-    calibrate_reid(frames, dets)
+    if cfg == "yolov3":                      # one ReID fixture: the headline config's crops
+        calibrate_reid(frames, dets)
 
 
 if __name__ == "__main__":

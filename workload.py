@@ -19,7 +19,15 @@ DATA = os.path.join(ROOT, "bench_data")
 # the reference demo's parameters (video_deepsort.py:18-45)
 TRACKER_KW = dict(max_dist=0.3, min_confidence=1, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
 DETECT_KW = dict(thres=0.5, nms_thres=0.4, class_mask=[0, 2, 4])
-N_SCENES, HOLD = 4, 8          # the clip cycles A x8, B x8, C x8, D x8, A x8 ... (tracks go missing and are re-identified)
+# The clip: (scene, frames it is held) in order, cycled.  Held scenes because a seeded random-weight detector is not a detector:
+# moving the rectangles by ONE pixel leaves 0 of 47 detections in place, so on a moving clip no track would ever
+# be confirmed.  The schedule exercises confirmation (holds >= n_init), tentative tracks that die (holds of 2), re-identification
+# of tracks that were missing for fewer than max_age frames (scenes 0, 1, 2 come back) and deletion by age.
+SCHEDULE = ((0, 8), (1, 8), (0, 6), (2, 2), (3, 8), (1, 6), (4, 8), (5, 2), (2, 8), (6, 8))
+N_SCENES = 1 + max(s for s, _ in SCHEDULE)
+CLIP_LEN = sum(n for _, n in SCHEDULE)                     # 64 frames per cycle
+_CLIP = [s for s, n in SCHEDULE for _ in range(n)]
+BETA_MEAN = 1.5                # BN beta ~ N(1.5, 0.1): the ordered edge of the random BN + leaky stack (see init_darknet_weights)
 
 
 def make_scene(h, w, seed, n_rect=50):
@@ -40,17 +48,16 @@ def make_scene(h, w, seed, n_rect=50):
     return img
 
 
-def scenes(h=608, w=608, seeds=None, cfg_name="yolov3", seed=0):
-    """The clip's distinct scenes.  Their seeds were chosen by the calibration (the N_SCENES candidates on which the
-    calibrated detector fires closest to 50 times) and are stored in the fixture."""
+def scenes(h=608, w=608, seeds=None):
+    """The clip's distinct scenes (the detector heads in bench_data/ were calibrated on exactly these)."""
     if seeds is None:
-        seeds = np.load(os.path.join(DATA, f"{cfg_name}_{h}_seed{seed}.npz"))["scene_seeds"].tolist()
+        seeds = range(N_SCENES)
     return [make_scene(h, w, int(s)) for s in seeds]
 
 
 def clip_index(t):
     """Which scene frame `t` of the endless clip shows."""
-    return (t // HOLD) % N_SCENES
+    return _CLIP[t % CLIP_LEN]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -74,7 +81,10 @@ def _channels(module_defs):
 
 
 def init_darknet_weights(module_defs, seed=0):
-    """One dict per conv block in cfg order: {'w': (Cout,Cin,k,k), 'bn': [gamma,beta,mean,var] | 'b': bias}."""
+    """One dict per conv block in cfg order: {'w': (Cout,Cin,k,k), 'bn': [gamma,beta,mean,var] | 'b': bias}.
+    BN beta ~ N(BETA_MEAN, 0.1): with beta = 0 a randomly initialised BN + leaky-ReLU stack is in the chaotic phase (mean-field
+    perturbation gain 1.34 per layer -- rounding noise doubles every ~2.4 layers, which no trained network does); beta = 1.5
+    puts it at the ordered edge (gain ~1.02) without changing a FLOP, so fp16-vs-fp32 differences reflect the arithmetic."""
     g = torch.Generator().manual_seed(seed)
     ch = _channels(module_defs)
     ws = []
@@ -87,7 +97,7 @@ def init_darknet_weights(module_defs, seed=0):
         e = {"w": w.numpy().copy()}
         if int(d["batch_normalize"]):
             gamma = 1.0 + 0.1 * torch.randn(cout, generator=g)
-            beta = 0.1 * torch.randn(cout, generator=g)
+            beta = BETA_MEAN + 0.1 * torch.randn(cout, generator=g)
             e["bn"] = [gamma.numpy().copy(), beta.numpy().copy(), np.zeros(cout, np.float32), np.ones(cout, np.float32)]
         else:
             e["b"] = np.zeros(cout, np.float32)
@@ -103,6 +113,11 @@ def head_rows(nc=80, na=3):
     return obj, cls0, other, wh
 
 
+def head_box_obj_rows(nc=80, na=3):
+    """tx, ty, tw, th and objectness rows of the three anchors (the rows the margin calibration refits)."""
+    return [a * (nc + 5) + k for a in range(na) for k in range(5)]
+
+
 def shape_heads(ws):
     """Deterministic head shaping (before calibration): class 0 wins everywhere, box sizes stay tame."""
     obj, cls0, other, wh = head_rows()
@@ -110,7 +125,7 @@ def shape_heads(ws):
         if "b" not in e:
             continue
         e["w"][other] *= 0.05
-        e["w"][cls0] *= 0.05
+        e["w"][cls0] *= 0.002              # (almost) constant class confidence: score order == objectness order
         e["w"][wh] *= 0.25
         e["b"][:] = 0
         e["b"][cls0] = 8.0
@@ -119,13 +134,17 @@ def shape_heads(ws):
 
 
 def apply_calibration(ws, calib):
-    """calib: npz with bn_mean_<i>, bn_var_<i> per BN conv i and head_bias_<i> per head conv i (conv index in cfg order)."""
+    """calib: npz with bn_mean_<i>, bn_var_<i> per BN conv i; head_bias_<i> and head_rows_w_<i> (the box and objectness rows
+    of the three anchors, refitted with decision margins on the clip's scenes: oracle/synth.py fit_head_margins) per head
+    conv i (cfg order)."""
+    rows = head_box_obj_rows()
     for i, e in enumerate(ws):
         if "bn" in e:
             e["bn"][2] = calib[f"bn_mean_{i}"].astype(np.float32)
             e["bn"][3] = calib[f"bn_var_{i}"].astype(np.float32)
         else:
             e["b"] = calib[f"head_bias_{i}"].astype(np.float32)
+            e["w"][rows, :, 0, 0] = calib[f"head_rows_w_{i}"].astype(np.float32)
     return ws
 
 
