@@ -699,13 +699,6 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         return true;
     };
 
-    // Register re-allocation (2 CTAs per SM cap every warp at 96 registers at launch): the two single-thread warps give most of
-    // theirs back, the eight epilogue warps -- which hold two 16-column accumulator blocks, scale/bias and residual -- take them.
-    // 256 * 112 + 64 * 40 = 31 232 <= 32 768 registers per CTA.
-    if constexpr (!kPers) {
-        if (warp >= kProdWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    }
     if (warp == kProdWarp) {
         if (elect_one()) {
             // ================= TMA producer =================
