@@ -213,6 +213,10 @@ int ydst_pipeline_submit_frame(ydst_pipeline* p, const uint8_t* frame, int heigh
                                void* stream);
 /* the ingest kernel alone: cv2.resize(src, (dst_w, dst_h), INTER_LINEAR) on uint8 HxWx3, optionally swapping R and B; synchronises */
 int ydst_resize_u8(const uint8_t* src_dev, int src_h, int src_w, uint8_t* dst_dev, int dst_h, int dst_w, int swap_rb, void* stream);
+/* Tracker inputs of the frame returned by the LAST _collect / _step: its m rows of tlwh boxes (m x 4), ReID features (m x 512,
+ * as handed to Tracker.update, deep_sort/deep_sort.py:55-60) and class ids, copied to the host.  Parity aid: lets a test feed
+ * the reference association with exactly what the CUDA association saw.  Valid until the next _submit / _collect. */
+int ydst_pipeline_last_inputs(ydst_pipeline* p, float* tlwh_host, float* feat_host, int32_t* cls_host, int cap_rows, int* m_host);
 int ydst_pipeline_in_flight(const ydst_pipeline* p);
 /* A detector handle created with batch B > 1 makes B the pipeline's MICRO-BATCH: B consecutive frames of the stream share one
  * Darknet forward (and one ReID forward), which amortises the per-layer launch latency that bounds a batch-1 frame; up to 2B

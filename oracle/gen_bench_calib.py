@@ -20,7 +20,13 @@ from .cv_resize_ref import crops_to_batch
 from .synth import calibrate_heads, frame_to_input
 
 
-def calibrate_darknet(cfg_name, size, seed=0, want_dets=50):
+# detections per frame the heads are calibrated for: ~50 on the headline config; yolov4's 110-conv Mish stack carries ~2.5x the
+# rounding noise at its heads, and the noise of a fitted row grows like n^1.5, so its score ladder only holds for ~30 rungs
+WANT_DETS = {"yolov3": 50, "yolov4": 30}
+
+
+def calibrate_darknet(cfg_name, size, seed=0, want_dets=None):
+    want_dets = WANT_DETS.get(cfg_name, 50) if want_dets is None else want_dets
     blocks = D.parse_cfg(os.path.join(W.ROOT, "config", cfg_name + ".cfg"))
     defs = blocks[1:]
     ws = W.shape_heads(W.init_darknet_weights(defs, seed))

@@ -57,23 +57,28 @@ def _bn(x, sd, p):
                         False, 0.1, 1e-5)
 
 
-def net_forward(sd, x):
-    """Net.forward, reid=True (deep_sort/deep/model.py:81-92).  x: (m,3,128,64) float32."""
+def net_forward(sd, x, half_storage=False):
+    """Net.forward, reid=True (deep_sort/deep/model.py:81-92).  x: (m,3,128,64) float32.
+    half_storage=True is NOT a reference mode (the Extractor never halves): it rounds the conv weights and every materialised
+    activation to fp16 while the arithmetic stays fp32 -- the rounding points of fp16 tensor-core convolutions with a fused fp32
+    epilogue -- and is used only to measure the storage-format floor of the feature error (tests/test_precision_floor.py).  The
+    stem conv (Cin = 3) keeps fp32 operands, as the CUDA path's hi/lo split does."""
     sd = {k: torch.as_tensor(v) for k, v in sd.items()}
+    h = (lambda t: t.half().float()) if half_storage else (lambda t: t)
     x = torch.as_tensor(x).clone()        # ATen-allocated (aligned) storage: oneDNN's fp32 result depends on it
     with torch.no_grad():
         x = F.conv2d(x, sd["conv.0.weight"], sd["conv.0.bias"], 1, 1)
-        x = F.relu(_bn(x, sd, "conv.1"))
+        x = h(F.relu(_bn(x, sd, "conv.1")))
         x = F.max_pool2d(x, 3, 2, 1)
         for li, cin, cout, down in STAGES:
             for bi in range(2):
                 p = f"layer{li}.{bi}"
                 s = 2 if (bi == 0 and down) else 1
-                y = F.relu(_bn(F.conv2d(x, sd[p + ".conv1.weight"], None, s, 1), sd, p + ".bn1"))
-                y = _bn(F.conv2d(y, sd[p + ".conv2.weight"], None, 1, 1), sd, p + ".bn2")
+                y = h(F.relu(_bn(F.conv2d(x, h(sd[p + ".conv1.weight"]), None, s, 1), sd, p + ".bn1")))
+                y = _bn(F.conv2d(y, h(sd[p + ".conv2.weight"]), None, 1, 1), sd, p + ".bn2")
                 if bi == 0 and down:
-                    x = _bn(F.conv2d(x, sd[p + ".downsample.0.weight"], None, 2, 0), sd, p + ".downsample.1")
-                x = F.relu(x.add(y))
+                    x = h(_bn(F.conv2d(x, h(sd[p + ".downsample.0.weight"]), None, 2, 0), sd, p + ".downsample.1"))
+                x = h(F.relu(x.add(y)))
         x = F.avg_pool2d(x, (8, 4), 1)
         x = x.view(x.size(0), -1)
         x = x.div(x.norm(p=2, dim=1, keepdim=True))

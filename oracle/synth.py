@@ -165,6 +165,7 @@ def fit_head_margins(blocks, ws, frames, target=50, conf_thres=0.5, iou_thres=0.
     # A fitted row's rounding noise grows with the number of outputs it has to prescribe, so the nine rows share the
     # detections round-robin, each contributing its own upper tail on that frame.
     picks, site_boxes = [], []
+    quota = [float(feats[h][0].shape[1]) ** (1.0 / 3.0) for h in range(len(heads))]    # n ~ C^(1/3) balances n^1.5 / sqrt(C)
     lim = max_box * min(H_img, W_img)
     for fi in range(nf):
         n_want = int(round(target * (1.0 + rng.uniform(-0.1, 0.1))))
@@ -176,7 +177,7 @@ def fit_head_margins(blocks, ws, frames, target=50, conf_thres=0.5, iou_thres=0.
             zz = z[fi, o0:o0 + ncell[h]]
             rk = np.empty(ncell[h])
             rk[np.argsort(-zz, kind="stable")] = np.arange(ncell[h])
-            prio[o0:o0 + ncell[h]] = (rk + 0.5) - 1e-3 * zz
+            prio[o0:o0 + ncell[h]] = (rk + 0.5) / quota[h] - 1e-3 * zz
             cy, cx = np.divmod(np.arange(ncell[h]), gx)
             nb_ = boxes[fi][o0:o0 + ncell[h]]
             bw = 2 * np.floor(0.5 * (nb_[:, 2] - nb_[:, 0])) + 1   # odd integer sizes next to the natural ones

@@ -46,7 +46,6 @@ def test_entry_script_flow_through_dropin_names(dropin_path, tmp_path):
     from oracle import darknet_ref as D
     from oracle.synth import darknet_weights, make_frame, reid_state_dict
     from test_gpu_pipeline import oracle_run
-    from util import IdBijection, match_boxes
     from deep_sort import DeepSort
     from yolo3.detect.video_detect import VideoDetector
     from yolo3.models import Darknet
@@ -61,7 +60,7 @@ def test_entry_script_flow_through_dropin_names(dropin_path, tmp_path):
     torch.save({"net_dict": sd, "acc": 0.0, "epoch": 0}, ckpt)          # deep_sort/deep/train.py:137-144 checkpoint layout
     with open(names, "w") as fh:
         fh.write("\n".join(f"c{i}" for i in range(80)) + "\n")
-    clip = [scenes[0]] * 4 + [scenes[1]] * 3
+    clip = [scenes[0]] * 9
     wr = cv2.VideoWriter(video, cv2.VideoWriter_fourcc(*"FFV1"), 25, (416, 416))
     for f in clip:
         wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
@@ -72,17 +71,15 @@ def test_entry_script_flow_through_dropin_names(dropin_path, tmp_path):
     model.load_darknet_weights(wpath)
     model.to("cuda:0")
     tracker = DeepSort(ckpt, min_confidence=1, use_cuda=True, nn_budget=30, n_init=3, max_iou_distance=0.7, max_dist=0.3, max_age=30)
-    video_detector = VideoDetector(model, names, thickness=2, skip_frames=1, thres=0.5, class_mask=[0, 2, 4], nms_thres=0.4,
+    video_detector = VideoDetector(model, names, thickness=2, skip_frames=2, thres=0.5, class_mask=[0, 2, 4], nms_thres=0.4,
                                    tracker=tracker, half=True)
-    ref_out, _ = oracle_run(blocks, ws, sd, clip)
-    ids = IdBijection()
+    # skip_frames=2 (video_deepsort.py:41): the detector + tracker run on every second frame, the rows are held in between
+    # (yolo3/detect/video_detect.py:132-157)
+    ref_steps, _ = oracle_run(blocks, ws, sd, clip[::2])
     n = 0
     for t, (image, detections, _) in enumerate(video_detector.detect(video, real_show=False, skip_secs=0, show_fps=False)):
-        ro = np.asarray(ref_out[t], np.int32).reshape(-1, 6)
-        got = np.asarray(detections, np.int32).reshape(-1, 6)
-        assert image.shape == (416, 416, 3) and got.shape == ro.shape, f"frame {t}"
-        p = match_boxes(got[:, :4], ro[:, :4])
-        assert np.abs(got[p, :4] - ro[:, :4]).max(initial=0) <= 2 and (got[p, 5] == ro[:, 5]).all()
-        ids.check(got[p, 4], ro[:, 4], f"frame {t}")
+        assert image.shape == (416, 416, 3), f"frame {t}"
+        np.testing.assert_array_equal(np.asarray(detections, np.int32).reshape(-1, 6), np.asarray(ref_steps[t // 2], np.int32).reshape(-1, 6),
+                                      err_msg=f"frame {t}: rows [x1,y1,x2,y2,id,cls] differ from the oracle")
         n += 1
     assert n == len(clip)

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, ROOT
-from util import DEV, match_boxes
+from util import DEV
 from yolo_deepsort_b200 import Darknet, soft_non_max_suppression
 from yolo_deepsort_b200._lib import check, lib, ptr, stream_ptr
 
@@ -120,16 +120,18 @@ def test_detections_match_golden(tiny):
     got = soft_non_max_suppression(pred, 0.5, 0.4)[0].cpu().numpy()
     ref = g["dets"]
     assert got.shape == ref.shape, f"{got.shape[0]} detections vs {ref.shape[0]} in the reference"
-    # order-free pairing: two detections whose fp32 scores are nearly tied may come out swapped (fp16 activations)
-    p = match_boxes(got[:, :4], ref[:, :4])
-    got = got[p]
+    # same rows in the same ORDER (no pairing): the calibrated heads keep the score ladder clear of fp16 rounding noise
     np.testing.assert_array_equal(got[:, 5], ref[:, 5])
-    rel = np.abs(got[:, :4] - ref[:, :4]) / np.maximum(np.abs(ref[:, :4]), 1.0)
-    swapped = int((p != np.arange(len(p))).sum())
-    print("detections: max rel box err %.3g, max score err %.3g, %d of %d rows out of score order" %
-          (rel.max(), np.abs(got[:, 4] - ref[:, 4]).max(), swapped, len(p)))
-    assert rel.max() < 1e-3 * 5            # see DESIGN.md: fp16 activations give ~2e-3 on 416-px coordinates
-    assert np.abs(got[:, 4] - ref[:, 4]).max() < 5e-3
+    centre = np.abs(0.5 * (got[:, :2] + got[:, 2:4]) - 0.5 * (ref[:, :2] + ref[:, 2:4])).max()
+    size = np.abs((got[:, 2:4] - got[:, :2]) - (ref[:, 2:4] - ref[:, :2])).max()
+    rel = np.abs(got[:, :4] - ref[:, :4]).max(1) / np.minimum(ref[:, 2] - ref[:, 0], ref[:, 3] - ref[:, 1])
+    print("detections: centre err %.3g px, size err %.3g px, max box err relative to the box size %.3g, max score err %.3g" %
+          (centre, size, rel.max(), np.abs(got[:, 4] - ref[:, 4]).max()))
+    # fp16 storage against the fp32 reference: the storage-format floor of this net is measured by tests/test_precision_floor.py
+    # (oracle with fp16 rounding points vs fp32 oracle: 0.13 px / 2.2e-3 of the box size); the CUDA path must stay within 1.5x of it
+    assert centre <= 1e-3 and size <= 0.25 and rel.max() < 4e-3
+    assert np.abs(got[:, 4] - ref[:, 4]).max() < 1e-2
+    assert np.array_equal(got[:, :4].astype(np.int64), ref[:, :4].astype(np.int64)), "integer box corners (crop rectangles) differ"
     own = soft_non_max_suppression(pred, 0.5, 0.4)[0][:, 4].cpu().numpy()
     assert (np.diff(own) <= 0).all(), "NMS output must be score-descending"
 

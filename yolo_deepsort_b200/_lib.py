@@ -74,6 +74,7 @@ SIGNATURES = {
     "ydst_pipeline_submit_frame": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ydst_resize_u8": (_I, [_P, _I, _I, _P, _I, _I, _I, _P]),
     "ydst_pipeline_collect": (_I, [_P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I)]),
+    "ydst_pipeline_last_inputs": (_I, [_P, _P, _P, _P, _I, ctypes.POINTER(_I)]),
     "ydst_pipeline_in_flight": (_I, [_P]),
     "ydst_pipeline_can_submit": (_I, [_P]),
     "ydst_pipeline_step": (_I, [_P, _P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I), _P]),

@@ -54,6 +54,7 @@ struct ydst_pipeline {
     cudaEvent_t ev_in = nullptr, ev_h2d = nullptr;
     bool h2d_pending = false;
     long long submitted = 0, collected = 0;
+    int last_slot = -1, last_sub = 0, last_m = 0;   // frame returned by the last collect (ydst_pipeline_last_inputs)
     long long fill = 0, drain = 0;    // slot sequence numbers: slot[fill % kSlots] accepts frames, slot[drain % kSlots] is collected from
     int* h_payload = nullptr;
 };
@@ -652,6 +653,7 @@ static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, fl
             }
         }
     }
+    p->last_slot = si; p->last_sub = sub; p->last_m = n_dets > 0 ? m : 0;
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
     const float* h_cls = sl.h_cls + (size_t)sub * md;
     for (int i = 0; i < m; ++i) p->h_payload[i] = (int)h_cls[i];
@@ -691,6 +693,22 @@ int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, floa
     YDST_CHECK(p && out_host && k_host, "null argument");
     const int rc = pipeline_collect(p, out_host, k_host, dets_host, n_dets_host);
     if (rc) return rc;
+    YDST_API_END
+}
+int ydst_pipeline_last_inputs(ydst_pipeline* p, float* tlwh_host, float* feat_host, int32_t* cls_host, int cap_rows, int* m_host) {
+    YDST_API_BEGIN
+    YDST_CHECK(p && m_host, "null argument");
+    YDST_CHECK(p->last_slot >= 0, "no frame has been collected yet");
+    const ydst_pipeline::Slot& sl = p->slot[p->last_slot];
+    const int m = p->last_m, md = p->det->nms_.max_det;
+    *m_host = m;
+    YDST_CHECK(m <= cap_rows, "buffer too small (%d rows, capacity %d)", m, cap_rows);
+    if (m > 0) {
+        YDST_CUDA(cudaStreamSynchronize(p->sB));
+        if (tlwh_host) YDST_CUDA(cudaMemcpy(tlwh_host, sl.tlwh + (size_t)p->last_sub * md * 4, sizeof(float) * 4 * m, cudaMemcpyDeviceToHost));
+        if (feat_host) YDST_CUDA(cudaMemcpy(feat_host, sl.feat + (size_t)sl.feat_off[p->last_sub] * 512, sizeof(float) * 512 * m, cudaMemcpyDeviceToHost));
+        if (cls_host) for (int i = 0; i < m; ++i) cls_host[i] = (int32_t)sl.h_cls[(size_t)p->last_sub * md + i];
+    }
     YDST_API_END
 }
 int ydst_pipeline_in_flight(const ydst_pipeline* p) { return p ? (int)(p->submitted - p->collected) : 0; }

@@ -67,6 +67,16 @@ class FramePipeline:
             return None, dets
         return (self._out[:k.value].copy() if k.value else []), dets
 
+    def last_inputs(self):
+        """(tlwh (m,4) f32, features (m,512) f32, class ids (m,) i32): what the tracker was handed for the frame returned by the
+        last collect()/step() (deep_sort/deep_sort.py:55-60).  Parity aid."""
+        cap = self._dets.shape[0]
+        tl, ft, cl = np.zeros((cap, 4), np.float32), np.zeros((cap, 512), np.float32), np.zeros(cap, np.int32)
+        m = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().ydst_pipeline_last_inputs(self._h, tl.ctypes.data, ft.ctypes.data, cl.ctypes.data, cap, ctypes.byref(m)))
+        return tl[:m.value].copy(), ft[:m.value].copy(), cl[:m.value].copy()
+
     def in_flight(self):
         return int(lib().ydst_pipeline_in_flight(self._h))
 
