@@ -1,19 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- end-to-end frames/s of the detect-and-track hot path on B200 (BASELINE.json configs[1]).
+"""bench.py -- end-to-end frames/s of the detect-and-track hot path on B200 (BASELINE.json configs[1]; --config for the others).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path (libydst, sm_100a)
+    python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path (libydst, sm_100a), yolov3 608 + DeepSort
+    python bench.py --config yolov4|reid|assoc [...]              BASELINE.json configs[2] / [3] / [4] (bench_side.py for the last two)
     python bench.py --impl reference [...]                        the reference's CPU path (oracle port) on the host cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      one video stream per GPU
 
-One "step" = one 608x608 frame through the whole per-frame path: u8 frame -> Darknet(yolov3) -> YOLO decode -> NMS ->
-box hand-off -> crop + cv2-exact resize -> ReID CNN -> Kalman predict -> cosine+Mahalanobis cost -> LSAP -> IoU cost ->
-LSAP -> Kalman update -> track bookkeeping -> (K,6) int32 rows on the host.  ~50 detections per frame (workload.py).
+One "step" = one 608x608 frame through the whole per-frame path: u8 frame -> Darknet -> YOLO decode -> NMS -> box hand-off ->
+crop + cv2-exact resize -> ReID CNN -> Kalman predict -> cosine+Mahalanobis cost -> LSAP -> IoU cost -> LSAP -> Kalman update ->
+track bookkeeping -> (K,6) int32 rows on the host.  ~50 detections per frame (workload.py).
 
-Timed legs (per rank; max over ranks; rank 0 prints ONE JSON line):
-  value  K steps with the frames already resident in HBM (ydst_pipeline_step_dev); CUDA events on the launching stream.
-  e2e    K steps through the reference-facing call with HOST frames (FramePipeline.step -> ydst_pipeline_step): the
-         1.1 MB host->device copy of each frame and the device->host read of the track rows are inside the timed region.
-Then (untimed): a per-op CUDA-event pass for the roofline object, and -- rank 0, N=1 only -- the CPU baseline.
+Timing.  A WINDOW is exactly K steps between two CUDA events on the launching stream, bracketed by a barrier and a device
+synchronize on both sides.  The stream is in steady state: the look-ahead pipeline stays primed across windows (the reference's
+reader thread keeps up to 128 decoded frames queued, yolo3/detect/video_detect.py:86), every window COLLECTS exactly K frames
+and submits as many new ones as free slots allow (K on average).  Windows are repeated until at least --min-seconds (2 s) have
+been timed, whatever K is; `value` and `ms_per_step` are the MEDIAN window (max over ranks per window), `windows` holds count,
+min and max.  Legs (rank 0 prints ONE JSON line):
+  value   frames already resident in HBM (FramePipeline.submit of CUDA tensors / collect).
+  e2e     HOST frames through the same reference-facing calls: the pinned 1.1 MB host->device copy of every frame and the
+          device->host read of its track rows are inside the window.
+  value_b1 the same stream at micro-batch 1 with one frame of look-ahead -- what VideoDetector.detect gets.
+  api     VideoDetector.detect() itself on an FFV1 clip of the workload (cv2 decode, colour conversion, overlay drawing on the
+          host included): the literal drop-in call of video_deepsort.py, wall clock.
+Then (untimed): a per-op CUDA-event pass for the roofline object, the parity gate (oracle/clip.py ParityCheck on the first
+frames of the clip) and -- rank 0, N=1 only -- the CPU baseline.
 """
 import argparse
 import ctypes
@@ -31,7 +41,7 @@ if ROOT not in sys.path:
 
 METRIC = "end-to-end FPS (608x608, ~50 dets/frame)"
 UNIT = "frames/s"
-CFG, SIZE = "yolov3", 608
+SIZE = 608
 MICRO_BATCH = 8          # consecutive frames per Darknet / ReID forward (3 slots in flight: 24 frames of look-ahead)
 
 
@@ -127,7 +137,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:                                    # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:
@@ -152,21 +162,82 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------------------
-def build_pipeline(device, micro_batch=1):
+def build_pipeline(cfg, device, micro_batch=1, model=None):
     import workload as W
     from yolo_deepsort_b200 import Darknet, DeepSort, FramePipeline
-    defs, ws = W.darknet_workload(CFG, SIZE)
-    model = Darknet(os.path.join(ROOT, "config", CFG + ".cfg"), img_size=(SIZE, SIZE))
-    model.set_weights(W.flatten_darknet(ws))
-    model.to(device)
+    if model is None:
+        defs, ws = W.darknet_workload(cfg, SIZE)
+        model = Darknet(os.path.join(ROOT, "config", cfg + ".cfg"), img_size=(SIZE, SIZE))
+        model.set_weights(W.flatten_darknet(ws))
+        model.to(device)
     ds = DeepSort(W.reid_workload(), use_cuda=True, device=str(device), **W.TRACKER_KW)
     pipe = FramePipeline(model, ds, W.DETECT_KW["thres"], W.DETECT_KW["nms_thres"], W.DETECT_KW["class_mask"], micro_batch=micro_batch)
     return model, ds, pipe
 
 
+class Stream:
+    """The endless clip fed through a FramePipeline in steady state: run(K) collects exactly K frames, keeping the pipeline full."""
+
+    def __init__(self, pipe, frames):
+        self.pipe, self.frames, self.t = pipe, frames, 0
+        self.n_dets, self.n_rows, self.d2h, self.in_flight = [], [], 0, []
+
+    def set_frames(self, frames):
+        self.frames = frames
+
+    def run(self, K):
+        import workload as W
+        pipe = self.pipe
+        for _ in range(K):
+            while pipe.can_submit():
+                pipe.submit(self.frames[W.clip_index(self.t)]); self.t += 1
+            self.in_flight.append(pipe.in_flight())
+            tracks, dets = pipe.collect()
+            self.n_dets.append(len(dets)); self.n_rows.append(0 if tracks is None else len(tracks))
+            self.d2h += (0 if tracks is None else np.asarray(tracks).nbytes) + dets.nbytes + 32      # rows + detections + counters
+
+
+def timed_windows(run_k, K, min_seconds, device, max_windows=2000):
+    """Repeat the K-step window until min_seconds have been timed.  Returns (per-window ms: max over ranks, this rank's own ms)."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wins, own, total = [], [], 0.0
+    while True:
+        barrier(device); torch.cuda.synchronize()
+        e0.record()
+        run_k(K)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        own.append(ms)
+        wins.append(max_over_ranks(ms, device))               # every rank sees the same list, so all stop after the same window
+        total += wins[-1]
+        if total >= min_seconds * 1e3 or len(wins) >= max_windows:
+            return wins, own
+
+
+def window_stats(wins, K, world):
+    med = float(np.median(wins))
+    return {"count": len(wins), "steps_per_window": K, "timed_s": round(float(np.sum(wins)) / 1e3, 3),
+            "ms_per_step_median": round(med / K, 4), "ms_per_step_min": round(float(np.min(wins)) / K, 4),
+            "ms_per_step_max": round(float(np.max(wins)) / K, 4)}, K * world / (med / 1e3), med / K
+
+
+def gather_floats(x, device=None):
+    """this rank's float from every rank, in rank order."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [float(x)]
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device if device is not None else "cpu")
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def profile_ops(pipe, frames_dev, t0, n=3):
     """Per-op CUDA-event timings of the layer graphs over `n` micro-batches (ydst_profile_begin/_end); eager launches with an
-    event pair around every op, so nothing overlaps and the durations are per kernel."""
+    event pair around every op, so nothing overlaps and the durations are per kernel.  Needs an empty pipeline."""
     import workload as W
     from yolo_deepsort_b200._lib import check, lib
     L = lib()
@@ -234,80 +305,133 @@ def ncu_traffic():
     return None
 
 
+def parity_leg(cfg, model, micro_batch, device, n_frames):
+    """The parity gate on the workload being timed (untimed): the first n_frames of the clip through a fresh pipeline at the
+    bench's micro-batch, every stage against the oracle (oracle/clip.py ParityCheck).  The one place besides the CPU baseline
+    where bench.py executes oracle/ -- as the checker."""
+    import torch
+    import workload as W
+    from oracle import darknet_ref as D
+    from oracle.clip import ParityCheck
+    torch.set_num_threads(os.cpu_count() or 1)
+    blocks = D.parse_cfg(os.path.join(ROOT, "config", cfg + ".cfg"))
+    _, ws = W.darknet_workload(cfg, SIZE)
+    scenes = W.scenes(SIZE, SIZE)
+    _, _, pipe = build_pipeline(cfg, device, micro_batch, model)
+    chk = ParityCheck(blocks, ws, W.reid_workload(), scenes, W.DETECT_KW["thres"], W.DETECT_KW["nms_thres"], W.DETECT_KW["class_mask"], W.TRACKER_KW)
+    dev = [torch.from_numpy(s).to(device) for s in scenes]
+    sub = col = 0
+    while col < n_frames:
+        while sub < n_frames and pipe.can_submit():
+            pipe.submit(dev[W.clip_index(sub)]); sub += 1
+        rows, dets = pipe.collect()
+        chk.frame(W.clip_index(col), dets, rows, pipe.last_inputs())
+        col += 1
+    out = chk.summary()
+    out["micro_batch"] = micro_batch
+    if chk.problems:
+        out["problems"] = chk.problems[:4]
+    return out
+
+
+def api_leg(cfg, model, device, n_frames=96):
+    """VideoDetector.detect() -- the call video_deepsort.py makes -- on an FFV1 (lossless) clip of the workload; wall clock over
+    the generator, host decode / colour conversion / overlay drawing included."""
+    import tempfile
+
+    import cv2
+    import torch
+    import workload as W
+    from yolo_deepsort_b200 import DeepSort, VideoDetector
+    scenes = W.scenes(SIZE, SIZE)
+    with tempfile.TemporaryDirectory() as td:
+        path, names = os.path.join(td, "clip.avi"), os.path.join(td, "coco.names")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 25, (SIZE, SIZE))
+        if not wr.isOpened():
+            return {"unavailable": "cv2 cannot write FFV1 here"}
+        for t in range(n_frames + 8):
+            wr.write(cv2.cvtColor(scenes[W.clip_index(t)], cv2.COLOR_RGB2BGR))
+        wr.release()
+        with open(names, "w") as fh:
+            fh.write("\n".join(f"c{i}" for i in range(80)) + "\n")
+        ds = DeepSort(W.reid_workload(), use_cuda=True, device=str(device), **W.TRACKER_KW)
+        vd = VideoDetector(model, names, thickness=2, skip_frames=-1, thres=W.DETECT_KW["thres"], class_mask=W.DETECT_KW["class_mask"],
+                           nms_thres=W.DETECT_KW["nms_thres"], tracker=ds, half=True)
+        n, t0 = 0, None
+        for image, rows, _ in vd.detect(path, show_fps=False):
+            n += 1
+            if n == 8:                                   # 8 warm-up frames
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": round((n - 8) / dt, 2), "unit": UNIT, "frames": n - 8,
+            "call": "VideoDetector(model, names, tracker=DeepSort(...), skip_frames=-1, half=True).detect(clip.avi)",
+            "note": "wall clock; batch 1, one frame of look-ahead; cv2 FFV1 decode + BGR->RGB + host overlay drawing per frame included"}
+
+
 def run_ours(args):
     import torch
     import workload as W
     from yolo_deepsort_b200._lib import lib
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (B200); there is no CPU fallback"
+    cfg = args.config
     local = env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     rank, world = dist_init("nccl")
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    K, Wm = args.steps, args.warmup
+    K, Wm = args.steps, max(args.warmup, 3)
+    B = args.micro_batch
 
-    model, ds, pipe = build_pipeline(device, args.micro_batch)
+    model, ds, pipe = build_pipeline(cfg, device, B)
     scenes = W.scenes(SIZE, SIZE)
     host = [torch.from_numpy(s).pin_memory() for s in scenes]            # pinned host frames (e2e leg)
     host_np = [h.numpy() for h in host]
     dev = [h.to(device) for h in host]                                   # resident frames (value leg)
     L = lib()
-    t = 0
-    n_dets, n_trk = [], []
-    for _ in range(max(Wm, 3)):
-        tracks, dets = pipe.step(dev[W.clip_index(t)]); t += 1
-    # ... and two full micro-batches through the look-ahead path, so that the full-batch plans and CUDA graphs exist before the clock starts
-    if args.micro_batch > 1:
-        sub = col = 0
-        while col < 2 * args.micro_batch:
-            while sub < 2 * args.micro_batch and pipe.can_submit():
-                pipe.submit(dev[W.clip_index(t)]); t += 1; sub += 1
-            pipe.collect(); col += 1
+    stream = Stream(pipe, dev)
+    # warm-up: W steps, at least three full micro-batches so that the full-batch plans and CUDA graphs exist and the pipeline is primed
+    stream.run(max(Wm, 3 * B))
     torch.cuda.synchronize()
+    stream.n_dets, stream.n_rows, stream.in_flight = [], [], []
 
     clocks = ClockSampler(local)
-    # ---------------- value leg: inputs resident in HBM ----------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(device); torch.cuda.synchronize()
     clocks.start()
+    # ---------------- value leg: inputs resident in HBM ----------------
     launches0 = L.ydst_launch_count()
-    # software-pipelined steady state (ydst_pipeline_submit/_collect): the detector half of frame t+1 is enqueued before the
-    # ReID + association half of frame t is collected; exactly K frames are submitted AND collected inside the timed region
-    e0.record()
-    sub = col = 0
-    while col < K:
-        while sub < K and pipe.can_submit():
-            pipe.submit(dev[W.clip_index(t)]); t += 1; sub += 1
-        tracks, dets = pipe.collect(); col += 1
-        n_dets.append(len(dets)); n_trk.append(0 if tracks is None else len(tracks))
-    e1.record()
-    torch.cuda.synchronize()
-    launches = L.ydst_launch_count() - launches0
-    barrier(device)
-    ms_value = e0.elapsed_time(e1)
-    # ---------------- e2e leg: host frames through the reference-facing call ----------------
-    d2h = 0
-    barrier(device); torch.cuda.synchronize()
-    e0.record()
-    sub = col = 0
-    while col < K:
-        while sub < K and pipe.can_submit():
-            pipe.submit(host_np[W.clip_index(t)]); t += 1; sub += 1       # pinned host frame -> async H2D inside the timed region
-        tracks, dets = pipe.collect(); col += 1
-        d2h += (0 if tracks is None else np.asarray(tracks).nbytes) + dets.nbytes + 32      # rows + detections + counters
-    e1.record()
-    torch.cuda.synchronize()
+    wins_v, own_v = timed_windows(stream.run, K, args.min_seconds, device)
+    launches = (L.ydst_launch_count() - launches0) / len(wins_v)
+    n_dets, n_rows, in_flight = list(stream.n_dets), list(stream.n_rows), list(stream.in_flight)
+    # ---------------- e2e leg: host frames through the same calls ----------------
+    stream.set_frames(host_np)
+    stream.run(3 * B)                                                    # the slots in flight now hold host-fed frames
+    stream.d2h = 0
+    n_before = len(stream.n_dets)
+    wins_e, own_e = timed_windows(stream.run, K, args.min_seconds, device)
+    d2h_per_step = stream.d2h // max(1, len(stream.n_dets) - n_before)
     clocks.stop()
-    barrier(device)
-    ms_e2e = e0.elapsed_time(e1)
+    pipe.drain()
+    torch.cuda.synchronize()
 
-    fps, worst_ms = aggregate_fps(K, ms_value, device)
-    fps_e2e, worst_e2e = aggregate_fps(K, ms_e2e, device)
+    wv, fps, ms_step = window_stats(wins_v, K, world)
+    we, fps_e2e, ms_step_e2e = window_stats(wins_e, K, world)
+    per_rank = gather_floats(float(np.median(own_v)) / K, device)
+
+    # ---------------- micro-batch 1 (what VideoDetector gets), same stream ----------------
+    b1 = None
+    if B != 1 and not args.no_b1:
+        _, _, pipe1 = build_pipeline(cfg, device, 1, model)
+        s1 = Stream(pipe1, dev)
+        s1.run(max(Wm, 8))
+        w1, _ = timed_windows(s1.run, K, min(args.min_seconds, 1.0), device)
+        pipe1.drain()
+        st1, fps1, ms1 = window_stats(w1, K, world)
+        b1 = {"value": round(fps1, 2), "unit": UNIT, "ms_per_step": round(ms1, 4), "latency_frames": round(float(np.mean(s1.in_flight)), 2),
+              "windows": st1}
 
     # ---------------- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), untimed pass ----------------
-    kind, layer, flops, nbytes, ms, nunits = profile_ops(pipe, dev, t)
-    t += nunits * args.micro_batch
-    nprof = nunits * args.micro_batch                                     # frames covered by the profile pass
+    kind, layer, flops, nbytes, ms, nunits = profile_ops(pipe, dev, stream.t)
+    nprof = nunits * B                                                    # frames covered by the profile pass
     if args.dump_ops and rank == 0:
         per = len(kind) // nunits                                       # ops per micro-batch (same op list every time)
         with open(args.dump_ops, "w") as fh:
@@ -326,34 +450,45 @@ def run_ours(args):
             "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); kernel timed inside a long step",
             "traffic": ncu_traffic(),
-            "launches_per_micro_batch": int(conv.sum() // nunits), "frames_per_micro_batch": args.micro_batch, "flops_per_step": conv_flops,
+            "launches_per_micro_batch": int(conv.sum() // nunits), "frames_per_micro_batch": B, "flops_per_step": conv_flops,
             "avg_launch_us": round(conv_ms * nprof * 1e3 / max(1, int(conv.sum())), 2),
             "conv_ms_per_step": round(conv_ms, 4), "all_graph_ops_ms_per_step": round(float(ms.sum()) / nprof, 4),
-            "share_of_step": round(conv_ms / (worst_ms / K), 4),
+            "share_of_step": round(conv_ms / ms_step, 4),
             "share_note": "GPU time of the conv launches per frame / wall time per frame; the three pipeline streams overlap, so the shares of all "
                           "kernels can add up to more than 1",
             "hbm_frac_conv": round(float(nbytes[conv].sum()) / nprof / (conv_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), 4) if conv_ms > 0 else None}
 
-    stages = stage_times(model, ds, dev, dets, device, args.micro_batch)
-    out = {"metric": METRIC, "value": round(fps, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-           "ms_per_step": round(worst_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    _, last_dets = pipe.step(dev[0])
+    stages = stage_times(model, ds, dev, last_dets, device, B)
+    lat = float(np.mean(in_flight)) if in_flight else 0.0
+    out = {"metric": METRIC, "value": round(fps, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "fp16", "data": "synthetic",
-           "config": {"workload": f"{CFG} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream per GPU, {args.micro_batch} consecutive frames per forward",
-                      "dets_per_frame": round(float(np.mean(n_dets)), 1), "track_rows_per_frame": round(float(np.mean(n_trk)), 1),
+           "config": {"workload": f"{cfg} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream per GPU, {B} consecutive frames per forward",
+                      "dets_per_frame": round(float(np.mean(n_dets)), 1), "track_rows_per_frame": round(float(np.mean(n_rows)), 1),
                       "clip": f"{W.N_SCENES} synthetic scenes held per workload.SCHEDULE ({W.CLIP_LEN}-frame cycle); seeded random weights, BN statistics and head rows calibrated with decision margins",
                       "tracker": W.TRACKER_KW, "detector": W.DETECT_KW,
                       "l2": "per-step working set (124 MB fp16 weights + ~340 MB activations) exceeds the 126 MB L2; no explicit flush",
-                      "pipelining": f"look-ahead: the detector half of the next {args.micro_batch} frame(s) of the stream (one forward) overlaps the "
-                                    f"crops+ReID of the previous {args.micro_batch} and the association of the {args.micro_batch} before on three CUDA streams; every one of the K frames is "
-                                    "submitted and collected inside the timed region; per-frame results identical to the synchronous step",
-                      "micro_batch": args.micro_batch,
+                      "pipelining": f"steady state: the look-ahead pipeline (detector of the next {B} frame(s) under the crops+ReID of the previous {B} and the "
+                                    f"association of the {B} before, three CUDA streams) stays primed across windows; every window collects exactly K frames and "
+                                    "submits as many as free slots allow; per-frame results identical to the synchronous step",
+                      "micro_batch": B, "latency_frames": round(lat, 2), "latency_ms": round(lat * ms_step, 3),
                       "parallelism": f"{world} independent streams (no data-path collective)"},
-           "e2e": {"value": round(fps_e2e, 2), "unit": UNIT, "ms_per_step": round(worst_e2e / K, 4),
-                   "h2d_bytes_per_step": int(SIZE * SIZE * 3), "d2h_bytes_per_step": int(d2h // K)},
-           "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "stage_ms": stages}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(args.cpu_frames, 2)
+           "windows": wv, "per_rank_ms_per_step": [round(x, 4) for x in per_rank],
+           "e2e": {"value": round(fps_e2e, 2), "unit": UNIT, "ms_per_step": round(ms_step_e2e, 4),
+                   "h2d_bytes_per_step": int(SIZE * SIZE * 3), "d2h_bytes_per_step": int(d2h_per_step), "windows": we},
+           "gpu_launches": int(round(launches)), "clocks": clocks.summary(), "roofline": roof, "stage_ms": stages}
+    if b1 is not None:
+        out["value_b1"] = b1
+    if rank == 0 and world == 1:
+        if not args.no_api:
+            try:
+                out["api"] = api_leg(cfg, model, device)
+            except Exception as e:                                   # noqa: BLE001  (the drop-in leg must never cost the bench line)
+                out["api"] = {"unavailable": repr(e)[:200]}
+        if not args.no_cpu_baseline:
+            out["parity"] = parity_leg(cfg, model, B, device, args.parity_frames)
+            out["cpu_baseline"] = cpu_reference(cfg, args.cpu_frames, 2)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -362,17 +497,17 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline leg: the reference's CPU path, restated in oracle/ (the only place bench.py executes
-# oracle code); same frames, same weights, all host threads
+# reference arm / cpu_baseline leg: the reference's CPU path, restated in oracle/ (with the parity leg the only places bench.py
+# executes oracle code); same frames, same weights, all host threads
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference(n_frames, n_warm):
+def cpu_reference(cfg, n_frames, n_warm):
     import torch
     import workload as W
     from oracle import darknet_ref as D, reid_ref as R, sort_ref as S
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    blocks = D.parse_cfg(os.path.join(ROOT, "config", CFG + ".cfg"))
-    _, ws = W.darknet_workload(CFG, SIZE)
+    blocks = D.parse_cfg(os.path.join(ROOT, "config", cfg + ".cfg"))
+    _, ws = W.darknet_workload(cfg, SIZE)
     sd = W.reid_workload()
     scenes = W.scenes(SIZE, SIZE)
     kw = {k: v for k, v in W.TRACKER_KW.items() if k != "min_confidence"}
@@ -400,7 +535,7 @@ def cpu_reference(n_frames, n_warm):
         step(t, True)
     dt = time.perf_counter() - t0
     return {"value": round(n_frames / dt, 4), "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
-            "sample": f"{n_frames} frames of the same clip after {n_warm} warm-up frames (oracle/: torch CPU fp32 convs + restated tracker)",
+            "sample": f"{n_frames} frames of the same clip after {n_warm} warm-up frames (oracle/: torch CPU fp32 convs + restated tracker), batch 1",
             "ms_per_frame": round(dt / n_frames * 1e3, 2), "detect_ms": round(stage["detect"] / n_frames * 1e3, 2),
             "track_ms": round(stage["track"] / n_frames * 1e3, 2), "dets_per_frame": round(float(np.mean(n_dets)), 1),
             "host_cores": int(cores)}
@@ -412,13 +547,16 @@ def run_reference(args):
         return
     K, Wm = args.steps, max(args.warmup, 1)
     import workload as W
-    b = cpu_reference(K, Wm)
+    cfg = args.config
+    b = cpu_reference(cfg, K, Wm)
     out = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
            "ms_per_step": b["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": f"{CFG} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream, batch 1, CPU",
+           "config": {"workload": f"{cfg} {SIZE}x{SIZE} + DeepSort (ReID 128x64 crops), 1 stream, batch 1, CPU",
                       "dets_per_frame": b["dets_per_frame"], "tracker": W.TRACKER_KW, "detector": W.DETECT_KW,
-                      "clip": f"{W.N_SCENES} synthetic scenes held per workload.SCHEDULE ({W.CLIP_LEN}-frame cycle); same frames and weights as the CUDA arm"},
+                      "clip": f"{W.N_SCENES} synthetic scenes held per workload.SCHEDULE ({W.CLIP_LEN}-frame cycle); same frames and weights as the CUDA arm",
+                      "note": "the reference has no batched or look-ahead mode (yolo3/detect/video_detect.py:124-156 is batch 1): its arm runs "
+                              "the stream frame by frame; the CUDA arm's batch-1 number is its `value_b1`"},
            "cpu_baseline": b,
            "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -431,13 +569,22 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=["yolov3", "yolov4", "reid", "assoc"], default="yolov3",
+                    help="BASELINE.json configs[1] (default, the headline) / [2] / [3] / [4]")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="keep repeating the K-step window until this much has been timed")
     ap.add_argument("--cpu-frames", type=int, default=16, help="frames timed by the cpu_baseline leg (bounded sample)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-frames", type=int, default=16, help="frames of the clip the parity leg checks against the oracle")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline and parity)")
+    ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--no-b1", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=MICRO_BATCH, help="consecutive frames of the stream per Darknet/ReID forward")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event timings of the layer graphs to this CSV")
     args = ap.parse_args()
+    if args.config in ("reid", "assoc"):
+        import bench_side
+        return bench_side.main(args)
     if args.impl == "reference":
-        args.steps = 24 if args.steps is None else args.steps             # one step = one frame, ~0.7 s on 8 host cores
+        args.steps = 24 if args.steps is None else args.steps             # one step = one frame, ~0.2 s on 16 host cores
         args.warmup = 2 if args.warmup is None else args.warmup
         return run_reference(args)
     args.steps = 256 if args.steps is None else args.steps

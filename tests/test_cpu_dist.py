@@ -21,7 +21,8 @@ def _worker(rank, world, port, q):
     bench.barrier()
     # rank 0 processed 10 frames in 100 ms, rank 1 processed 10 frames in 250 ms -> 20 frames / 0.25 s
     fps, worst = bench.aggregate_fps(10, 100.0 if rank == 0 else 250.0)
-    q.put((rank, fps, worst, bench.max_over_ranks(float(rank)), bench.sum_over_ranks(1.0)))
+    per_rank = bench.gather_floats(10.0 + rank)                 # per-rank ms, in rank order (names a straggler)
+    q.put((rank, fps, worst, bench.max_over_ranks(float(rank)), bench.sum_over_ranks(1.0), per_rank))
     bench.barrier()
     dist.destroy_process_group()
 
@@ -37,8 +38,17 @@ def test_world_size_2_aggregation():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, fps, worst, mx, sm in res:
-        assert abs(fps - 80.0) < 1e-9 and worst == 250.0 and mx == 1.0 and sm == 2.0
+    for rank, fps, worst, mx, sm, per_rank in res:
+        assert abs(fps - 80.0) < 1e-9 and worst == 250.0 and mx == 1.0 and sm == 2.0 and per_rank == [10.0, 11.0]
+
+
+def test_window_statistics():
+    """value / ms_per_step come from the MEDIAN window; count, min and max are reported next to it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    st, fps, ms_step = bench.window_stats([10.0, 12.0, 50.0], 20, 2)
+    assert st["count"] == 3 and st["ms_per_step_median"] == 0.6 and st["ms_per_step_min"] == 0.5 and st["ms_per_step_max"] == 2.5
+    assert abs(fps - 2 * 20 / 0.012) < 1e-6 and abs(ms_step - 0.6) < 1e-12
 
 
 def test_reference_arm_non_zero_ranks_do_nothing():

@@ -54,6 +54,13 @@ def test_workload_parity(cfg, mb):
     assert s["ids_equal"], chk.problems[:5]
     assert s["track_rows"] > 40 * W.CLIP_LEN * 0.6, "the clip should keep ~50 confirmed tracks alive"
     assert s["max_centre_px"] <= 1e-3                    # saturated centres: exact up to the fp32 rounding of x1 + w/2
-    assert s["max_size_px"] <= 0.5 and s["max_score_err"] <= 2.5e-2
-    # ReID: fp16 operands against the fp32 reference -- the storage-format floor is ~1.9e-3 (tests/test_precision_floor.py)
-    assert s["max_feature_rel"] <= 2.5e-3
+    # sizes: the fp16-storage floor of these stacks is 0.73 px (yolov3) / 0.85 px (yolov4) (tests/test_precision_floor.py); measured on
+    # B200 0.67 / 1.04 px -- pinned at measured x 1.25.  A corner moves by half of that, and the crop rectangles are asserted equal.
+    assert s["max_size_px"] <= (0.85 if cfg == "yolov3" else 1.3) and s["max_score_err"] <= 2e-2
+    # ReID: fp16 operands against the fp32 reference -- the storage-format floor is 1.2e-3 worst crop (tests/test_precision_floor.py),
+    # measured 1.42e-3 on the clip's ~350 distinct crops
+    assert s["max_feature_rel"] <= 1.8e-3
+    # And from pixels, free-running: the track ids of the CUDA run equal the fp32 oracle's on every frame of the clip, IN ORDER.
+    # (Not a law of nature -- association at scene changes is sensitive to sub-pixel differences, and the fp16-storage oracle parts
+    # ways with the fp32 one inside this very clip, `oracles_part_ways_at` -- but deterministic, so it is asserted: a regression gate.)
+    assert s["e2e_first_id_mismatch"]["fp32"] is None, s

@@ -248,7 +248,7 @@ int ydst_reid_extract(ydst_reid* r, const uint8_t* frame_dev, int height, int wi
                       void* stream) {
     YDST_API_BEGIN
     YDST_CHECK(r && frame_dev && (m == 0 || (tlwh_dev && feat_dev)), "null argument");
-    YDST_CUDA(cudaMemsetAsync(r->impl->err_flag, 0, sizeof(int), S(stream)));
+    YDST_CUDA(cudaMemsetAsync(r->impl->err_flag, 0, 8 * sizeof(int), S(stream)));
     r->impl->extract(frame_dev, height, width, tlwh_dev, m, feat_dev, S(stream));
     int flag = 0;
     YDST_CUDA(cudaMemcpyAsync(&flag, r->impl->err_flag, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
@@ -550,37 +550,44 @@ static void pipeline_submit(ydst_pipeline* p, const uint8_t* frame, bool frame_i
     if (fh <= 0 || fw <= 0) { fh = det.H; fw = det.W; }
     const bool plain = fh == det.H && fw == det.W && !is_bgr;            // already what the network eats
     sl.fh[sub] = fh; sl.fw[sub] = fw; sl.resized[sub] = !plain;
-    if (!frame_is_host) {
-        // the caller's frame was produced on the caller's stream and must stay readable until this frame is collected: keep a copy
-        YDST_CUDA(cudaEventRecord(p->ev_in, caller));
-        YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
-    }
     const cudaMemcpyKind kind = frame_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    // A DEVICE frame belongs to the caller and may be freed or overwritten as soon as this call returns (a torch tensor going out
+    // of scope hands its block back to the caching allocator, which reuses it on the caller's stream): its copy into the slot is
+    // therefore enqueued on the CALLER's stream, ordered with whatever the caller does next, and sA picks up after it.  The slot
+    // being filled has no reader left (its last collect waited for the ReID half), so writing it from another stream is safe.
+    // HOST frames are read by the copy engine until collected (the Python side keeps them alive); at the network size they go
+    // through the copy stream, under the previous slot's detector forward.
+    const cudaStream_t cs = frame_is_host ? p->sA : caller;
     if (plain && frame_is_host) {
-        // a free slot has no reader left (its last collect waited for the ReID half), so the upload need not queue behind the
-        // detector forward of the previous slot on sA: it runs on the copy stream, under that forward
         YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, p->sH));
         p->h2d_pending = true;
     } else if (plain) {
-        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, p->sA));
+        YDST_CUDA(cudaMemcpyAsync(sl.frame_dev + sub * bytes, frame, bytes, kind, cs));
     } else {
         // ingest on the device: (BGR ->) RGB copy of the captured frame for the ReID crops, cv2-exact resize to the network size
         const size_t fbytes = (size_t)fh * fw * 3;
         if (fbytes > sl.orig_cap) {
             YDST_CHECK(sub == 0, "frames of one micro-batch must not grow in size");
             YDST_CUDA(cudaStreamSynchronize(p->sA));
+            YDST_CUDA(cudaStreamSynchronize(p->sC));
             cudaFree(sl.orig_dev); cudaFree(sl.raw_dev);
             sl.orig_cap = fbytes;
             YDST_CUDA(cudaMalloc(&sl.orig_dev, sl.orig_cap * p->B));
             YDST_CUDA(cudaMalloc(&sl.raw_dev, sl.orig_cap));
         }
         uint8_t* orig = sl.orig_dev + (size_t)sub * sl.orig_cap;
+        YDST_CUDA(cudaMemcpyAsync(is_bgr ? sl.raw_dev : orig, frame, fbytes, kind, cs));
+    }
+    if (!frame_is_host) {
+        YDST_CUDA(cudaEventRecord(p->ev_in, caller));
+        YDST_CUDA(cudaStreamWaitEvent(p->sA, p->ev_in, 0));
+    }
+    if (!plain) {
+        const size_t fbytes = (size_t)fh * fw * 3; (void)fbytes;
+        uint8_t* orig = sl.orig_dev + (size_t)sub * sl.orig_cap;
         if (is_bgr) {
-            YDST_CUDA(cudaMemcpyAsync(sl.raw_dev, frame, fbytes, kind, p->sA));
             launch_resize_u8(sl.raw_dev, fh, fw, orig, fh, fw, 1, p->sA);        // same size: a channel-swapping copy
             count_launch();
-        } else {
-            YDST_CUDA(cudaMemcpyAsync(orig, frame, fbytes, kind, p->sA));
         }
         launch_resize_u8(orig, fh, fw, sl.frame_dev + sub * bytes, det.H, det.W, 0, p->sA);
         count_launch();
@@ -611,9 +618,11 @@ static void pipeline_launch_reid(ydst_pipeline* p, ydst_pipeline::Slot& sl, bool
         ms[b] = sl.h_counts[b * 8 + 1] > 0 ? sl.h_counts[b * 8 + 3] : 0;
         sl.feat_off[b] = off; off += ms[b];
     }
-    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, sizeof(int), p->sC));
+    YDST_CUDA(cudaMemsetAsync(p->reid->err_flag, 0, 8 * sizeof(int), p->sC));
     p->reid->extract_multi(frames, hs, ws, boxes, ms, sl.n_frames, sl.feat, p->sC);
-    YDST_CUDA(cudaMemcpyAsync(sl.h_counts + 4, p->reid->err_flag, sizeof(int), cudaMemcpyDeviceToHost, p->sC));
+    // one empty-crop flag per frame, into that frame's counter row ([4])
+    YDST_CUDA(cudaMemcpy2DAsync(sl.h_counts + 4, 8 * sizeof(int), p->reid->err_flag, sizeof(int), sizeof(int), sl.n_frames,
+                                cudaMemcpyDeviceToHost, p->sC));
     YDST_CUDA(cudaEventRecord(sl.ev_feat, p->sC));
     sl.reid_launched = true;
 }
@@ -654,16 +663,21 @@ static int pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, fl
         }
     }
     p->last_slot = si; p->last_sub = sub; p->last_m = n_dets > 0 ? m : 0;
+    // the reference raises inside cv2.resize -- BEFORE tracker.update (deep_sort/deep/feature_extractor.py:45) -- when a box has
+    // no pixels inside the frame: make this frame's flag host-visible and test it before the tracker consumes the features
+    if (m > 0) {
+        YDST_CUDA(cudaEventSynchronize(sl.ev_feat));
+        if (sl.h_counts[sub * 8 + 4]) {
+            set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)");
+            *k_host = -1;
+            return 3;
+        }
+    }
     if (n_dets == 0) { *k_host = -1; return 0; }          // the reference skips tracker.update when nothing was detected
     const float* h_cls = sl.h_cls + (size_t)sub * md;
     for (int i = 0; i < m; ++i) p->h_payload[i] = (int)h_cls[i];
     p->trk->update(sl.tlwh + (size_t)sub * md * 4, sl.feat + (size_t)sl.feat_off[sub] * 512, p->h_payload, nullptr, m, out_host, k_host, p->sB);
     if (nxt.busy) pipeline_launch_reid(p, nxt, false);
-    if (sub == sl.n_frames - 1) {
-        // the crop error flag of this slot's ReID has long landed (the tracker waited for ev_feat on the device; make it host-visible)
-        YDST_CUDA(cudaEventSynchronize(sl.ev_feat));
-        if (sl.h_counts[4]) { set_error("empty crop: a detection has no pixels inside the frame (cv2.resize raises in the reference)"); return 3; }
-    }
     return 0;
 }
 

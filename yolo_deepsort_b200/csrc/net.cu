@@ -459,7 +459,7 @@ Reid::Reid(const float* weights, size_t n_weights, int max_batch_) : max_batch(m
     YDST_CHECK(wp == n_weights, "ReID weights: %zu floats given, %zu consumed", n_weights, wp);
     in_f32_ = (float*)arena_.alloc((size_t)max_batch * 128 * 64 * 3 * sizeof(float));
     feat_ = (float*)arena_.alloc((size_t)max_batch * 512 * sizeof(float));
-    err_flag = (int*)arena_.alloc(sizeof(int));
+    err_flag = (int*)arena_.alloc(8 * sizeof(int));           // one empty-crop flag per frame of a micro-batch
     ws_ = make_conv_workspace(arena_);
     bufs_.push_back(make_act(arena_, max_batch, 128, 64, 64));          // 0: stem out
     int h = 64, w = 32;
@@ -545,26 +545,32 @@ void Reid::forward(const float* x_dev, int m, float* feat_out, cudaStream_t st) 
 
 void Reid::extract_multi(const uint8_t* const* frames_dev, const int* H, const int* W, const float* const* tlwh_dev, const int* m, int nb,
                          float* feat_out, cudaStream_t st) {
-    int total = 0;
-    for (int b = 0; b < nb; ++b) total += m[b];
-    if (total == 0) return;
-    YDST_CHECK(total <= max_batch, "ReID batch %d exceeds max_batch %d", total, max_batch);
-    int off = 0;
+    // The crops of all frames go through the net in chunks of at most max_batch (the activation buffers' capacity): the reference
+    // has no limit on the number of detections (deep_sort/deep_sort.py:133-146), so neither a busy frame nor a micro-batch of B
+    // frames may overflow -- they just take more than one forward.  Stream order makes the reuse of in_f32_ / feat_ safe.
+    int done = 0, fill = 0;                                 // feature rows written so far | crops staged for the current chunk
+    auto flush = [&]() {
+        if (fill == 0) return;
+        forward(in_f32_, fill, feat_out ? feat_out + (size_t)done * 512 : nullptr, st);
+        done += fill;
+        fill = 0;
+    };
     for (int b = 0; b < nb; ++b) {
-        if (m[b] == 0) continue;
-        launch_crop_resize(frames_dev[b], H[b], W[b], tlwh_dev[b], m[b], in_f32_ + (size_t)off * 128 * 64 * 3, err_flag, st);
-        count_launch();
-        off += m[b];
+        int first = 0;
+        while (first < m[b]) {
+            const int take = std::min(m[b] - first, max_batch - fill);
+            launch_crop_resize(frames_dev[b], H[b], W[b], tlwh_dev[b] + (size_t)first * 4, take, in_f32_ + (size_t)fill * 128 * 64 * 3, err_flag + (b & 7), st);
+            count_launch();
+            first += take;
+            fill += take;
+            if (fill == max_batch) flush();
+        }
     }
-    forward(in_f32_, total, feat_out, st);
+    flush();
 }
 
 void Reid::extract(const uint8_t* frame_dev, int H, int W, const float* tlwh_dev, int m, float* feat_out, cudaStream_t st) {
-    if (m == 0) return;
-    YDST_CHECK(m <= max_batch, "ReID batch %d exceeds max_batch %d", m, max_batch);
-    launch_crop_resize(frame_dev, H, W, tlwh_dev, m, in_f32_, err_flag, st);
-    count_launch();
-    forward(in_f32_, m, feat_out, st);
+    extract_multi(&frame_dev, &H, &W, &tlwh_dev, &m, 1, feat_out, st);
 }
 
 }  // namespace ydst

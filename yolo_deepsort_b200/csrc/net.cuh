@@ -98,7 +98,7 @@ public:
     void extract_multi(const uint8_t* const* frames_dev, const int* H, const int* W, const float* const* tlwh_dev, const int* m, int nb,
                        float* feat_out, cudaStream_t st);
     int max_batch;
-    int* err_flag = nullptr;     // device
+    int* err_flag = nullptr;     // device, [8]: frame b of an extract_multi call raises err_flag[b] when one of its crops is empty
 private:
     const Plan& plan_for(int m);
     DeviceArena arena_;

@@ -195,6 +195,10 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
     if (trace) t_b = now();
     std::vector<std::pair<int, int>> matches = A.matches;
     matches.insert(matches.end(), B.matches.begin(), B.matches.end());
+    // capacity is checked BEFORE any track state is touched, so a refused frame leaves the tracker exactly as predict() left it
+    // (slots of tracks deleted in this very step only become reusable on the next frame)
+    YDST_CHECK(B.um_d.size() <= free_slots_.size(), "tracker capacity (%d tracks) exhausted: %zu new detections, %zu free slots", cap_t_,
+               B.um_d.size(), free_slots_.size());
     last_matches = matches;
 
     // ---- update matched tracks (tracker.py:129-156, track.py:125-144) ----

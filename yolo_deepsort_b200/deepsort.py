@@ -70,7 +70,7 @@ class TrackerHandle:
 
 class DeepSort:
     def __init__(self, model_path, max_dist=0.2, min_confidence=0.3, nms_max_overlap=1.0, max_iou_distance=0.7, max_age=70,
-                 n_init=3, nn_budget=100, use_cuda=False, cap_tracks=1024, cap_dets=512, device="cuda:0"):
+                 n_init=3, nn_budget=100, use_cuda=False, cap_tracks=4096, cap_dets=2048, device="cuda:0", reid_batch=512):
         _lib.require_cuda()
         if nn_budget is None:
             raise ValueError("nn_budget=None (unbounded galleries) is not supported: pass an integer budget")
@@ -84,7 +84,8 @@ class DeepSort:
         self.device = torch.device(device)
         self._cap = (cap_tracks, cap_dets)
         if isinstance(model_path, (str, dict)):
-            self.extractor = Extractor(model_path, use_cuda=True, max_batch=cap_dets, device=device)
+            # crops beyond reid_batch go through the net in several forwards (the reference has no limit on detections per frame)
+            self.extractor = Extractor(model_path, use_cuda=True, max_batch=min(cap_dets, reid_batch), device=device)
         else:
             self.extractor = model_path                    # injected extractor (deep_sort.py:28-31)
         self.tracker = TrackerHandle(max_dist, max_iou_distance, max_age, n_init, nn_budget, cap_tracks, cap_dets, device)
