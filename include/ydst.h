@@ -95,6 +95,16 @@ int ydst_detector_launches(const ydst_detector* d);
  * returns the count in *n_host.  Used by the parity tests to feed the oracle's exact predictions.   */
 int ydst_nms(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, float* dets_dev, int* n_host,
              void* stream);
+/* soft_non_max_suppression with its keyword options (yolo3/utils/model_build.py:52-53): is_p1p2 (boxes are corners), merge (the
+ * "Merge NMS" block :122-131 exactly as the reference executes it, see csrc/nms.cu), agnostic, classes (n_classes ids on the host, or
+ * NULL / 0 for all).  `merge`, `is_p1p2` are what the sliding-window mode of ImageDetector.detect passes
+ * (yolo3/detect/img_detect.py:140-143). */
+int ydst_nms_ex(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, int merge, int is_p1p2, int agnostic,
+                const int* classes_host, int n_classes, float* dets_dev, int* n_host, void* stream);
+/* Sliding-window mode (yolo3/detect/img_detect.py:97-137): tile t of the batch had its (x,y,w,h) boxes predicted in network pixels;
+ * convert in place to corners (xywh2p1p2), scale by (ratio_w[t], ratio_h[t]) (resize_boxes) and shift by (off_x[t], off_y[t]).
+ * pred_dev: [tiles][rows][fields] fp32; ratios_host / offsets_host: [tiles][2] = (w, h) / (x, y). */
+int ydst_window_boxes(float* pred_dev, int tiles, int rows, int fields, const float* ratios_host, const float* offsets_host, void* stream);
 
 /* One convolution through the same kernels the networks use (tcgen05 implicit GEMM, or the direct first-layer
  * kernel when cin == 3): nn.Conv2d(cin,cout,k,stride,(k-1)//2) [+ BatchNorm2d eval] [+ activation] [+ residual]
@@ -213,6 +223,10 @@ int ydst_pipeline_submit_frame(ydst_pipeline* p, const uint8_t* frame, int heigh
                                void* stream);
 /* the ingest kernel alone: cv2.resize(src, (dst_w, dst_h), INTER_LINEAR) on uint8 HxWx3, optionally swapping R and B; synchronises */
 int ydst_resize_u8(const uint8_t* src_dev, int src_h, int src_w, uint8_t* dst_dev, int dst_h, int dst_w, int swap_rb, void* stream);
+/* The same resize from a sub-rectangle (x0, y0, roi_w, roi_h) of a (src_h, src_w) frame: the window crops of the sliding-window
+ * mode, img[y:y+win_h+ov, x:x+win_w+ov] -> cv2.resize (yolo3/detect/img_detect.py:107-111). */
+int ydst_resize_u8_roi(const uint8_t* src_dev, int src_h, int src_w, int x0, int y0, int roi_w, int roi_h, uint8_t* dst_dev, int dst_h,
+                       int dst_w, int swap_rb, void* stream);
 /* Tracker inputs of the frame returned by the LAST _collect / _step: its m rows of tlwh boxes (m x 4), ReID features (m x 512,
  * as handed to Tracker.update, deep_sort/deep_sort.py:55-60) and class ids, copied to the host.  Parity aid: lets a test feed
  * the reference association with exactly what the CUDA association saw.  Valid until the next _submit / _collect. */

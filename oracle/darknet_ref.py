@@ -246,27 +246,94 @@ def forward(blocks, ws, x, return_layers=False, calibrate_bn=False, half_storage
     return (y, outs) if return_layers else y
 
 
-def postprocess(pred, conf_thres, iou_thres, max_det=300):
-    """soft_non_max_suppression for one image, merge=False, multi_label=True
-    (yolo3/utils/model_build.py:52-137).  pred: (R, 5+nc) float32, xywh-centre boxes.
-    Returns (n,6) float32 [x1,y1,x2,y2,conf,cls] in score-descending order, or None."""
+def _bbox_iou_elementwise(box1, box2):
+    """bbox_iou, p1p2=True (yolo3/utils/model_build.py:354-381): ELEMENTWISE (broadcasting) IoU with "+1" extents."""
+    inter_mins = torch.max(box1[..., :2], box2[..., :2])
+    inter_maxes = torch.min(box1[..., 2:4], box2[..., 2:4])
+    inter_wh = torch.clamp(inter_maxes - inter_mins + 1, min=0)
+    inter_area = inter_wh[..., 0] * inter_wh[..., 1]
+    a1 = (box1[..., 2] - box1[..., 0] + 1) * (box1[..., 3] - box1[..., 1] + 1)
+    a2 = (box2[..., 2] - box2[..., 0] + 1) * (box2[..., 3] - box2[..., 1] + 1)
+    return inter_area / (a1 + a2 - inter_area + 1e-16)
+
+
+def postprocess(pred, conf_thres, iou_thres, max_det=300, merge=False, is_p1p2=False, classes=None, agnostic=False):
+    """soft_non_max_suppression for one image, multi_label=True (yolo3/utils/model_build.py:52-137).
+    pred: (R, 5+nc) float32, xywh-centre boxes (corner boxes with is_p1p2).
+    Returns (n,6) float32 [x1,y1,x2,y2,conf,cls] in score-descending order, or None.
+
+    merge=True restates the "Merge NMS" block (:122-131) AS IT EXECUTES: the reference calls its elementwise bbox_iou where
+    ultralytics has the pairwise box_iou, inside a bare try/except.  With k kept rows of n candidates the shapes only broadcast
+    for k == n or k == 1; otherwise the line raises, the exception is swallowed and nothing is merged.  When they do broadcast,
+    `weights` is a (1,n) row, torch.mm yields ONE weighted mean box that the broadcast assignment writes into every kept row,
+    and the following `iou.sum(1)` raises on the 1-D tensor (swallowed too), so the `redundant` filter never runs."""
     x = np.array(pred, dtype=np.float32, copy=True)
     x = x[x[:, 4] > np.float32(conf_thres)]
     if not x.shape[0]:
         return None
     x[:, 5:] *= x[:, 4:5]
-    box = np.empty((x.shape[0], 4), np.float32)
-    box[:, 0] = x[:, 0] - x[:, 2] / np.float32(2.)
-    box[:, 1] = x[:, 1] - x[:, 3] / np.float32(2.)
-    box[:, 2] = x[:, 0] + x[:, 2] / np.float32(2.)
-    box[:, 3] = x[:, 1] + x[:, 3] / np.float32(2.)
+    if is_p1p2:
+        box = x[:, :4].copy()
+    else:
+        box = np.empty((x.shape[0], 4), np.float32)
+        box[:, 0] = x[:, 0] - x[:, 2] / np.float32(2.)
+        box[:, 1] = x[:, 1] - x[:, 3] / np.float32(2.)
+        box[:, 2] = x[:, 0] + x[:, 2] / np.float32(2.)
+        box[:, 3] = x[:, 1] + x[:, 3] / np.float32(2.)
     i, j = np.nonzero(x[:, 5:] > np.float32(conf_thres))          # row-major order
     det = np.concatenate((box[i], x[i, j + 5][:, None], j[:, None].astype(np.float32)), 1)
-    if not det.shape[0]:
+    if classes:
+        det = det[np.isin(det[:, 5], np.asarray(classes, np.float32))]
+    n = det.shape[0]
+    if not n:
         return None
-    c = det[:, 5:6] * np.float32(4096)
-    keep = nms_ref(det[:, :4] + c, det[:, 4], iou_thres)
-    return det[keep[:max_det]]
+    c = det[:, 5:6] * np.float32(0 if agnostic else 4096)
+    boxes = det[:, :4] + c
+    keep = nms_ref(boxes, det[:, 4], iou_thres)[:max_det]
+    if merge and 1 < n < 3000 and len(keep) in (1, n):
+        tb = torch.from_numpy(boxes)
+        iou = _bbox_iou_elementwise(tb[torch.from_numpy(keep)], tb) > iou_thres            # (n,)
+        weights = iou * torch.from_numpy(det[:, 4])[None]                                    # (1,n)
+        merged = torch.mm(weights, torch.from_numpy(det[:, :4])).float() / weights.sum(1, keepdim=True)
+        det[keep, :4] = merged.numpy()
+    return det[keep]
+
+
+def detect_windows(blocks, ws, img_rgb_u8, img_size, win_size, overlap, conf_thres, iou_thres):
+    """ImageDetector.detect, sliding-window branch, half=False (yolo3/detect/img_detect.py:97-151): windows of win_size
+    (width, height) plus `overlap` of it on the right / bottom, x outer and y inner, each cv2-resized to the network size and
+    pushed through the net as ONE batch; boxes to corners, scaled back to the window, shifted by the window origin, all windows
+    concatenated, then soft_non_max_suppression(merge=True, is_p1p2=True)."""
+    import cv2
+    h, w, _ = img_rgb_u8.shape
+    win_w, win_h = win_size
+    ov_x, ov_y = int(win_w * overlap), int(win_h * overlap)
+    tiles, sizes, offsets = [], [], []
+    for x in range(0, w, win_w):
+        for y in range(0, h, win_h):
+            sub = img_rgb_u8[y:y + win_h + ov_y, x:x + win_w + ov_x]
+            sizes.append((sub.shape[0], sub.shape[1]))
+            tiles.append(cv2.resize(sub, (img_size[1], img_size[0]), interpolation=cv2.INTER_LINEAR))
+            offsets.append(torch.tensor([x, y, x, y], dtype=torch.float32))
+    xb = torch.from_numpy(np.stack(tiles, 0)).permute(0, 3, 1, 2) / 255.
+    det = forward(blocks, ws, xb)
+    b = det[..., :4].clone()
+    det[..., 0] = b[..., 0] - b[..., 2] / 2
+    det[..., 1] = b[..., 1] - b[..., 3] / 2
+    det[..., 2] = b[..., 0] + b[..., 2] / 2
+    det[..., 3] = b[..., 1] + b[..., 3] / 2
+    out = []
+    for t in range(det.shape[0]):
+        d = det[t]
+        h_ratio, w_ratio = sizes[t][0] / img_size[0], sizes[t][1] / img_size[1]
+        d[..., 0] *= w_ratio
+        d[..., 1] *= h_ratio
+        d[..., 2] *= w_ratio
+        d[..., 3] *= h_ratio
+        d[..., :4] += offsets[t]
+        out.append(d)
+    allp = torch.cat(out, 0)
+    return postprocess(allp.numpy(), conf_thres, iou_thres, merge=True, is_p1p2=True), tiles
 
 
 def detect(blocks, ws, frame_rgb_u8, img_size, conf_thres, iou_thres):

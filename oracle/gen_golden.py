@@ -11,6 +11,10 @@ Golden files (small, committed):
                       (boxes, features, class ids) and the reference's (K,6) int32 outputs + track tables
   tiny416.npz         yolov3-tiny 416: head outputs digest, soft_non_max_suppression output, one frame
   reid.npz            Extractor features for boxes on one frame (crop + cv2.resize + Net)
+  overlay.npz         LabelDrawer.draw_labels_by_trackers / draw_labels output (images and digests) on two synthetic frames
+  window.npz          ImageDetector.detect in sliding-window mode (win_size, overlap; batched tiles + merge-NMS) on a 700x1000
+                      image, and soft_non_max_suppression(merge=True) on hand-built predictions that reach the k == n and
+                      k == 1 branches of the merge block
 """
 import hashlib
 import os
@@ -190,11 +194,116 @@ def gen_reid():
                         feats=feats.numpy())
 
 
+def window_image_and_weights():
+    """The sliding-window fixture: a 700x1000 synthetic image and yolov3-tiny weights whose heads are calibrated on its six
+    416x416(+15 %) windows (so that every window yields ~12 detections)."""
+    import cv2
+    from . import darknet_ref as D
+    from .synth import darknet_ref as _d, frame_to_input, make_frame, shape_heads, calibrate_heads
+    cfg = os.path.join(CFG_DIR, "yolov3-tiny.cfg")
+    blocks = D.parse_cfg(cfg)
+    img = make_frame(700, 1000, seed=21, n_rect=90)
+    win, ov = (416, 416), 0.15
+    tiles = []
+    for x in range(0, 1000, win[0]):
+        for y in range(0, 700, win[1]):
+            sub = img[y:y + win[1] + int(win[1] * ov), x:x + win[0] + int(win[0] * ov)]
+            tiles.append(cv2.resize(sub, (416, 416), interpolation=cv2.INTER_LINEAR))
+    ws = D.init_weights(blocks, 5)
+    D.forward(blocks, ws, torch.cat([frame_to_input(t) for t in tiles], 0), calibrate_bn=True)
+    shape_heads(ws)
+    ws, info = calibrate_heads(blocks, ws, tiles, want_dets=12)
+    return cfg, blocks, ws, img, win, ov, info
+
+
+def merge_cases():
+    """Hand-built corner-box predictions for soft_non_max_suppression(merge=True, is_p1p2=True): (a) nothing suppressed (k == n:
+    every kept row becomes the one weighted mean box), (b) one cluster (k == 1: the intended merge), (c) two clusters (1 < k < n:
+    the merge line raises inside the reference's try/except and nothing is merged)."""
+    def mk(boxes, scores):
+        p = np.zeros((len(boxes), 85), np.float32)
+        p[:, :4] = np.asarray(boxes, np.float32)
+        p[:, 4] = np.asarray(scores, np.float32)
+        p[:, 5] = 0.95
+        return p
+    a = mk([[50 + 160 * i, 100, 150 + 160 * i, 220] for i in range(4)], [0.9, 0.7, 0.8, 0.6])
+    b = mk([[50 + 3 * i, 100 + 2 * i, 150 + 3 * i, 220 + 2 * i] for i in range(5)], [0.7, 0.9, 0.8, 0.65, 0.75])
+    c = mk([[50 + 3 * i, 100, 150 + 3 * i, 220] for i in range(3)] + [[400 + 3 * i, 300, 520 + 3 * i, 420] for i in range(3)],
+           [0.7, 0.9, 0.8, 0.65, 0.75, 0.85])
+    return {"all_kept": a, "one_cluster": b, "two_clusters": c}
+
+
+def gen_window():
+    import contextlib
+    import io
+    from yolo3.detect.img_detect import ImageDetector
+    from yolo3.models import Darknet
+    from yolo3.utils.model_build import soft_non_max_suppression
+    from . import darknet_ref as D
+    cfg, blocks, ws, img, win, ov, info = window_image_and_weights()
+    print("  window calibration:", info)
+    with tempfile.TemporaryDirectory() as td:
+        wpath, names = os.path.join(td, "tiny.weights"), os.path.join(td, "coco.names")
+        D.write_weights(wpath, blocks, ws)
+        with open(names, "w") as fh:
+            fh.write("\n".join(f"c{i}" for i in range(80)) + "\n")
+        model = Darknet(cfg, img_size=(416, 416))
+        model.load_darknet_weights(wpath)
+        det = ImageDetector(model, names, thres=0.5, nms_thres=0.4, win_size=win, overlap=ov, half=False)
+        with contextlib.redirect_stdout(io.StringIO()):           # the merge block prints its tensors when it raises
+            ref = det.detect(img)
+    od, _ = D.detect_windows(blocks, ws, img, (416, 416), win, ov, 0.5, 0.4)
+    _eq(od, ref.numpy(), f"ImageDetector.detect, sliding-window mode ({len(od)} detections)")
+    out = {"dets": ref.numpy(), "win": np.asarray(win, np.int32), "overlap": np.float64(ov)}
+    for name, p in merge_cases().items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = soft_non_max_suppression(torch.from_numpy(p)[None].clone(), 0.5, 0.4, merge=True, is_p1p2=True)[0]
+        o = D.postprocess(p, 0.5, 0.4, merge=True, is_p1p2=True)
+        _eq(o, r.numpy(), f"soft_non_max_suppression(merge=True) case {name} ({len(o)} rows)")
+        out["merge_" + name] = r.numpy()
+    np.savez_compressed(os.path.join(GOLD, "window.npz"), **out)
+
+
+def overlay_inputs():
+    """Frames and rows for the overlay fixture: tracker rows [x1,y1,x2,y2,id,cls] (int32, DeepSort.update's output) and detector
+    rows [x1,y1,x2,y2,conf,cls] (float32), on a 240x320 and a 608x608 synthetic frame."""
+    from .synth import make_frame
+    rng = np.random.default_rng(33)
+    out = {}
+    for name, (h, w) in (("small", (240, 320)), ("full", (608, 608))):
+        n = 14
+        x1 = rng.integers(-5, w - 40, n); y1 = rng.integers(-5, h - 60, n)
+        rows = np.stack([x1, y1, x1 + rng.integers(20, 90, n), y1 + rng.integers(30, 120, n), rng.integers(1, 400, n),
+                         rng.choice([0, 2, 4, 7], n)], 1).astype(np.int32)
+        dets = np.concatenate([rows[:, :4].astype(np.float32) + rng.uniform(0, 1, (n, 4)).astype(np.float32),
+                               rng.uniform(0.5, 1.0, (n, 1)).astype(np.float32), rows[:, 5:6].astype(np.float32)], 1)
+        out[name] = (make_frame(h, w, seed=40 + len(out)), rows, dets)
+    return out
+
+
+def gen_overlay():
+    from yolo3.utils.label_draw import LabelDrawer
+    classes = [f"c{i}" for i in range(80)]
+    res = {}
+    for name, (frame, rows, dets) in overlay_inputs().items():
+        ld = LabelDrawer(classes, None, 10, 2, img_size=frame.shape[:2])
+        a, _, _ = ld.draw_labels_by_trackers(frame.copy(), rows, only_rect=False)
+        b, _, _ = ld.draw_labels(frame.copy(), torch.from_numpy(dets), only_rect=False)
+        c, _, _ = ld.draw_labels_by_trackers(frame.copy(), rows, only_rect=True)
+        if name == "small":
+            res["small_tracks"], res["small_dets"], res["small_rects"] = a, b, c
+        for k, im in (("tracks", a), ("dets", b), ("rects", c)):
+            res[f"{name}_{k}_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(im).tobytes()).digest(), np.uint8)
+        res[name + "_colors"] = np.asarray(ld.colors, np.int32)
+    np.savez_compressed(os.path.join(GOLD, "overlay.npz"), **res)
+    print("  overlay fixture written (reference LabelDrawer on 2 frames x 3 modes)")
+
+
 def main():
     ref_shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_reid):
+    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_reid, gen_window, gen_overlay):
         print(fn.__name__)
         fn()
     print("golden vectors written to", GOLD)

@@ -18,12 +18,8 @@ from yolo_deepsort_b200._lib import check, lib, ptr, stream_ptr
 pytestmark = pytest.mark.gpu
 
 
-def make_model(name, size, frames, seed=0, target=50):
-    from oracle import darknet_ref as D
-    from oracle.synth import darknet_weights
-    cfg = os.path.join(ROOT, "config", name + ".cfg")
-    blocks = D.parse_cfg(cfg)
-    ws, info = darknet_weights(blocks, frames, seed=seed, target=target)
+def flatten_ws(blocks, ws):
+    """The float32 payload of a darknet .weights file for the oracle's weight list (yolo3/models/models.py:315-366 layout)."""
     flat = []
     it = iter(ws)
     for b in blocks[1:]:
@@ -36,8 +32,17 @@ def make_model(name, size, frames, seed=0, target=50):
         else:
             flat.append(d["b"])
         flat.append(d["w"].ravel())
+    return np.concatenate([np.asarray(a, np.float32).ravel() for a in flat])
+
+
+def make_model(name, size, frames, seed=0, target=50):
+    from oracle import darknet_ref as D
+    from oracle.synth import darknet_weights
+    cfg = os.path.join(ROOT, "config", name + ".cfg")
+    blocks = D.parse_cfg(cfg)
+    ws, info = darknet_weights(blocks, frames, seed=seed, target=target)
     model = Darknet(cfg, img_size=size)
-    model.set_weights(np.concatenate([np.asarray(a, np.float32).ravel() for a in flat]))
+    model.set_weights(flatten_ws(blocks, ws))
     model.to(DEV)
     return model, blocks, ws
 

@@ -113,3 +113,46 @@ def test_reid_features_vs_golden():
     assert tuple(f.shape) == (12, 512)
     np.testing.assert_allclose(np.asarray(f), g["feats"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(np.linalg.norm(np.asarray(f), axis=1), 1.0, atol=1e-5)
+
+
+def test_sliding_window_mode_and_merge_nms_bit_exact():
+    """tests/golden/window.npz: the unmodified reference's ImageDetector.detect with win_size=(416,416), overlap=0.15 on a 700x1000
+    image (six windows batched through the net, merge-NMS over their union), and soft_non_max_suppression(merge=True,
+    is_p1p2=True) on hand-built predictions that reach every branch of the merge block as it actually executes."""
+    from oracle.gen_golden import merge_cases, window_image_and_weights
+    g = _g("window.npz")
+    cfg, blocks, ws, img, win, ov, info = window_image_and_weights()
+    dets, tiles = D.detect_windows(blocks, ws, img, (416, 416), win, ov, 0.5, 0.4)
+    assert len(tiles) == 6
+    np.testing.assert_array_equal(dets, g["dets"])
+    for name, p in merge_cases().items():
+        np.testing.assert_array_equal(D.postprocess(p, 0.5, 0.4, merge=True, is_p1p2=True), g["merge_" + name])
+    # what the branches do: all kept -> every row carries the same weighted-mean box; one cluster -> one merged row; otherwise untouched
+    a = g["merge_all_kept"]
+    assert len(a) == 4 and (a[:, :4] == a[0, :4]).all()
+    assert len(g["merge_one_cluster"]) == 1 and len(g["merge_two_clusters"]) == 2
+    plain = D.postprocess(merge_cases()["two_clusters"], 0.5, 0.4, is_p1p2=True)
+    np.testing.assert_array_equal(plain, g["merge_two_clusters"])
+
+
+def test_overlay_matches_reference_label_drawer():
+    """yolo_deepsort_b200.label_draw.LabelDrawer (host cv2, the reference's own calls) against the images the
+    unmodified reference LabelDrawer drew (tests/golden/overlay.npz): tracker rows with labels, detector rows with labels,
+    rectangles only -- identical pixels on a 240x320 frame (full images) and a 608x608 frame (digests)."""
+    from oracle.gen_golden import overlay_inputs
+    from yolo_deepsort_b200.label_draw import LabelDrawer
+    g = _g("overlay.npz")
+    classes = [f"c{i}" for i in range(80)]
+    for name, (frame, rows, dets) in overlay_inputs().items():
+        ld = LabelDrawer(classes, None, 10, 2, img_size=frame.shape[:2])
+        np.testing.assert_array_equal(np.asarray(ld.colors, np.int32), g[name + "_colors"])
+        a, _, _ = ld.draw_labels_by_trackers(frame.copy(), rows, only_rect=False)
+        b, _, _ = ld.draw_labels(frame.copy(), torch.from_numpy(dets), only_rect=False)
+        c, _, _ = ld.draw_labels_by_trackers(frame.copy(), rows, only_rect=True)
+        if name == "small":
+            np.testing.assert_array_equal(a, g["small_tracks"]); np.testing.assert_array_equal(b, g["small_dets"])
+            np.testing.assert_array_equal(c, g["small_rects"])
+        for k, im in (("tracks", a), ("dets", b), ("rects", c)):
+            digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(im).tobytes()).digest(), np.uint8)
+            np.testing.assert_array_equal(digest, g[f"{name}_{k}_sha256"], err_msg=f"{name} {k}")
+        assert (a != frame).any()

@@ -47,6 +47,8 @@ SIGNATURES = {
     "ydst_detector_flops": (ctypes.c_double, [_P]),
     "ydst_detector_launches": (_I, [_P]),
     "ydst_nms": (_I, [_P, _I, _I, _F, _F, _P, ctypes.POINTER(_I), _P]),
+    "ydst_nms_ex": (_I, [_P, _I, _I, _F, _F, _I, _I, _I, _P, _I, _P, ctypes.POINTER(_I), _P]),
+    "ydst_window_boxes": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "ydst_conv2d": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P]),
     "ydst_conv_tiling": (_I, [_I, _I, _I, _I, _I, _I] + [ctypes.POINTER(_I)] * 4 + [ctypes.POINTER(ctypes.c_double)]),
     "ydst_reid_create": (_I, [_P, _SZ, _I, ctypes.POINTER(_P)]),
@@ -73,6 +75,7 @@ SIGNATURES = {
     "ydst_pipeline_submit": (_I, [_P, _P, _I, _I, _P]),
     "ydst_pipeline_submit_frame": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ydst_resize_u8": (_I, [_P, _I, _I, _P, _I, _I, _I, _P]),
+    "ydst_resize_u8_roi": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "ydst_pipeline_collect": (_I, [_P, _P, ctypes.POINTER(_I), _P, ctypes.POINTER(_I)]),
     "ydst_pipeline_last_inputs": (_I, [_P, _P, _P, _P, _I, ctypes.POINTER(_I)]),
     "ydst_pipeline_in_flight": (_I, [_P]),

@@ -153,13 +153,14 @@ int ydst_detector_layer_output(const ydst_detector* d, int layer, void* dense_de
 double ydst_detector_flops(const ydst_detector* d) { return d ? d->impl->plan.flops : 0.0; }
 int ydst_detector_launches(const ydst_detector* d) { return d ? d->impl->plan.launches + 1 : 0; }
 
-int ydst_nms(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, float* dets_dev, int* n_host, void* stream) {
+static int nms_standalone(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, const NmsOptions* opt,
+                          float* dets_dev, int* n_host, void* stream) {
     YDST_API_BEGIN
     YDST_CHECK(pred_dev && dets_dev && n_host && rows >= 0 && fields > 5, "bad argument");
     Nms nms;
     nms.init(4096, 300);
     try {
-        nms.run(pred_dev, rows, fields, conf_thres, iou_thres, S(stream));
+        nms.run(pred_dev, rows, fields, conf_thres, iou_thres, S(stream), 1, opt);
         int h[4];
         YDST_CUDA(cudaMemcpyAsync(dets_dev, nms.dets, sizeof(float) * 6 * 300, cudaMemcpyDeviceToDevice, S(stream)));
         YDST_CUDA(cudaMemcpyAsync(h, nms.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, S(stream)));
@@ -168,6 +169,39 @@ int ydst_nms(const float* pred_dev, int rows, int fields, float conf_thres, floa
         *n_host = h[1];
     } catch (...) { nms.destroy(); throw; }
     nms.destroy();
+    YDST_API_END
+}
+int ydst_nms(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, float* dets_dev, int* n_host, void* stream) {
+    return nms_standalone(pred_dev, rows, fields, conf_thres, iou_thres, nullptr, dets_dev, n_host, stream);
+}
+int ydst_nms_ex(const float* pred_dev, int rows, int fields, float conf_thres, float iou_thres, int merge, int is_p1p2, int agnostic,
+                const int* classes_host, int n_classes, float* dets_dev, int* n_host, void* stream) {
+    NmsOptions opt{};
+    opt.merge = merge != 0; opt.p1p2 = is_p1p2 != 0; opt.agnostic = agnostic != 0;
+    if (classes_host && n_classes > 0) {
+        opt.use_classes = 1;
+        for (int i = 0; i < n_classes; ++i)
+            if (classes_host[i] >= 0 && classes_host[i] < 256) opt.class_bits[classes_host[i] >> 6] |= 1ull << (classes_host[i] & 63);
+    }
+    return nms_standalone(pred_dev, rows, fields, conf_thres, iou_thres, &opt, dets_dev, n_host, stream);
+}
+int ydst_window_boxes(float* pred_dev, int tiles, int rows, int fields, const float* ratios_host, const float* offsets_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(pred_dev && ratios_host && offsets_host && tiles > 0 && rows > 0 && fields > 5, "bad argument");
+    std::vector<float> geo((size_t)tiles * 4);
+    for (int t = 0; t < tiles; ++t) {
+        geo[t * 4 + 0] = ratios_host[t * 2]; geo[t * 4 + 1] = ratios_host[t * 2 + 1];
+        geo[t * 4 + 2] = offsets_host[t * 2]; geo[t * 4 + 3] = offsets_host[t * 2 + 1];
+    }
+    float* geo_dev = nullptr;
+    YDST_CUDA(cudaMalloc(&geo_dev, geo.size() * sizeof(float)));
+    try {
+        YDST_CUDA(cudaMemcpyAsync(geo_dev, geo.data(), geo.size() * sizeof(float), cudaMemcpyHostToDevice, S(stream)));
+        launch_window_boxes(pred_dev, tiles, rows, fields, geo_dev, S(stream));
+        count_launch();
+        YDST_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) { cudaFree(geo_dev); throw; }
+    cudaFree(geo_dev);
     YDST_API_END
 }
 
@@ -700,6 +734,15 @@ int ydst_resize_u8(const uint8_t* src_dev, int src_h, int src_w, uint8_t* dst_de
     launch_resize_u8(src_dev, src_h, src_w, dst_dev, dst_h, dst_w, swap_rb, S(stream));
     count_launch();
     YDST_CUDA(cudaStreamSynchronize(S(stream)));
+    YDST_API_END
+}
+int ydst_resize_u8_roi(const uint8_t* src_dev, int src_h, int src_w, int x0, int y0, int roi_w, int roi_h, uint8_t* dst_dev, int dst_h,
+                       int dst_w, int swap_rb, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(src_dev && dst_dev, "null argument");
+    YDST_CHECK(x0 >= 0 && y0 >= 0 && roi_w > 0 && roi_h > 0 && x0 + roi_w <= src_w && y0 + roi_h <= src_h, "the window leaves the frame");
+    launch_resize_u8(src_dev + ((size_t)y0 * src_w + x0) * 3, roi_h, roi_w, dst_dev, dst_h, dst_w, swap_rb, S(stream), (long long)src_w * 3);
+    count_launch();
     YDST_API_END
 }
 int ydst_pipeline_collect(ydst_pipeline* p, int32_t* out_host, int* k_host, float* dets_host, int* n_dets_host) {

@@ -580,7 +580,10 @@ void launch_lsap(const float* cost, int R, int C, float max_dist, int* col4row, 
     w.col4row = (int*)p; p += align16(sizeof(int) * R);
     w.SR = p; p += align16(R);
     w.SC = p;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};            // the shared-memory opt-in is a per-device attribute
+    int dev = 0;
+    YDST_CUDA(cudaGetDevice(&dev));
+    bool& attr_set = attr_set_dev[dev & 63];
     if (!attr_set) {
         YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

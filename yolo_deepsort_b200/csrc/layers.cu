@@ -729,21 +729,21 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
 // Whole-frame ingest (next to the hot path): the reader thread's BGR->RGB (yolo3/detect/video_detect.py:33-36) and
 // ImageDetector's cv2.resize(img, (W, H), INTER_LINEAR) (yolo3/detect/img_detect.py:70) on the device, with the same
 // fixed-point arithmetic as the crop kernel above (bit-exact against cv2 on every size tried, tests/test_gpu_ingest.py).
-__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh,
-                                                        int dw, int swap_rb) {
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, long long pitch,
+                                                        uint8_t* __restrict__ dst, int dh, int dw, int swap_rb) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)dh * dw) return;
     const int dx = (int)(idx % dw), dy = (int)(idx / dw);
     int v[3];
     if (sh == dh && sw == dw) {
-        const uint8_t* s = src + idx * 3;
+        const uint8_t* s = src + (long long)dy * pitch + dx * 3;
         v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
     } else {
         int xa, xb, a0, a1, ya, yb, b0, b1;
         axis_coeff(dx, dw, sw, true, xa, xb, a0, a1);
         axis_coeff(dy, dh, sh, false, ya, yb, b0, b1);
-        const uint8_t* r0 = src + (long long)ya * sw * 3;
-        const uint8_t* r1 = src + (long long)yb * sw * 3;
+        const uint8_t* r0 = src + (long long)ya * pitch;
+        const uint8_t* r1 = src + (long long)yb * pitch;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const int h0 = (int)r0[xa * 3 + c] * a0 + (int)r0[xb * 3 + c] * a1;
@@ -755,9 +755,27 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
     uint8_t* o = dst + idx * 3;
     o[0] = (uint8_t)(swap_rb ? v[2] : v[0]); o[1] = (uint8_t)v[1]; o[2] = (uint8_t)(swap_rb ? v[0] : v[2]);
 }
-void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st) {
+void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st, long long pitch) {
     YDST_CHECK(sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad resize geometry");
-    resize_u8_kernel<<<cdiv((long long)dh * dw, 256), 256, 0, st>>>(src, sh, sw, dst, dh, dw, swap_rb);
+    resize_u8_kernel<<<cdiv((long long)dh * dw, 256), 256, 0, st>>>(src, sh, sw, pitch > 0 ? pitch : (long long)sw * 3, dst, dh, dw, swap_rb);
+    YDST_CUDA(cudaGetLastError());
+}
+
+// Sliding-window mode (yolo3/detect/img_detect.py:126-134): per tile, xywh2p1p2 (model_build.py:317-323), resize_boxes (:12-19: the
+// python-float ratio multiplies the fp32 box), then the window offset is added -- same fp32 operations in the same order.
+__global__ void __launch_bounds__(256) window_boxes_kernel(float* __restrict__ pred, int tiles, int rows, int nf, const float* __restrict__ geo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)tiles * rows) return;
+    const int t = (int)(i / rows);
+    float* p = pred + i * nf;
+    const float rw = geo[t * 4 + 0], rh = geo[t * 4 + 1], ox = geo[t * 4 + 2], oy = geo[t * 4 + 3];
+    const float cx = p[0], cy = p[1], w = p[2], h = p[3];
+    const float x1 = cx - w / 2.f, y1 = cy - h / 2.f, x2 = cx + w / 2.f, y2 = cy + h / 2.f;
+    p[0] = __fadd_rn(__fmul_rn(x1, rw), ox); p[1] = __fadd_rn(__fmul_rn(y1, rh), oy);
+    p[2] = __fadd_rn(__fmul_rn(x2, rw), ox); p[3] = __fadd_rn(__fmul_rn(y2, rh), oy);
+}
+void launch_window_boxes(float* pred, int tiles, int rows, int nf, const float* geo_dev, cudaStream_t st) {
+    window_boxes_kernel<<<cdiv((long long)tiles * rows, 256), 256, 0, st>>>(pred, tiles, rows, nf, geo_dev);
     YDST_CUDA(cudaGetLastError());
 }
 

@@ -47,7 +47,8 @@ void launch_avgpool_l2(const Act& in, float* out, cudaStream_t st);
 // deep_sort/deep/feature_extractor.py:34-51).  frame: u8 HWC RGB; boxes: tlwh fp32 [m][4]; out fp32 NHWC [m][128][64][3].
 // err_flag (device int) is set to 1 if a box yields an empty crop (the reference raises there).
 // cv2.resize(u8 HWC, INTER_LINEAR) of a whole frame, optionally swapping R and B (BGR capture -> RGB); same size = (swapping) copy
-void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st);
+void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st, long long pitch = 0);
+void launch_window_boxes(float* pred, int tiles, int rows, int nf, const float* geo_dev, cudaStream_t st);   // geo: [tiles][4] = rw, rh, ox, oy
 void launch_crop_resize(const uint8_t* frame, int H, int W, const float* tlwh, int m, float* out, int* err_flag, cudaStream_t st);
 
 }  // namespace ydst

@@ -143,7 +143,10 @@ void run_plan(const Plan& plan, cudaStream_t st) {
     if (!plan.exec) {
         if (plan.runs++ == 0) { run_ops(plan, st); return; }             // first run eager: one-time attribute / driver-entry setup
         // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
-        static thread_local cudaStream_t cap = nullptr;
+        static thread_local cudaStream_t cap_dev[64] = {nullptr};          // one per device: a stream belongs to the device it was created on
+        int dev = 0;
+        YDST_CUDA(cudaGetDevice(&dev));
+        cudaStream_t& cap = cap_dev[dev & 63];
         if (!cap) YDST_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
         cudaGraph_t g = nullptr;
         YDST_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));

@@ -1,5 +1,5 @@
-// Detection post-processing for sm_100a: the single-image video path of soft_non_max_suppression
-// (yolo3/utils/model_build.py:52-137; merge=False, multi_label, class-offset trick) plus the
+// Detection post-processing for sm_100a: soft_non_max_suppression (yolo3/utils/model_build.py:52-137; multi_label,
+// class-offset trick; the options of the sliding-window mode -- is_p1p2, merge -- and classes / agnostic included) plus the
 // box hand-off to the tracker (resize_boxes :12-19, p1p2Toxywh :326-332, class mask
 // yolo3/detect/video_detect.py:138-147).  Integer/index results are bit-exact with the reference
 // given identical fp32 predictions: same fp32 operations, same strict comparisons, stable
@@ -10,7 +10,7 @@ namespace ydst {
 
 // ---- 1. candidates: obj > thr, then every class with obj*cls > thr (row-major (row, class) key) ----
 __global__ void nms_collect_kernel(const float* __restrict__ pred, int rows, int nf, float conf, NmsCand* __restrict__ cand,
-                                   int cap, int* __restrict__ count) {
+                                   int cap, int* __restrict__ count, NmsOptions opt) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const int img = blockIdx.y;
@@ -19,10 +19,14 @@ __global__ void nms_collect_kernel(const float* __restrict__ pred, int rows, int
     const float obj = p[4];
     if (!(obj > conf)) return;
     const float cx = p[0], cy = p[1], w = p[2], h = p[3];
-    const float x1 = cx - w / 2.f, y1 = cy - h / 2.f, x2 = cx + w / 2.f, y2 = cy + h / 2.f;
+    // is_p1p2: the four fields already are corners (model_build.py:90-93)
+    const float x1 = opt.p1p2 ? cx : cx - w / 2.f, y1 = opt.p1p2 ? cy : cy - h / 2.f;
+    const float x2 = opt.p1p2 ? w : cx + w / 2.f, y2 = opt.p1p2 ? h : cy + h / 2.f;
     const int nc = nf - 5;
     for (int j = 0; j < nc; ++j) {
         const float s = p[5 + j] * obj;
+        // `classes`: keep only the listed class ids (model_build.py:103-105)
+        if (opt.use_classes && !((opt.class_bits[(j >> 6) & 3] >> (j & 63)) & 1ull)) continue;
         if (s > conf) {
             const int slot = atomicAdd(count, 1);
             if (slot < cap) {
@@ -63,14 +67,14 @@ __global__ void nms_rank_kernel(const NmsCand* __restrict__ cand, const int* __r
 
 // ---- 3. suppression bitmask on class-offset boxes (boxes + cls*4096 in fp32, as the reference does) ----
 __global__ void nms_mask_kernel(const NmsCand* __restrict__ sorted, const int* __restrict__ count, int cap, float iou_thr,
-                                unsigned long long* __restrict__ mask, int words) {
+                                unsigned long long* __restrict__ mask, int words, float off_mul) {
     const int img = blockIdx.y;
     sorted += (long long)img * cap; count += img * 8; mask += (long long)img * cap * words;
     const int n = min(*count, cap);
     const int i = blockIdx.x;                 // row
     if (i >= n) return;
     const NmsCand a = sorted[i];
-    const float off_a = a.cls * 4096.f;
+    const float off_a = a.cls * off_mul;                 // 4096, or 0 when agnostic (model_build.py:117)
     const float ax1 = a.x1 + off_a, ay1 = a.y1 + off_a, ax2 = a.x2 + off_a, ay2 = a.y2 + off_a;
     const float area_a = (ax2 - ax1) * (ay2 - ay1);
     const int nw = (n + 63) >> 6;              // words beyond the candidate count are never read by the sweep
@@ -80,7 +84,7 @@ __global__ void nms_mask_kernel(const NmsCand* __restrict__ sorted, const int* _
             const int j = w * 64 + b;
             if (j <= i || j >= n) continue;
             const NmsCand c = sorted[j];
-            const float off_c = c.cls * 4096.f;
+            const float off_c = c.cls * off_mul;
             const float bx1 = c.x1 + off_c, by1 = c.y1 + off_c, bx2 = c.x2 + off_c, by2 = c.y2 + off_c;
             const float area_b = (bx2 - bx1) * (by2 - by1);
             const float iw = fmaxf(0.f, fminf(ax2, bx2) - fmaxf(ax1, bx1));
@@ -146,6 +150,71 @@ __global__ void __launch_bounds__(256) nms_sweep_kernel(const NmsCand* __restric
     }
 }
 
+// ---- 4b. "Merge NMS" exactly as the reference executes it (model_build.py:122-131), quirks included ----
+// The reference calls its ELEMENTWISE bbox_iou(boxes[i], boxes) (model_build.py:354-381: (n,4) x (n,4) -> (n,), "+1" areas,
+// eps 1e-16) where ultralytics has the pairwise box_iou.  With k kept rows out of n candidates that line
+//   * raises inside the bare try/except unless the shapes broadcast, i.e. unless k == n or k == 1: nothing is merged and the
+//     `redundant` filter never runs (the exception is swallowed, model_build.py:129-131);
+//   * k == n: pairs kept row j (score order) with candidate j (row-major candidate order), weights_j = (iou_j > thr) * score_j is
+//     a (1,n) row, torch.mm gives ONE (1,4) weighted mean box, which the broadcast assignment x[i, :4] = ... writes into EVERY
+//     kept row; then iou.sum(1) raises (1-D tensor) and is swallowed;
+//   * k == 1: the kept box against all n candidates -- the one case that does what "merge" promises -- same assignment, same
+//     swallowed exception.
+// Only applies for 1 < n < 3000 (:122).  fp32 sums here, torch.mm there: equal to rounding (summation order).
+__global__ void __launch_bounds__(256) nms_merge_kernel(const NmsCand* __restrict__ sorted, const int* __restrict__ count, int cap,
+                                                        float iou_thr, float off_mul, int max_det, float* __restrict__ dets,
+                                                        const int* __restrict__ n_out) {
+    __shared__ int order[1024];                // candidate (key) order -> index into sorted[], k == n case (n <= max_det <= 1024)
+    __shared__ float red[5][8];
+    const int img = blockIdx.x;
+    sorted += (long long)img * cap; count += img * 8; dets += (long long)img * max_det * 6; n_out += img * 8;
+    const int total = *count;
+    const int n = min(total, cap), k = *n_out;
+    if (!(total > 1 && total < 3000) || total > cap) return;
+    if (k != n && k != 1) return;
+    const bool all = k == n && k != 1;
+    if (all) {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            int rank = 0;
+            const int key = sorted[t].key;
+            for (int u = 0; u < n; ++u) rank += sorted[u].key < key ? 1 : 0;
+            order[rank] = t;
+        }
+    }
+    __syncthreads();
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const NmsCand a = all ? sorted[j] : sorted[0];            // kept row j | the single kept row
+        const NmsCand b = all ? sorted[order[j]] : sorted[j];     // candidate j
+        const float oa = a.cls * off_mul, ob = b.cls * off_mul;
+        const float ax1 = a.x1 + oa, ay1 = a.y1 + oa, ax2 = a.x2 + oa, ay2 = a.y2 + oa;
+        const float bx1 = b.x1 + ob, by1 = b.y1 + ob, bx2 = b.x2 + ob, by2 = b.y2 + ob;
+        const float iw = fmaxf(fminf(ax2, bx2) - fmaxf(ax1, bx1) + 1.f, 0.f);
+        const float ih = fmaxf(fminf(ay2, by2) - fmaxf(ay1, by1) + 1.f, 0.f);
+        const float inter = iw * ih;
+        const float area_a = (ax2 - ax1 + 1.f) * (ay2 - ay1 + 1.f), area_b = (bx2 - bx1 + 1.f) * (by2 - by1 + 1.f);
+        const float iou = inter / (area_a + area_b - inter + 1e-16f);
+        const float w = iou > iou_thr ? b.score : 0.f;
+        acc[0] += w; acc[1] += w * b.x1; acc[2] += w * b.y1; acc[3] += w * b.x2; acc[4] += w * b.y2;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        float v = acc[f];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[f][wid] = v;
+    }
+    __syncthreads();
+    float tot[5];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[f][w];
+        tot[f] = v;
+    }
+    for (int e = threadIdx.x; e < k * 4; e += blockDim.x) dets[(e >> 2) * 6 + (e & 3)] = tot[1 + (e & 3)] / tot[0];   // 0/0 = NaN, as torch
+}
+
 // ---- 5. hand-off: resize_boxes, xyxy -> tlwh, class mask; order preserved (one block, ballot scan) ----
 __global__ void __launch_bounds__(1024) dets_to_tracks_kernel(const float* __restrict__ dets, const int* __restrict__ n_dets, NmsRatios ratios,
                                                               int max_det, const int* __restrict__ class_mask, int n_mask,
@@ -196,21 +265,32 @@ void Nms::destroy() {
     cand = sorted = nullptr; mask = nullptr; counters = nullptr; dets = nullptr;
 }
 // counters (per image, stride 8): [0] candidate count, [1] n_out, [2] overflow flag, [3] m (tracker inputs)
-void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaStream_t st, int nb) {
+void Nms::run(const float* pred, int rows, int nf, float conf, float iou, cudaStream_t st, int nb, const NmsOptions* options) {
     YDST_CHECK(nb >= 1 && nb <= batch, "nms over %d images, capacity %d", nb, batch);
+    NmsOptions opt{};
+    if (options) opt = *options;
+    const float off_mul = opt.agnostic ? 0.f : 4096.f;
     YDST_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 8 * nb, st));
-    nms_collect_kernel<<<dim3((rows + 255) / 256, nb), 256, 0, st>>>(pred, rows, nf, conf, cand, cap, counters);
+    nms_collect_kernel<<<dim3((rows + 255) / 256, nb), 256, 0, st>>>(pred, rows, nf, conf, cand, cap, counters, opt);
     nms_rank_kernel<<<dim3(cap / 256 > 0 ? cap / 256 : 1, nb), 256, 0, st>>>(cand, counters, cap, sorted);
-    nms_mask_kernel<<<dim3(cap, nb), 64, 0, st>>>(sorted, counters, cap, iou, mask, words);
-    static bool attr_set = false;
+    nms_mask_kernel<<<dim3(cap, nb), 64, 0, st>>>(sorted, counters, cap, iou, mask, words, off_mul);
+    // the dynamic shared memory opt-in is a per-device attribute of the kernel
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    YDST_CUDA(cudaGetDevice(&dev));
     const int sweep_smem = kSweepSmemRows * (kSweepSmemRows / 64) * (int)sizeof(unsigned long long);
-    if (!attr_set) {
+    if (!attr_set[dev & 63]) {
         YDST_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     nms_sweep_kernel<<<nb, 256, sweep_smem, st>>>(sorted, counters, cap, mask, words, max_det, dets, counters + 1, counters + 2);
+    int launches = 4;
+    if (opt.merge) {
+        nms_merge_kernel<<<nb, 256, 0, st>>>(sorted, counters, cap, iou, off_mul, max_det, dets, counters + 1);
+        ++launches;
+    }
     YDST_CUDA(cudaGetLastError());
-    count_launch(4);
+    count_launch(launches);
 }
 void Nms::to_tracker_inputs_batch(const NmsRatios& r, int nb, const int* class_mask_dev, int n_mask, float* tlwh, float* conf, float* cls,
                                   cudaStream_t st) {

@@ -206,18 +206,19 @@ class Darknet:
 
 
 def soft_non_max_suppression(prediction, conf_thres=0.1, iou_thres=0.6, merge=False, classes=None, agnostic=False, is_p1p2=False):
-    """yolo3/utils/model_build.py:52-137 for the configuration the video path uses (merge=False, all classes,
-    class-aware, xywh input).  Returns a list with one (n,6) tensor [x1,y1,x2,y2,conf,cls] (or None) per image."""
-    if merge or classes or agnostic or is_p1p2:
-        raise NotImplementedError("only the video-path configuration of soft_non_max_suppression is accelerated")
+    """yolo3/utils/model_build.py:52-137 with all of its keyword options (the video path uses none; the sliding-window mode
+    passes merge=True, is_p1p2=True).  `merge` behaves exactly as the reference's block executes, see csrc/nms.cu.
+    Returns a list with one (n,6) tensor [x1,y1,x2,y2,conf,cls] (or None) per image."""
     prediction = prediction.float().contiguous()
+    cls = np.ascontiguousarray(classes, dtype=np.int32) if classes else None
     out = []
     for x in prediction:
         dets = torch.empty((300, 6), dtype=torch.float32, device=x.device)
         n = ctypes.c_int()
         with torch.cuda.device(x.device):
-            check(lib().ydst_nms(ptr(x), x.shape[0], x.shape[1], float(conf_thres), float(iou_thres), ptr(dets), ctypes.byref(n),
-                                 stream_ptr()))
+            check(lib().ydst_nms_ex(ptr(x), x.shape[0], x.shape[1], float(conf_thres), float(iou_thres), int(bool(merge)), int(bool(is_p1p2)),
+                                    int(bool(agnostic)), cls.ctypes.data if cls is not None else None, 0 if cls is None else int(cls.size),
+                                    ptr(dets), ctypes.byref(n), stream_ptr()))
         out.append(dets[:n.value].clone() if n.value else None)
     return out
 
