@@ -117,6 +117,7 @@ static std::vector<OpSample> g_samples;
 void profile_begin() { g_profiling = true; g_samples.clear(); }
 bool profile_active() { return g_profiling; }
 std::vector<OpSample>& profile_samples() { g_profiling = false; return g_samples; }
+void profile_push(const OpSample& s) { g_samples.push_back(s); }
 
 // algorithmic bytes of one conv: activations in + out (fp16, logical dims) + weights
 static double conv_bytes(const ConvTcLaunch& L) {

@@ -65,6 +65,10 @@ struct OpSample { int kind; int layer; double flops; double bytes; cudaEvent_t e
 void profile_begin();
 bool profile_active();
 std::vector<OpSample>& profile_samples();
+void profile_push(const OpSample& s);
+// OpSample.kind of the association kernels (tracker.cu), next to the OpKind values of the layer graphs
+enum TrackerOpKind { TOP_KF_PREDICT = 100, TOP_NORMALIZE, TOP_FILL, TOP_COSINE_MIN, TOP_COST_FINALIZE, TOP_LSAP, TOP_IOU_COST, TOP_KF_UPDATE,
+                     TOP_KF_INITIATE, TOP_GALLERY_APPEND, TOP_GATHER, TOP_TRANSPOSE };
 
 class Detector {
 public:

@@ -10,6 +10,7 @@
 // decides new ids) is a few hundred integer operations per frame and stays on the host, fed by the
 // assignment result (two small D2H copies per frame).
 #include "tracker.cuh"
+#include "net.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -35,6 +36,24 @@ __global__ void cls_to_int_kernel(const float* __restrict__ cls, int m, int* __r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) out[i] = (int)cls[i];
 }
+
+// per-kernel CUDA-event sample while ydst_profile_begin() is active (bench.py --config assoc: roofline objects per kernel)
+struct TrkProf {
+    OpSample s{};
+    cudaStream_t st;
+    bool on;
+    TrkProf(int kind, double bytes, double flops, cudaStream_t st_) : st(st_), on(profile_active()) {
+        if (!on) return;
+        s.kind = kind; s.layer = -1; s.flops = flops; s.bytes = bytes;
+        cudaEventCreate(&s.e0); cudaEventCreate(&s.e1);
+        cudaEventRecord(s.e0, st);
+    }
+    ~TrkProf() {
+        if (!on) return;
+        cudaEventRecord(s.e1, st);
+        profile_push(s);
+    }
+};
 
 Tracker::Tracker(double max_dist, double max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets)
     : max_dist_(max_dist), max_iou_(max_iou), max_age_(max_age), n_init_(n_init), budget_(budget), cap_t_(cap_tracks), cap_d_(cap_dets) {
@@ -84,8 +103,8 @@ Tracker::Assign Tracker::solve(const float* cost, const std::vector<int>& tis, c
     const bool transposed = nd < nt;
     const int R = transposed ? nd : nt, C = transposed ? nt : nd;
     const float* c = cost;
-    if (transposed) { launch_transpose(cost, cost_t_, nt, nd, st); c = cost_t_; }
-    launch_lsap(c, R, C, max_dist, col4row_, over_, lsap_work_, st);
+    if (transposed) { TrkProf pr(TOP_TRANSPOSE, 8.0 * nt * nd, 0, st); launch_transpose(cost, cost_t_, nt, nd, st); c = cost_t_; }
+    { TrkProf pr(TOP_LSAP, 4.0 * R * C, 0, st); launch_lsap(c, R, C, max_dist, col4row_, over_, lsap_work_, st); }
     launches_last += transposed ? 2 : 1;
     YDST_CUDA(cudaMemcpyAsync(h_res_, col4row_, R * sizeof(int), cudaMemcpyDeviceToHost, st));
     YDST_CUDA(cudaMemcpyAsync(h_res_ + R, over_, R * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -144,11 +163,11 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
     if (n > 0) {
         std::vector<int> slots(n);
         for (int i = 0; i < n; ++i) slots[i] = tracks[i].slot;
-        launch_kf_predict(mean_, cov_, upload(slots, st), n, st);
+        { int* d_s = upload(slots, st); TrkProf pr(TOP_KF_PREDICT, 576.0 * n, 0, st); launch_kf_predict(mean_, cov_, d_s, n, st); }
         ++launches_last;
         for (auto& t : tracks) { t.age += 1; t.tsu += 1; }
     }
-    if (m > 0) { launch_normalize_rows(feat, det_n_, m, st); ++launches_last; }
+    if (m > 0) { TrkProf pr(TOP_NORMALIZE, 4096.0 * m, 0, st); launch_normalize_rows(feat, det_n_, m, st); ++launches_last; }
 
     // ---- match (tracker.py:56-93) ----
     std::vector<int> confirmed, unconfirmed, all_dets(m);
@@ -169,9 +188,11 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         int* d_slots = upload(slots, st);
         int* d_rp = upload(row_ptr, st);
         int* d_rt = upload(row_track, st);
-        launch_fill_i32(cost_enc_, 0x7f800000, (long long)na * m, st);
-        launch_cosine_min(gallery_, d_rp, d_rt, G, det_n_, m, cost_enc_, st);
-        launch_cost_finalize(cost_enc_, mean_, cov_, d_slots, na, tlwh, m, max_dist_, cost_, st);
+        { TrkProf pr(TOP_FILL, 4.0 * na * m, 0, st); launch_fill_i32(cost_enc_, 0x7f800000, (long long)na * m, st); }
+        { TrkProf pr(TOP_COSINE_MIN, 2048.0 * G + 2048.0 * m + 4.0 * na * m, 2.0 * G * (double)m * kFeat, st);
+          launch_cosine_min(gallery_, d_rp, d_rt, G, det_n_, m, cost_enc_, st); }
+        { TrkProf pr(TOP_COST_FINALIZE, 8.0 * na * m + 288.0 * na + 16.0 * m, 0, st);
+          launch_cost_finalize(cost_enc_, mean_, cov_, d_slots, na, tlwh, m, max_dist_, cost_, st); }
         launches_last += 3;
         A = solve(cost_, confirmed, all_dets, (float)max_dist_, st);
     }
@@ -188,7 +209,7 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         int* d_slots = upload(slots, st);
         int* d_tsu = upload(tsu, st);
         int* d_dets = upload(A.um_d, st);
-        launch_iou_cost(mean_, d_slots, d_tsu, nb, tlwh, d_dets, mb, max_iou_, cost_, st);
+        { TrkProf pr(TOP_IOU_COST, 4.0 * nb * mb + 32.0 * nb + 16.0 * mb, 0, st); launch_iou_cost(mean_, d_slots, d_tsu, nb, tlwh, d_dets, mb, max_iou_, cost_, st); }
         ++launches_last;
         B = solve(cost_, iou_cand, A.um_d, (float)max_iou_, st);
     }
@@ -217,7 +238,8 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
             if (t.state == TRACK_TENTATIVE && t.hits >= n_init_) t.state = TRACK_CONFIRMED;
             t.payload = payload[matches[i].second];
         }
-        launch_kf_update(mean_, cov_, upload(slots, st), tlwh, upload(dets, st), (int)matches.size(), st);
+        { int* d_s = upload(slots, st); int* d_d = upload(dets, st); TrkProf pr(TOP_KF_UPDATE, 592.0 * matches.size(), 0, st);
+          launch_kf_update(mean_, cov_, d_s, tlwh, d_d, (int)matches.size(), st); }
         ++launches_last;
     }
     // ---- mark missed (track.py:146-152) ----
@@ -239,12 +261,14 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
             slots.push_back(slot); dets.push_back(d);
             app_src.push_back(d); app_dst.push_back(slot * budget_ + 0);
         }
-        launch_kf_initiate(tlwh, upload(dets, st), mean_, cov_, upload(slots, st), (int)slots.size(), st);
+        { int* d_d = upload(dets, st); int* d_s = upload(slots, st); TrkProf pr(TOP_KF_INITIATE, 304.0 * slots.size(), 0, st);
+          launch_kf_initiate(tlwh, d_d, mean_, cov_, d_s, (int)slots.size(), st); }
         ++launches_last;
     }
     if (!app_src.empty()) {
-        gallery_append_kernel<<<(unsigned)app_src.size(), 128, 0, st>>>(det_n_, upload(app_src, st), gallery_, upload(app_dst, st),
-                                                                      (int)app_src.size());
+        int* d_src = upload(app_src, st); int* d_dst = upload(app_dst, st);
+        TrkProf pr(TOP_GALLERY_APPEND, 4096.0 * app_src.size(), 0, st);
+        gallery_append_kernel<<<(unsigned)app_src.size(), 128, 0, st>>>(det_n_, d_src, gallery_, d_dst, (int)app_src.size());
         YDST_CUDA(cudaGetLastError());
         ++launches_last;
     }
