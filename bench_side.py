@@ -237,7 +237,8 @@ def run_assoc(args):
     rank, world = B.dist_init("nccl")
     K, Wm = (args.steps or 8), ASSOC_WARM
     L = lib()
-    n_frames = Wm + 4 + 2 * 64
+    max_windows = max(2, 160 // K)                           # the crowd never rewinds: every timed update sees a fresh frame
+    n_frames = Wm + 2 + 4 + 2 * max_windows * K
     frames = assoc_frames(n, n_frames, seed=rank)
     trk = TrackerHandle(device=str(device), cap_tracks=4096, cap_dets=2048, **{"max_dist": 0.3, "max_iou_distance": 0.7, "max_age": 30, "n_init": 3, "nn_budget": 30})
     dev = [(torch.from_numpy(tl).to(device), torch.from_numpy(ft).to(device)) for tl, ft, _ in frames]
@@ -247,12 +248,12 @@ def run_assoc(args):
 
     def steps_dev(k):
         for _ in range(k):
-            tl, ft = dev[state["t"] % n_frames]
+            tl, ft = dev[state["t"]]
             state["rows"].append(trk.update(tl, ft, cls)); state["t"] += 1
 
     def steps_host(k):
         for _ in range(k):
-            tl, ft = host[state["t"] % n_frames]
+            tl, ft = host[state["t"]]
             state["rows"].append(trk.update(tl.to(device, non_blocking=True), ft.to(device, non_blocking=True), cls)); state["t"] += 1
 
     steps_dev(Wm)                                            # galleries fill up to their 30 rows
@@ -265,9 +266,9 @@ def run_assoc(args):
     clocks.start()
     launches0 = L.ydst_launch_count()
     t_before = state["t"]
-    wins, _ = B.timed_windows(steps_dev, K, args.min_seconds, device, max_windows=16)
+    wins, _ = B.timed_windows(steps_dev, K, args.min_seconds, device, max_windows=max_windows)
     launches = (L.ydst_launch_count() - launches0) / max(1, state["t"] - t_before)
-    wins_e, _ = B.timed_windows(steps_host, K, args.min_seconds, device, max_windows=16)
+    wins_e, _ = B.timed_windows(steps_host, K, args.min_seconds, device, max_windows=max_windows)
     clocks.stop()
     st, value, ms_step = B.window_stats(wins, K, world)
     ste, value_e, ms_step_e = B.window_stats(wins_e, K, world)

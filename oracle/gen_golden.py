@@ -9,7 +9,11 @@ Golden files (small, committed):
   kalman_batch.npz    seeded KalmanFilter.initiate/predict/update/gating_distance in/out
   assoc_seq.npz       24-frame DeepSort.update sequence with an injected extractor: per-frame inputs
                       (boxes, features, class ids) and the reference's (K,6) int32 outputs + track tables
+  assoc_seq2.npz      44 frames with nn_budget=4, max_age=3, n_init=2: gallery FIFO truncation, deletion by age, re-identification
   tiny416.npz         yolov3-tiny 416: head outputs digest, soft_non_max_suppression output, one frame
+  yolov4_tiny_416.npz, yolov4_416.npz   the same for the grouped-route and the Mish / SPP / shortcut architectures
+  video_detector.npz  the reference's own VideoDetector loop (skip_frames=2, tracker, overlay) on a lossless clip: held rows and
+                      image digests per frame
   reid.npz            Extractor features for boxes on one frame (crop + cv2.resize + Net)
   overlay.npz         LabelDrawer.draw_labels_by_trackers / draw_labels output (images and digests) on two synthetic frames
   window.npz          ImageDetector.detect in sliding-window mode (win_size, overlap; batched tiles + merge-NMS) on a 700x1000
@@ -91,12 +95,10 @@ def gen_kalman():
     _eq(S.kf_gating_position(mean3, cov3, torch.from_numpy(dets)), gate2, "gating (position only)")
 
 
-def gen_assoc():
+def _assoc_sequence(name, sc, n_frames, kw):
     from deep_sort import DeepSort
     from . import sort_ref as S
-    from .synth import Scenario
-    sc = Scenario(n=40, seed=3, p_miss=0.08, p_new=0.03, p_leave=0.02)
-    frames = [sc.step() for _ in range(24)]
+    frames = [sc.step() for _ in range(n_frames)]
     feats_now = {}
 
     class Inject:                                    # extractor injection point, deep_sort/deep_sort.py:28-31
@@ -104,10 +106,11 @@ def gen_assoc():
             return torch.from_numpy(feats_now["f"])
 
     frame_img = np.zeros((608, 608, 3), np.uint8)
-    kw = dict(max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
     ref = DeepSort(Inject(), min_confidence=1, use_cuda=False, **kw)
     orc = S.DeepSortRef(lambda fr, tl: torch.from_numpy(feats_now["f"]), **kw)
     out = {}
+    stats = dict(max_tracks=0, deleted=0, rows=0, budget_hit=0)
+    seen = set()
     for t, (tl, ft, cl) in enumerate(frames):
         ft = ft.astype(np.float16).astype(np.float32)      # stored as fp16 in the fixture: keep it lossless
         feats_now["f"] = ft
@@ -123,12 +126,30 @@ def gen_assoc():
         if len(trk):
             _eq(st["mean"], torch.cat([k.mean for k in trk], 0).numpy(), f"track means frame {t}")
             _eq(st["cov"], torch.cat([k.covariance for k in trk], 0).numpy(), f"track covs frame {t}")
+        ids = set(int(k.track_id) for k in trk)
+        stats["deleted"] += len(seen - ids)
+        seen = ids
+        stats["max_tracks"] = max(stats["max_tracks"], len(trk)); stats["rows"] += len(r)
+        stats["budget_hit"] += sum(1 for v in ref.tracker.metric.samples.values() if len(v) >= kw["nn_budget"])
         out[f"tlwh_{t}"], out[f"feat_{t}"], out[f"cls_{t}"] = tl, ft.astype(np.float16), cl
         out[f"out_{t}"], out[f"table_{t}"] = r, tab
         out[f"mean_{t}"] = st["mean"]
     out["n_frames"] = np.int32(len(frames))
     out["params"] = np.array([kw["max_dist"], kw["max_iou_distance"], kw["max_age"], kw["n_init"], kw["nn_budget"]], np.float64)
-    np.savez_compressed(os.path.join(GOLD, "assoc_seq.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(f"  {name}: {stats}")
+    return stats
+
+
+def gen_assoc():
+    from .synth import Scenario
+    _assoc_sequence("assoc_seq.npz", Scenario(n=40, seed=3, p_miss=0.08, p_new=0.03, p_leave=0.02), 24,
+                    dict(max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30))
+    # second sequence: a tiny budget and a short life, so that the FIFO truncation of the galleries (nn_matching.py:153-154), the
+    # deletion by age (track.py:146-152) and re-identification after misses are all inside what the unmodified reference pins
+    st = _assoc_sequence("assoc_seq2.npz", Scenario(n=24, seed=9, p_miss=0.25, p_new=0.06, p_leave=0.04), 44,
+                         dict(max_dist=0.3, max_iou_distance=0.7, max_age=3, n_init=2, nn_budget=4))
+    assert st["deleted"] > 10 and st["budget_hit"] > 50, st
 
 
 def gen_tiny():
@@ -162,6 +183,96 @@ def gen_tiny():
     np.savez_compressed(os.path.join(GOLD, "tiny416.npz"), frame_seed=np.int32(0), weight_seed=np.int32(0),
                         pred_top_idx=sel.astype(np.int32), pred_top=pred[0, sel].numpy(), dets=dets.numpy(),
                         pred_sha256=np.frombuffer(hashlib.sha256(pred.numpy().tobytes()).digest(), np.uint8))
+
+
+def gen_other_cfgs():
+    """yolov4-tiny 416 (grouped routes) and yolov4 416 (Mish, SPP 5/9/13 max-pools, shortcuts, PAN routes): forward digest and
+    soft_non_max_suppression output of the unmodified reference, on seeded weights with calibrated heads."""
+    from yolo3.models import Darknet
+    from yolo3.utils.model_build import soft_non_max_suppression
+    from . import darknet_ref as D
+    from .synth import make_frame, darknet_weights, frame_to_input
+    for name in ("yolov4-tiny", "yolov4"):
+        cfg = os.path.join(CFG_DIR, name + ".cfg")
+        blocks = D.parse_cfg(cfg)
+        frames = [make_frame(416, 416, seed=s) for s in (6, 7)]
+        ws, info = darknet_weights(blocks, frames, seed=2, target=40)
+        with tempfile.TemporaryDirectory() as td:
+            wpath = os.path.join(td, "w.weights")
+            D.write_weights(wpath, blocks, ws)
+            model = Darknet(cfg, img_size=(416, 416))
+            model.load_darknet_weights(wpath)
+            model.eval()
+        x = frame_to_input(frames[0])
+        with torch.no_grad():
+            pred = model(x)
+            dets = soft_non_max_suppression(pred.clone(), 0.5, 0.4)[0]
+        op = D.forward(blocks, ws, x)
+        _eq(op, pred, f"Darknet.forward {name} 416")
+        od = D.postprocess(op[0].numpy(), 0.5, 0.4)
+        _eq(od, dets.numpy(), f"soft_non_max_suppression {name} ({len(od)} detections)")
+        sel = np.argsort(-pred[0, :, 4].numpy(), kind="stable")[:256]
+        np.savez_compressed(os.path.join(GOLD, name.replace("-", "_") + "_416.npz"), frame_seeds=np.asarray([6, 7], np.int32),
+                            weight_seed=np.int32(2), pred_top_idx=sel.astype(np.int32), pred_top=pred[0, sel].numpy(), dets=dets.numpy(),
+                            pred_sha256=np.frombuffer(hashlib.sha256(pred.numpy().tobytes()).digest(), np.uint8))
+
+
+def video_fixture(td):
+    """Files of the VideoDetector fixture: a 9-frame FFV1 clip of one held 416x416 scene, yolov3-tiny weights calibrated on it, a ReID
+    checkpoint and a names file.  Returns (cfg, blocks, ws, sd, paths, clip)."""
+    import cv2
+    from . import darknet_ref as D
+    from .synth import darknet_weights, make_frame, reid_state_dict
+    cfg = os.path.join(CFG_DIR, "yolov3-tiny.cfg")
+    blocks = D.parse_cfg(cfg)
+    scenes = [make_frame(416, 416, seed=s) for s in (0, 1)]
+    ws, _ = darknet_weights(blocks, scenes, seed=0, target=50)
+    sd = reid_state_dict(seed=0)
+    paths = {k: os.path.join(td, v) for k, v in (("weights", "tiny.weights"), ("ckpt", "ckpt.t7"), ("names", "coco.names"), ("video", "clip.avi"))}
+    D.write_weights(paths["weights"], blocks, ws)
+    torch.save({"net_dict": sd, "acc": 0.0, "epoch": 0}, paths["ckpt"])
+    with open(paths["names"], "w") as fh:
+        fh.write("\n".join(f"c{i}" for i in range(80)) + "\n")
+    clip = [scenes[0]] * 9
+    wr = cv2.VideoWriter(paths["video"], cv2.VideoWriter_fourcc(*"FFV1"), 25, (416, 416))
+    assert wr.isOpened()
+    for f in clip:
+        wr.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    wr.release()
+    return cfg, blocks, ws, sd, paths, clip
+
+
+def gen_video():
+    """The reference's own VideoDetector loop (yolo3/detect/video_detect.py:78-208) with video_deepsort.py's keyword arguments
+    (skip_frames=2 among them) on a lossless clip: per frame the held rows and the digest of the yielded image (overlay drawn)."""
+    from deep_sort import DeepSort
+    from yolo3.detect.video_detect import VideoDetector
+    from yolo3.models import Darknet
+    from . import darknet_ref as D, reid_ref as R, sort_ref as S
+    with tempfile.TemporaryDirectory() as td:
+        cfg, blocks, ws, sd, paths, clip = video_fixture(td)
+        model = Darknet(cfg, img_size=(416, 416))
+        model.load_darknet_weights(paths["weights"])
+        tracker = DeepSort(paths["ckpt"], min_confidence=1, use_cuda=False, nn_budget=30, n_init=3, max_iou_distance=0.7, max_dist=0.3, max_age=30)
+        vd = VideoDetector(model, paths["names"], thickness=2, skip_frames=2, thres=0.5, class_mask=[0, 2, 4], nms_thres=0.4, tracker=tracker,
+                           half=False)
+        out = {}
+        orc = S.DeepSortRef(lambda fr, tl: R.extract(sd, fr, tl), max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
+        held = None
+        n = 0
+        for t, (image, rows, actions) in enumerate(vd.detect(paths["video"], real_show=False, skip_secs=0, show_fps=False)):
+            rows = np.asarray(rows, np.int32).reshape(-1, 6)
+            if t % 2 == 0:                                # the oracle steps on the frames the reference loop detects on
+                det = D.detect(blocks, ws, clip[t], (416, 416), 0.5, 0.4)
+                tlwh, conf, cls = D.to_tracker_inputs(det, [0, 2, 4])
+                held = np.asarray(orc.update(tlwh, conf, clip[t], torch.from_numpy(cls)), np.int32).reshape(-1, 6)
+            _eq(held, rows, f"VideoDetector frame {t} ({len(rows)} rows held)")
+            out[f"rows_{t}"] = rows
+            out[f"image_sha256_{t}"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(image).tobytes()).digest(), np.uint8)
+            n += 1
+        assert n == len(clip)
+        out["n_frames"] = np.int32(n)
+        np.savez_compressed(os.path.join(GOLD, "video_detector.npz"), **out)
 
 
 def gen_reid():
@@ -303,7 +414,7 @@ def main():
     ref_shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_reid, gen_window, gen_overlay):
+    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_other_cfgs, gen_reid, gen_window, gen_overlay, gen_video):
         print(fn.__name__)
         fn()
     print("golden vectors written to", GOLD)

@@ -203,10 +203,13 @@ def run_tracker_sequence(frames, params, expect_out, expect_tab, expect_mean=Non
             np.testing.assert_allclose(mean, expect_mean[t], rtol=1e-4, atol=1e-3, err_msg=f"frame {t}: track means")
 
 
-def test_tracker_golden_sequence():
-    """24 frames of DeepSort.update produced by the UNMODIFIED reference: identical (K,6) int32 rows (track ids, class ids,
-    truncated boxes) and identical [id,hits,age,tsu,state] tables every frame."""
-    g = np.load(os.path.join(GOLDEN, "assoc_seq.npz"))
+@pytest.mark.parametrize("name", ["assoc_seq.npz", "assoc_seq2.npz"])
+def test_tracker_golden_sequence(name):
+    """DeepSort.update sequences produced by the UNMODIFIED reference: identical (K,6) int32 rows (track ids, class ids,
+    truncated boxes) and identical [id,hits,age,tsu,state] tables every frame.  assoc_seq: 24 frames, demo parameters;
+    assoc_seq2: 44 frames with nn_budget=4, max_age=3, n_init=2 -- gallery FIFO truncation (nn_matching.py:153-154), deletion by
+    age (track.py:146-152) and re-identification after misses."""
+    g = np.load(os.path.join(GOLDEN, name))
     T = int(g["n_frames"])
     frames = [(g[f"tlwh_{t}"], g[f"feat_{t}"].astype(np.float32), g[f"cls_{t}"]) for t in range(T)]
     run_tracker_sequence(frames, g["params"], [g[f"out_{t}"] for t in range(T)], [g[f"table_{t}"] for t in range(T)],

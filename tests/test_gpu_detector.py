@@ -201,3 +201,30 @@ def test_other_cfgs_forward(name, size):
     drift = max(1.0, worst / 2e-2)
     assert np.median(d[..., 4:]) < 1e-3 * drift and np.median(d[..., :4]) < 0.05 * drift
     assert np.median(dl) < 2e-2 * drift * max(1.0, logit(ref[..., 4]).std())
+
+
+@pytest.mark.parametrize("name", ["yolov4-tiny", "yolov4"])
+def test_other_architectures_match_reference_golden(name):
+    """tests/golden/yolov4_tiny_416.npz / yolov4_416.npz (written by the unmodified reference): grouped routes; Mish, SPP max-pools,
+    shortcuts, PAN routes.  Same detections in the same order, exact centres, sizes and scores at the fp16-storage floor."""
+    from oracle import darknet_ref as D
+    from oracle.synth import darknet_weights, make_frame
+    g = np.load(os.path.join(GOLDEN, name.replace("-", "_") + "_416.npz"))
+    frames = [make_frame(416, 416, seed=int(s_)) for s_ in g["frame_seeds"]]
+    cfg = os.path.join(ROOT, "config", name + ".cfg")
+    blocks = D.parse_cfg(cfg)
+    ws, _ = darknet_weights(blocks, frames, seed=int(g["weight_seed"]), target=40)
+    model = Darknet(cfg, img_size=(416, 416))
+    model.set_weights(flatten_ws(blocks, ws))
+    model.to(DEV)
+    pred = model.forward_frame(torch.from_numpy(frames[0]).to(DEV))
+    np.testing.assert_allclose(pred[0].cpu().numpy()[g["pred_top_idx"]][:, 4], g["pred_top"][:, 4], atol=2e-2)
+    got = soft_non_max_suppression(pred, 0.5, 0.4)[0].cpu().numpy()
+    ref = g["dets"]
+    assert got.shape == ref.shape, f"{len(got)} detections vs {len(ref)} in the reference"
+    np.testing.assert_array_equal(got[:, 5], ref[:, 5])
+    centre = np.abs(0.5 * (got[:, :2] + got[:, 2:4]) - 0.5 * (ref[:, :2] + ref[:, 2:4])).max()
+    size = np.abs((got[:, 2:4] - got[:, :2]) - (ref[:, 2:4] - ref[:, :2])).max()
+    print("%s vs the reference golden: centre err %.3g px, size err %.3g px, score err %.3g" % (name, centre, size, np.abs(got[:, 4] - ref[:, 4]).max()))
+    assert centre <= 1e-3 and size <= (0.3 if name == "yolov4-tiny" else 0.8) and np.abs(got[:, 4] - ref[:, 4]).max() < 2e-2
+    assert np.array_equal(got[:, :4].astype(np.int64), ref[:, :4].astype(np.int64))

@@ -136,3 +136,26 @@ def test_lookahead_pipeline_equals_synchronous_steps():
             assert a.shape == b.shape
             np.testing.assert_array_equal(b[:, 4:], a[:, 4:], err_msg=f"micro_batch {mb} frame {t}: ids / classes")
             assert np.abs(b[:, :4] - a[:, :4]).max(initial=0) <= 1
+
+
+def test_video_detector_matches_reference_loop(tmp_path):
+    """tests/golden/video_detector.npz: the unmodified reference's VideoDetector.detect (video_deepsort.py's arguments, skip_frames=2,
+    DeepSort tracker, overlay) on a lossless clip.  The drop-in class on the same files yields, frame by frame, the same held rows
+    [x1,y1,x2,y2,id,cls] and -- since the overlay is drawn from them with the same cv2 calls -- bit-identical images."""
+    import hashlib
+    from oracle.gen_golden import video_fixture
+    from yolo_deepsort_b200 import Darknet, DeepSort, VideoDetector
+    g = np.load(os.path.join(ROOT, "tests", "golden", "video_detector.npz"))
+    cfg, blocks, ws, sd, paths, clip = video_fixture(str(tmp_path))
+    model = Darknet(cfg, img_size=(416, 416))
+    model.load_darknet_weights(paths["weights"])
+    model.to(DEV)
+    tracker = DeepSort(paths["ckpt"], min_confidence=1, use_cuda=True, nn_budget=30, n_init=3, max_iou_distance=0.7, max_dist=0.3, max_age=30)
+    vd = VideoDetector(model, paths["names"], thickness=2, skip_frames=2, thres=0.5, class_mask=[0, 2, 4], nms_thres=0.4, tracker=tracker, half=True)
+    n = 0
+    for t, (image, rows, actions) in enumerate(vd.detect(paths["video"], real_show=False, skip_secs=0, show_fps=False)):
+        np.testing.assert_array_equal(np.asarray(rows, np.int32).reshape(-1, 6), g[f"rows_{t}"], err_msg=f"frame {t}: held rows")
+        digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(image).tobytes()).digest(), np.uint8)
+        np.testing.assert_array_equal(digest, g[f"image_sha256_{t}"], err_msg=f"frame {t}: yielded image")
+        n += 1
+    assert n == int(g["n_frames"])

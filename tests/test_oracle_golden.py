@@ -52,9 +52,12 @@ def test_kalman_batch_bit_exact():
         np.testing.assert_array_equal(m0.numpy()[0], g["mean0"][i]); np.testing.assert_array_equal(c0.numpy()[0], g["cov0"][i])
 
 
-def test_association_sequence_bit_exact():
-    """24-frame DeepSort.update sequence: per-frame (K,6) int32 rows, the track table and the means."""
-    g = _g("assoc_seq.npz")
+@pytest.mark.parametrize("name", ["assoc_seq.npz", "assoc_seq2.npz"])
+def test_association_sequence_bit_exact(name):
+    """DeepSort.update sequences written by the unmodified reference: per-frame (K,6) int32 rows, the track table and the means.
+    assoc_seq: 24 frames with the demo parameters; assoc_seq2: 44 frames with nn_budget=4, max_age=3, n_init=2 (gallery FIFO
+    truncation, deletion by age and re-identification after misses all happen inside it)."""
+    g = _g(name)
     p = g["params"]
     feats = {}
     orc = S.DeepSortRef(lambda fr, tl: torch.from_numpy(feats["f"]), max_dist=float(p[0]), max_iou_distance=float(p[1]),
@@ -156,3 +159,47 @@ def test_overlay_matches_reference_label_drawer():
             digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(im).tobytes()).digest(), np.uint8)
             np.testing.assert_array_equal(digest, g[f"{name}_{k}_sha256"], err_msg=f"{name} {k}")
         assert (a != frame).any()
+
+
+@pytest.mark.parametrize("name", ["yolov4-tiny", "yolov4"])
+def test_other_architectures_forward_and_nms_vs_golden(name):
+    """yolov4-tiny 416 (grouped routes) and yolov4 416 (Mish, SPP 5/9/13 max-pools, shortcuts, PAN routes): the oracle against the
+    forward digest and the soft_non_max_suppression output written by the unmodified reference."""
+    g = _g(name.replace("-", "_") + "_416.npz")
+    blocks = D.parse_cfg(os.path.join(ROOT, "config", name + ".cfg"))
+    frames = [make_frame(416, 416, seed=int(s_)) for s_ in g["frame_seeds"]]
+    ws, info = darknet_weights(blocks, frames, seed=int(g["weight_seed"]), target=40)
+    pred = D.forward(blocks, ws, frame_to_input(frames[0]))
+    np.testing.assert_allclose(pred[0, g["pred_top_idx"]].numpy(), g["pred_top"], rtol=2e-4, atol=2e-4)
+    dets = D.postprocess(pred[0].numpy(), 0.5, 0.4)
+    assert dets.shape == g["dets"].shape and 30 <= len(dets) <= 50
+    if hashlib.sha256(pred.numpy().tobytes()).digest() == g["pred_sha256"].tobytes():
+        np.testing.assert_array_equal(dets, g["dets"])
+    else:
+        np.testing.assert_allclose(dets, g["dets"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_array_equal(dets[:, 5], g["dets"][:, 5])
+
+
+def test_video_detector_loop_vs_golden(tmp_path):
+    """tests/golden/video_detector.npz: the reference's own VideoDetector.detect loop with video_deepsort.py's keyword arguments
+    (skip_frames=2: detector + tracker on every second frame, rows held in between) on a lossless clip.  The oracle flow
+    reproduces the held rows of every frame; drawing them with the LabelDrawer mirror reproduces the yielded images."""
+    import cv2
+    from oracle.gen_golden import video_fixture
+    from yolo_deepsort_b200.label_draw import LabelDrawer
+    g = _g("video_detector.npz")
+    cfg, blocks, ws, sd, paths, clip = video_fixture(str(tmp_path))
+    orc = S.DeepSortRef(lambda fr, tl: R.extract(sd, fr, tl), max_dist=0.3, max_iou_distance=0.7, max_age=30, n_init=3, nn_budget=30)
+    ld = LabelDrawer([f"c{i}" for i in range(80)], None, 10, 2, img_size=(416, 416))
+    held = None
+    for t in range(int(g["n_frames"])):
+        if t % 2 == 0:
+            det = D.detect(blocks, ws, clip[t], (416, 416), 0.5, 0.4)
+            tlwh, conf, cls = D.to_tracker_inputs(det, [0, 2, 4])
+            held = orc.update(tlwh, conf, clip[t], torch.from_numpy(cls))
+        rows = np.asarray(held, np.int32).reshape(-1, 6)
+        np.testing.assert_array_equal(rows, g[f"rows_{t}"], err_msg=f"frame {t}")
+        img, _, _ = ld.draw_labels_by_trackers(clip[t].copy(), held, only_rect=False)
+        result = cv2.cvtColor(img, cv2.COLOR_RGB2BGR)
+        digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(result).tobytes()).digest(), np.uint8)
+        np.testing.assert_array_equal(digest, g[f"image_sha256_{t}"], err_msg=f"yielded image of frame {t}")
