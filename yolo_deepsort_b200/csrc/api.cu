@@ -5,6 +5,7 @@
 #include <algorithm>
 #include "../../include/ydst.h"
 #include "assoc.cuh"
+#include "cosine_tc.cuh"
 #include "net.cuh"
 #include "tracker.cuh"
 
@@ -353,25 +354,22 @@ int ydst_appearance_cost(const float* gallery_dev, const int* seg_host, int n, c
     YDST_CHECK(seg_host && n >= 0 && m >= 0, "bad argument");
     if (n == 0 || m == 0) return 0;
     const int G = seg_host[n];
-    std::vector<int> row_ptr(G), row_track(G);
-    for (int t = 0; t < n; ++t)
-        for (int g = seg_host[t]; g < seg_host[t + 1]; ++g) { row_ptr[g] = g; row_track[g] = t; }
+    std::vector<int> row_ptr(G);
+    for (int g = 0; g < G; ++g) row_ptr[g] = g;
     float *gal_n = nullptr, *det_n = nullptr;
-    int *d_rp = nullptr, *d_rt = nullptr, *enc = nullptr;
-    auto cleanup = [&]() { cudaFree(gal_n); cudaFree(det_n); cudaFree(d_rp); cudaFree(d_rt); cudaFree(enc); };
+    int *d_rp = nullptr, *d_seg = nullptr;
+    auto cleanup = [&]() { cudaFree(gal_n); cudaFree(det_n); cudaFree(d_rp); cudaFree(d_seg); };
     try {
         YDST_CUDA(cudaMalloc(&gal_n, (size_t)std::max(G, 1) * kFeat * sizeof(float)));
         YDST_CUDA(cudaMalloc(&det_n, (size_t)m * kFeat * sizeof(float)));
         YDST_CUDA(cudaMalloc(&d_rp, (size_t)std::max(G, 1) * sizeof(int)));
-        YDST_CUDA(cudaMalloc(&d_rt, (size_t)std::max(G, 1) * sizeof(int)));
-        YDST_CUDA(cudaMalloc(&enc, (size_t)n * m * sizeof(int)));
+        YDST_CUDA(cudaMalloc(&d_seg, (size_t)(n + 1) * sizeof(int)));
         YDST_CUDA(cudaMemcpyAsync(d_rp, row_ptr.data(), G * sizeof(int), cudaMemcpyHostToDevice, S(stream)));
-        YDST_CUDA(cudaMemcpyAsync(d_rt, row_track.data(), G * sizeof(int), cudaMemcpyHostToDevice, S(stream)));
+        YDST_CUDA(cudaMemcpyAsync(d_seg, seg_host, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, S(stream)));
         launch_normalize_rows(gallery_dev, gal_n, G, S(stream));
         launch_normalize_rows(det_feat_dev, det_n, m, S(stream));
-        launch_fill_i32(enc, 0x7f800000, (long long)n * m, S(stream));
-        launch_cosine_min(gal_n, d_rp, d_rt, G, det_n, m, enc, S(stream));
-        launch_cost_finalize(enc, mean_dev, cov_dev, nullptr, n, det_tlwh_dev, m, max_dist, cost_dev, S(stream));
+        CosineTc cos;
+        cos.run(gal_n, d_rp, d_seg, G, n, det_n, m, mean_dev, cov_dev, nullptr, det_tlwh_dev, max_dist, cost_dev, S(stream));
         YDST_CUDA(cudaStreamSynchronize(S(stream)));
     } catch (...) { cleanup(); throw; }
     cleanup();

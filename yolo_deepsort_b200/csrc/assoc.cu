@@ -212,24 +212,6 @@ void launch_kf_update(float* mean, float* cov, const int* idx, const float* det_
     YDST_CUDA(cudaGetLastError());
 }
 
-// squared Mahalanobis distance in (x, y) only: project, 2x2 LU inverse (getrf + getri order), d S^-1 d^T
-__device__ __forceinline__ float maha_position(const float* __restrict__ mean, const float* __restrict__ cov, float zx, float zy) {
-    const float h = mean[3];
-    const float sp = h * 0.05f;
-    float a = cov[0] + sp * sp, b = cov[1], c = cov[8], d = cov[9] + sp * sp;
-    const bool swap = fabsf(c) > fabsf(a);
-    if (swap) { float t = a; a = c; c = t; t = b; b = d; d = t; }
-    const float l = c * (1.f / a);
-    const float u22 = d - l * b;
-    const float iu00 = 1.f / a, iu11 = 1.f / u22;
-    const float iu01 = (iu00 * b) * (-iu11);
-    float i00 = iu00 - iu01 * l, i10 = 0.f - iu11 * l, i01 = iu01, i11 = iu11;
-    if (swap) { float t = i00; i00 = i01; i01 = t; t = i10; i10 = i11; i11 = t; }
-    const float d0 = -mean[0] + zx, d1 = -mean[1] + zy;
-    const float t0 = fmaf(d1, i10, d0 * i00), t1 = fmaf(d1, i11, d0 * i01);
-    return fmaf(t1, d1, t0 * d0);
-}
-
 __global__ void gate_position_kernel(const float* __restrict__ mean, const float* __restrict__ cov, const int* __restrict__ idx, int n,
                                      const float* __restrict__ det_tlwh, int m, float* __restrict__ maha) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,97 +246,6 @@ __global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __rest
 void launch_normalize_rows(const float* src, float* dst, int n, cudaStream_t st) {
     if (n == 0) return;
     normalize_rows_kernel<<<n, 128, 0, st>>>(src, dst, n);
-    YDST_CUDA(cudaGetLastError());
-}
-
-__global__ void fill_i32_kernel(int* p, int v, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-void launch_fill_i32(int* p, int v, long long n, cudaStream_t st) {
-    if (n == 0) return;
-    fill_i32_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, v, n);
-    YDST_CUDA(cudaGetLastError());
-}
-
-// order-preserving float <-> int so that a signed atomicMin implements a float min
-__device__ __forceinline__ int f2ord(float f) {
-    const int b = __float_as_int(f);
-    return b >= 0 ? b : b ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
-static constexpr int kOrdInf = 0x7f800000;
-
-// 16 gallery rows x 64 detections per CTA (a frame has ~1500 gallery rows x ~50 detections: small row tiles keep ~100 CTAs
-// busy), K = 512 in steps of 16; each thread owns 1 row x 4 detections.
-// Epilogue: d = 1 - dot, segmented min over each track's gallery rows through atomicMin (order independent).
-__global__ void __launch_bounds__(256) cosine_min_kernel(const float* __restrict__ gallery, const int* __restrict__ row_ptr,
-                                                         const int* __restrict__ row_track, int G, const float* __restrict__ det, int m,
-                                                         int* __restrict__ cost_enc) {
-    __shared__ __align__(16) float As[16][16 + 1];      // [k][row]
-    __shared__ __align__(16) float Bs[16][64 + 4];      // [k][det]
-    const int g0 = blockIdx.x * 16, j0 = blockIdx.y * 64;
-    const int t = threadIdx.x;
-    const int ar = t >> 4, ak = t & 15;                 // A loader: row ar, k ak
-    const int br = t >> 2, bk = (t & 3) * 4;            // B loader: det br, k bk..bk+3
-    const int ga = g0 + ar, jb = j0 + br;
-    const float* arow = ga < G ? gallery + (long long)row_ptr[ga] * kFeat : nullptr;
-    const float* brow = jb < m ? det + (long long)jb * kFeat : nullptr;
-    const int ty = t >> 4, tx = t & 15;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < kFeat; k0 += 16) {
-        As[ak][ar] = arow ? __ldg(arow + k0 + ak) : 0.f;
-        const float4 vb = brow ? __ldg(reinterpret_cast<const float4*>(brow + k0 + bk)) : make_float4(0, 0, 0, 0);
-        Bs[bk + 0][br] = vb.x; Bs[bk + 1][br] = vb.y; Bs[bk + 2][br] = vb.z; Bs[bk + 3][br] = vb.w;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float a = As[k][ty];
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            acc[0] = fmaf(a, b4.x, acc[0]); acc[1] = fmaf(a, b4.y, acc[1]);
-            acc[2] = fmaf(a, b4.z, acc[2]); acc[3] = fmaf(a, b4.w, acc[3]);
-        }
-        __syncthreads();
-    }
-    const int g = g0 + ty;
-    if (g >= G) return;
-    const int trk = row_track[g];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int j = j0 + tx * 4 + b;
-        if (j < m) atomicMin(cost_enc + (long long)trk * m + j, f2ord(1.f - acc[b]));
-    }
-}
-void launch_cosine_min(const float* gallery, const int* row_ptr, const int* row_track, int G, const float* det_feat_n, int m,
-                       int* cost_enc, cudaStream_t st) {
-    if (G == 0 || m == 0) return;
-    dim3 grid(cdiv(G, 16), cdiv(m, 64));
-    cosine_min_kernel<<<grid, 256, 0, st>>>(gallery, row_ptr, row_track, G, det_feat_n, m, cost_enc);
-    YDST_CUDA(cudaGetLastError());
-}
-
-// gate (position-only chi^2, strict >) then clamp (cost > max -> max + 1e-5): linear_assignment.py:201-202, :52
-__global__ void cost_finalize_kernel(const int* __restrict__ cost_enc, const float* __restrict__ mean, const float* __restrict__ cov,
-                                     const int* __restrict__ idx, int n, const float* __restrict__ det_tlwh, int m, float max_dist,
-                                     float clamp_val, float* __restrict__ cost) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)n * m) return;
-    const int i = (int)(e / m), j = (int)(e % m);
-    const int slot = idx ? idx[i] : i;
-    float c = ord2f(cost_enc[e]);
-    float zx, zy, za, zh;
-    tlwh_to_xyah(det_tlwh + j * 4, zx, zy, za, zh);
-    const float g = maha_position(mean + (long long)slot * 8, cov + (long long)slot * 64, zx, zy);
-    if (g > kChi2inv95_2) c = kInftyCost;
-    if (c > max_dist) c = clamp_val;
-    cost[e] = c;
-}
-void launch_cost_finalize(const int* cost_enc, const float* mean, const float* cov, const int* idx, int n, const float* det_tlwh, int m,
-                          double max_dist, float* cost, cudaStream_t st) {
-    if ((long long)n * m == 0) return;
-    // the reference compares in fp32 but forms the replacement value in double: max_distance + 1e-5 (linear_assignment.py:52)
-    const float clamp_val = (float)(max_dist + 1e-5);
-    cost_finalize_kernel<<<cdiv((long long)n * m, 256), 256, 0, st>>>(cost_enc, mean, cov, idx, n, det_tlwh, m, (float)max_dist, clamp_val, cost);
     YDST_CUDA(cudaGetLastError());
 }
 
@@ -433,61 +324,81 @@ __device__ __forceinline__ LsapBest lsap_shfl(const LsapBest& v, int o) {
 struct LsapWork {
     double *u, *v, *spc;
     int *path, *col4row, *row4col, *remaining;
-    unsigned char *SR, *SC;
+    int *ep_col;          // shortestPathCosts[j] is valid for the augmentation whose number it holds (otherwise: +inf, as scipy fills it)
+    int *vis_col, *vis_row, *vis_bit;   // per augmentation: columns removed (SC), rows visited (SR), positions of `remaining` overwritten
+    float* rowbuf;        // [C]: cost row of the next augmentation's first scan (known in advance: row cur + 1)
 };
 
 static __host__ __device__ inline size_t lsap_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+static __host__ __device__ inline size_t lsap_state_bytes(int R, int C) {
+    return lsap_align16(sizeof(double) * R) + 2 * lsap_align16(sizeof(double) * C) + 7 * lsap_align16(sizeof(int) * C) +
+           lsap_align16(sizeof(int) * R) + lsap_align16(sizeof(float) * C);
+}
+static __host__ __device__ inline void lsap_carve(unsigned char* p, int R, int C, LsapWork& w) {
+    w.u = (double*)p; p += lsap_align16(sizeof(double) * R);
+    w.v = (double*)p; p += lsap_align16(sizeof(double) * C);
+    w.spc = (double*)p; p += lsap_align16(sizeof(double) * C);
+    w.path = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.row4col = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.remaining = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.ep_col = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.vis_col = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.vis_row = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.vis_bit = (int*)p; p += lsap_align16(sizeof(int) * C);
+    w.col4row = (int*)p; p += lsap_align16(sizeof(int) * R);
+    w.rowbuf = (float*)p;
+}
 
-// state_in_smem: the whole solver state (duals, shortest-path costs, predecessor / assignment / remaining arrays) lives in
-// dynamic shared memory instead of the global workspace -- the algorithm is a chain of dependent scans, so every global
-// round trip (~700 clk) sat on the critical path.  cost_in_smem additionally stages the cost matrix when it is small.
+// state_in_smem: the whole solver state lives in dynamic shared memory instead of the global workspace -- the algorithm is a
+// chain of dependent scans, so every global round trip (~700 clk) sat on the critical path.  cost_in_smem additionally stages
+// the cost matrix when it is small.
+//
+// What scipy does per augmentation -- fill shortestPathCosts with inf, clear SR / SC, reset `remaining` to C-1..0, then, after the
+// path is found, sweep ALL rows and columns for the dual update -- costs O(R + C) work and three CTA-wide barriers around a
+// search that usually ends after ONE scan.  The same state is kept lazily here, with identical results:
+//   * shortestPathCosts[j] carries the number of the augmentation that wrote it (ep_col); anything older reads as +inf;
+//   * the removed columns (SC), the visited rows (SR) and the overwritten positions of `remaining` are LOGGED as the search goes
+//     (one of each per scan), so the dual update and the restoration of `remaining` touch only those k entries;
+//   * the first scan of augmentation `cur` always reads cost row `cur`: it is prefetched into shared memory while the previous
+//     augmentation finishes, which takes the L2 round trip off the chain for the (common) single-scan augmentations.
 template <int T>
 __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_g, int R, int C, float max_dist, int* __restrict__ col4row_out,
                                                  int* __restrict__ over_max, LsapWork w, int state_in_smem, int cost_in_smem) {
     extern __shared__ __align__(16) unsigned char lsap_smem[];
     __shared__ LsapBest s_part[32];
     __shared__ double s_min;
-    __shared__ int s_i, s_nrem, s_sink;
+    __shared__ int s_i, s_nrem, s_sink, s_k;
     const int tid = threadIdx.x;
     auto bar = [&]() { if (T == 32) __syncwarp(); else __syncthreads(); };
     const float* cost = cost_g;
     if (state_in_smem) {
-        unsigned char* p = lsap_smem;
-        w.u = (double*)p; p += lsap_align16(sizeof(double) * R);
-        w.v = (double*)p; p += lsap_align16(sizeof(double) * C);
-        w.spc = (double*)p; p += lsap_align16(sizeof(double) * C);
-        w.path = (int*)p; p += lsap_align16(sizeof(int) * C);
-        w.row4col = (int*)p; p += lsap_align16(sizeof(int) * C);
-        w.remaining = (int*)p; p += lsap_align16(sizeof(int) * C);
-        w.col4row = (int*)p; p += lsap_align16(sizeof(int) * R);
-        w.SR = p; p += lsap_align16(R);
-        w.SC = p; p += lsap_align16(C);
+        lsap_carve(lsap_smem, R, C, w);
         if (cost_in_smem) {
-            float* cs = (float*)p;
+            float* cs = (float*)(lsap_smem + lsap_state_bytes(R, C));
             for (int i = tid; i < R * C; i += T) cs[i] = cost_g[i];
             cost = cs;
         }
     }
-
     for (int i = tid; i < R; i += T) { w.u[i] = 0.0; w.col4row[i] = -1; }
-    for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; w.path[j] = -1; }
+    for (int j = tid; j < C; j += T) {
+        w.v[j] = 0.0; w.row4col[j] = -1; w.path[j] = -1; w.ep_col[j] = -1; w.remaining[j] = C - 1 - j;
+        if (!cost_in_smem) w.rowbuf[j] = cost_g[j];          // row 0
+    }
+    if (tid == 0) { s_min = 0.0; s_i = 0; s_nrem = C; s_sink = -1; s_k = 0; }
     bar();
     for (int cur = 0; cur < R; ++cur) {
-        for (int j = tid; j < C; j += T) { w.remaining[j] = C - 1 - j; w.spc[j] = CUDART_INF; w.SC[j] = 0; }
-        for (int i = tid; i < R; i += T) w.SR[i] = 0;
-        if (tid == 0) { s_min = 0.0; s_i = cur; s_nrem = C; s_sink = -1; }
-        bar();
+        int k = 0;                                             // scans done in this augmentation (uniform: read from shared state)
         while (true) {
             const int i = s_i, nrem = s_nrem;
             const double mv = s_min, ui = w.u[i];
-            const float* crow = cost + (long long)i * C;
+            const float* crow = (k == 0 && !cost_in_smem) ? w.rowbuf : cost + (long long)i * C;
             LsapBest best;
             best.val = CUDART_INF; best.key = 0x7fffffff;
             for (int it = tid; it < nrem; it += T) {
                 const int j = w.remaining[it];
                 const double r = mv + (double)crow[j] - ui - w.v[j];
-                double s = w.spc[j];
-                if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
+                double s = w.ep_col[j] == cur ? w.spc[j] : CUDART_INF;
+                if (r < s) { w.path[j] = i; w.spc[j] = r; w.ep_col[j] = cur; s = r; }
                 LsapBest c;
                 c.val = s; c.key = w.row4col[j] == -1 ? C - 1 - it : C + it;
                 if (lsap_better(c, best)) best = c;
@@ -513,7 +424,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                 }
             }
             if (tid == 0) {
-                w.SR[i] = 1;
+                w.vis_row[k] = i;                             // SR[i] = true
                 s_min = best.val;
                 if (!(best.val < CUDART_INF)) {
                     s_sink = -2;                              // infeasible (cannot happen with finite costs)
@@ -521,11 +432,14 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                     const int bit = best.key < C ? C - 1 - best.key : best.key - C;      // position in `remaining`
                     const int j = w.remaining[bit];
                     if (w.row4col[j] == -1) s_sink = j; else s_i = w.row4col[j];
-                    w.SC[j] = 1;
+                    w.vis_col[k] = j;                         // SC[j] = true
+                    w.vis_bit[k] = bit;
                     w.remaining[bit] = w.remaining[nrem - 1];
                     s_nrem = nrem - 1;
                 }
+                s_k = k + 1;
             }
+            ++k;
             bar();
             if (s_sink != -1) break;
         }
@@ -535,10 +449,17 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
             return;
         }
         const double mv = s_min;
-        for (int i = tid; i < R; i += T)
-            if (w.SR[i] && i != cur) w.u[i] += mv - w.spc[w.col4row[i]];
-        for (int j = tid; j < C; j += T)
-            if (w.SC[j]) w.v[j] -= mv - w.spc[j];
+        // dual update over the logged rows / columns only (each row and each column appears once in its log); col4row still holds
+        // the assignment from before this augmentation, as in scipy (the path is applied afterwards)
+        for (int e = tid; e < k; e += T) {
+            const int i = w.vis_row[e];
+            if (i != cur) w.u[i] += mv - w.spc[w.col4row[i]];
+            const int j = w.vis_col[e];
+            w.v[j] -= mv - w.spc[j];
+        }
+        // the next augmentation's first row, fetched under the bookkeeping below
+        if (!cost_in_smem && cur + 1 < R)
+            for (int j = tid; j < C; j += T) w.rowbuf[j] = __ldg(cost_g + (long long)(cur + 1) * C + j);
         bar();
         if (tid == 0) {
             w.u[cur] += mv;
@@ -551,6 +472,9 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                 j = t;
                 if (i == cur) break;
             }
+            // `remaining` back to C-1..0: only the logged positions were overwritten (in reverse: a position may be logged twice)
+            for (int e = k - 1; e >= 0; --e) { const int bit = w.vis_bit[e]; w.remaining[bit] = C - 1 - bit; }
+            s_min = 0.0; s_i = cur + 1; s_nrem = C; s_sink = -1; s_k = 0;
         }
         bar();
     }
@@ -561,25 +485,12 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
     }
 }
 
-static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-size_t lsap_work_bytes(int R, int C) {
-    return align16(sizeof(double) * R) + 2 * align16(sizeof(double) * C) + 3 * align16(sizeof(int) * C) + align16(sizeof(int) * R) +
-           align16(R) + align16(C) + 64;
-}
+size_t lsap_work_bytes(int R, int C) { return lsap_state_bytes(R, C) + 64; }
 void launch_lsap(const float* cost, int R, int C, float max_dist, int* col4row, int* over_max, void* work, cudaStream_t st) {
     if (R == 0 || C == 0) return;
     YDST_CHECK(R <= C, "launch_lsap needs R <= C (transpose first)");
-    unsigned char* p = (unsigned char*)work;
     LsapWork w;
-    w.u = (double*)p; p += align16(sizeof(double) * R);
-    w.v = (double*)p; p += align16(sizeof(double) * C);
-    w.spc = (double*)p; p += align16(sizeof(double) * C);
-    w.path = (int*)p; p += align16(sizeof(int) * C);
-    w.row4col = (int*)p; p += align16(sizeof(int) * C);
-    w.remaining = (int*)p; p += align16(sizeof(int) * C);
-    w.col4row = (int*)p; p += align16(sizeof(int) * R);
-    w.SR = p; p += align16(R);
-    w.SC = p;
+    lsap_carve((unsigned char*)work, R, C, w);
     static bool attr_set_dev[64] = {false};            // the shared-memory opt-in is a per-device attribute
     int dev = 0;
     YDST_CUDA(cudaGetDevice(&dev));
@@ -590,9 +501,9 @@ void launch_lsap(const float* cost, int R, int C, float max_dist, int* col4row, 
         YDST_CUDA(cudaFuncSetAttribute(lsap_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    const size_t state_bytes = lsap_work_bytes(R, C);
+    const size_t state_bytes = lsap_state_bytes(R, C);
     const size_t cost_bytes = (size_t)R * C * sizeof(float);
-    const int state_in_smem = state_bytes <= 160 * 1024;
+    const int state_in_smem = state_bytes <= 190 * 1024;
     const int cost_in_smem = state_in_smem && state_bytes + cost_bytes <= 96 * 1024;
     const size_t smem = state_in_smem ? state_bytes + (cost_in_smem ? cost_bytes : 0) : 0;
     if (C <= 128) lsap_kernel<32><<<1, 32, smem, st>>>(cost, R, C, max_dist, col4row, over_max, w, state_in_smem, cost_in_smem);

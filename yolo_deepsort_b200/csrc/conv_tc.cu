@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             const long long pp = (long long)p0 + row;
             const int rem = (int)(pp % HpWp);
             const int y = rem / Wp, x = rem - y * Wp;
-            const bool valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
+            const bool valid = pp < p.P_total && (p.gemm || (y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo));
             if (p.ksplit == 1) {
                 if (it == 0 && h == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
                 if constexpr (!kPers && !kPair) {
@@ -1347,6 +1347,18 @@ static constexpr int kTraceSlots = 1024;
 static int g_trace_on = -1, g_trace_next = 0;
 static unsigned long long* g_trace_dev = nullptr;
 static int g_trace_desc[kTraceSlots], g_trace_shape[kTraceSlots];
+
+void conv_tc_plan_gemm(ConvTcLaunch& L, const __half* A, int rows, int K, const __half* Bw, int ncols, float* out_f32, const float* scale,
+                       const float* bias, const ConvWorkspace* ws) {
+    YDST_CHECK(rows >= 128 && rows % 128 == 0 && K % 64 == 0 && ncols % 16 == 0 && ncols > 0, "bad GEMM shape %d x %d x %d", rows, ncols, K);
+    // a (rows x K) matrix is the flat-padded view of an image with H + 2 = rows and W + 2 = 1: one "pixel" per row
+    Act in, out;
+    in.base = const_cast<__half*>(A); in.N = 1; in.H = rows - 2; in.W = -1; in.C = K; in.ctot = K; in.coff = 0;
+    out = in; out.base = nullptr; out.C = ncols; out.ctot = ncols;
+    conv_tc_plan(L, in, out, Bw, 1, 1, 1, scale, bias, ACT_LINEAR, 0, nullptr, out_f32, ncols, ws);
+    YDST_CHECK(L.p.v2 == 1, "the GEMM needs the halo kernel's 1x1 mode");
+    L.p.gemm = 1;
+}
 
 void conv_tc_trace_dump() {
     if (g_trace_on != 2 || !g_trace_dev) return;

@@ -48,6 +48,7 @@ struct ConvTcParams {
     const void* pf_ptr;   // next convolution's packed weights: each CTA asks L2 to prefetch its slice once its own loads are queued
     unsigned pf_bytes;
     int pdl;              // launched with programmatic stream serialization (the producer then prefetches all weight stages first)
+    int gemm;             // 1: plain row-major matrices (every row is a valid output row: no padded-pixel geometry); conv_tc_plan_gemm
     int bo_mode;          // UMMA descriptor base-offset mode for row-shifted starts (validated on hardware)
 };
 
@@ -77,6 +78,10 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
 // the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
 struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair, b_resident; double model_us; };
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets);
+// Plain GEMM on the same kernel: out[rows][ncols] (fp32, row stride ncols) = A[rows][K] * B[ncols][K]^T * scale[col] + bias[col], A and B
+// fp16 row-major, K a multiple of 64, rows a multiple of 128, ncols a multiple of 16.  Used by the appearance cost (cosine_tc.cu).
+void conv_tc_plan_gemm(ConvTcLaunch& L, const __half* A, int rows, int K, const __half* Bw, int ncols, float* out_f32, const float* scale,
+                       const float* bias, const ConvWorkspace* ws);
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_trace_dump();   // YDST_CONV_TRACE=2: print the per-launch timeline collected so far (debug aid)
 double conv_tc_flops(const ConvTcLaunch& L);   // useful 2*M*N*K (logical, unpadded)

@@ -55,6 +55,10 @@ struct TrkProf {
     }
 };
 
+static TrkProf* g_cos_prof = nullptr;
+static void cos_prof_begin(int kind, double bytes, double flops, cudaStream_t st) { g_cos_prof = new TrkProf(kind, bytes, flops, st); }
+static void cos_prof_end(cudaStream_t) { delete g_cos_prof; g_cos_prof = nullptr; }
+
 Tracker::Tracker(double max_dist, double max_iou, int max_age, int n_init, int budget, int cap_tracks, int cap_dets)
     : max_dist_(max_dist), max_iou_(max_iou), max_age_(max_age), n_init_(n_init), budget_(budget), cap_t_(cap_tracks), cap_d_(cap_dets) {
     YDST_CHECK(budget >= 1 && cap_tracks >= 1 && cap_dets >= 1, "bad tracker capacities");
@@ -65,22 +69,22 @@ Tracker::Tracker(double max_dist, double max_iou, int max_age, int n_init, int b
     YDST_CUDA(cudaMalloc(&det_n_, nd * kFeat * sizeof(float)));
     YDST_CUDA(cudaMalloc(&cost_, nt * nd * sizeof(float)));
     YDST_CUDA(cudaMalloc(&cost_t_, nt * nd * sizeof(float)));
-    YDST_CUDA(cudaMalloc(&cost_enc_, nt * nd * sizeof(int)));
     YDST_CUDA(cudaMalloc(&col4row_, (nt + nd) * sizeof(int)));
     YDST_CUDA(cudaMalloc(&over_, (nt + nd) * sizeof(int)));
     YDST_CUDA(cudaMalloc(&out_mean_, nt * 8 * sizeof(float)));
     YDST_CUDA(cudaMalloc(&lsap_work_, lsap_work_bytes((int)std::max(nt, nd), (int)std::max(nt, nd))));
-    ibuf_cap_ = nt * budget_ * 2 + 16 * (nt + nd) + 1024;
+    ibuf_cap_ = nt * budget_ * 2 + 20 * (nt + nd) + 1024;
     YDST_CUDA(cudaMalloc(&ibuf_, ibuf_cap_ * sizeof(int)));
     YDST_CUDA(cudaMallocHost(&h_ibuf_, ibuf_cap_ * sizeof(int)));
     YDST_CUDA(cudaMallocHost(&h_res_, 2 * (nt + nd) * sizeof(int)));
     YDST_CUDA(cudaMallocHost(&h_f_, nt * 8 * sizeof(float)));
+    cos_.prof_begin = cos_prof_begin; cos_.prof_end = cos_prof_end;
     free_slots_.reserve(nt);
     for (int s = cap_t_ - 1; s >= 0; --s) free_slots_.push_back(s);
 }
 
 Tracker::~Tracker() {
-    cudaFree(mean_); cudaFree(cov_); cudaFree(gallery_); cudaFree(det_n_); cudaFree(cost_); cudaFree(cost_t_); cudaFree(cost_enc_);
+    cudaFree(mean_); cudaFree(cov_); cudaFree(gallery_); cudaFree(det_n_); cudaFree(cost_); cudaFree(cost_t_);
     cudaFree(col4row_); cudaFree(over_); cudaFree(out_mean_); cudaFree(lsap_work_); cudaFree(ibuf_);
     cudaFreeHost(h_ibuf_); cudaFreeHost(h_res_); cudaFreeHost(h_f_);
 }
@@ -178,22 +182,20 @@ void Tracker::update(const float* tlwh, const float* feat, const int* payload_ho
         A.um_t = confirmed; A.um_d = all_dets;
     } else {
         const int na = (int)confirmed.size();
-        std::vector<int> slots(na), row_ptr, row_track;
+        std::vector<int> slots(na), row_ptr, seg(na + 1, 0);
         for (int r = 0; r < na; ++r) {
             const TrackHost& t = tracks[confirmed[r]];
             slots[r] = t.slot;
-            for (int k = 0; k < t.gal_count; ++k) { row_ptr.push_back(t.slot * budget_ + k); row_track.push_back(r); }
+            for (int k = 0; k < t.gal_count; ++k) row_ptr.push_back(t.slot * budget_ + k);
+            seg[r + 1] = (int)row_ptr.size();
         }
         const int G = (int)row_ptr.size();
         int* d_slots = upload(slots, st);
         int* d_rp = upload(row_ptr, st);
-        int* d_rt = upload(row_track, st);
-        { TrkProf pr(TOP_FILL, 4.0 * na * m, 0, st); launch_fill_i32(cost_enc_, 0x7f800000, (long long)na * m, st); }
-        { TrkProf pr(TOP_COSINE_MIN, 2048.0 * G + 2048.0 * m + 4.0 * na * m, 2.0 * G * (double)m * kFeat, st);
-          launch_cosine_min(gallery_, d_rp, d_rt, G, det_n_, m, cost_enc_, st); }
-        { TrkProf pr(TOP_COST_FINALIZE, 8.0 * na * m + 288.0 * na + 16.0 * m, 0, st);
-          launch_cost_finalize(cost_enc_, mean_, cov_, d_slots, na, tlwh, m, max_dist_, cost_, st); }
-        launches_last += 3;
+        int* d_seg = upload(seg, st);
+        // 1 - max cosine over each track's gallery rows, gate, clamp: split + tcgen05 GEMM + segmented max (cosine_tc.cu)
+        cos_.run(gallery_, d_rp, d_seg, G, na, det_n_, m, mean_, cov_, d_slots, tlwh, max_dist_, cost_, st);
+        launches_last += cos_.launches_last;
         A = solve(cost_, confirmed, all_dets, (float)max_dist_, st);
     }
     if (trace) t_a = now();

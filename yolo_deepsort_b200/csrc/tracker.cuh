@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "assoc.cuh"
+#include "cosine_tc.cuh"
 
 namespace ydst {
 
@@ -40,7 +41,8 @@ private:
     int* tsu_dev_ = nullptr;
     // device scratch
     float *cost_ = nullptr, *cost_t_ = nullptr, *out_mean_ = nullptr;
-    int *cost_enc_ = nullptr, *col4row_ = nullptr, *over_ = nullptr, *ibuf_ = nullptr;
+    int *col4row_ = nullptr, *over_ = nullptr, *ibuf_ = nullptr;
+    CosineTc cos_;                  // appearance cost on the tensor cores (owns its operand / product scratch)
     void* lsap_work_ = nullptr;
     size_t ibuf_cap_ = 0, ibuf_used_ = 0;
     // pinned host staging
