@@ -314,10 +314,22 @@ struct LsapBest {
 __device__ __forceinline__ bool lsap_better(const LsapBest& a, const LsapBest& b) {
     return a.val < b.val || (a.val == b.val && a.key < b.key);
 }
-__device__ __forceinline__ LsapBest lsap_shfl(const LsapBest& v, int o) {
+// Warp-wide lexicographic minimum of (val, key) with three redux.sync instead of fifteen shuffles: the double is mapped to an
+// order-preserving unsigned 64-bit integer (sign bit flipped for positives, all bits for negatives), its high and low words and
+// then the key are reduced in turn, each step among the lanes still tied on the previous ones.  Exact: no arithmetic is involved.
+__device__ __forceinline__ LsapBest lsap_warp_min(const LsapBest& v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v.val);
+    const unsigned long long o = b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+    const unsigned hi = (unsigned)(o >> 32), lo = (unsigned)o;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool tied = hi == mhi && lo == mlo;
+    const unsigned mkey = __reduce_min_sync(0xffffffffu, tied ? (unsigned)v.key : 0x7fffffffu);
+    const unsigned long long mo = ((unsigned long long)mhi << 32) | mlo;
+    const unsigned long long mb = mo ^ ((mo >> 63) ? 0x8000000000000000ull : ~0ull);
     LsapBest r;
-    r.val = __shfl_xor_sync(0xffffffffu, v.val, o);
-    r.key = __shfl_xor_sync(0xffffffffu, v.key, o);
+    r.val = __longlong_as_double((long long)mb);
+    r.key = (int)mkey;
     return r;
 }
 
@@ -388,6 +400,15 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
     bar();
     for (int cur = 0; cur < R; ++cur) {
         int k = 0;                                             // scans done in this augmentation (uniform: read from shared state)
+        // the next augmentation's first row goes to registers now and to shared memory once this augmentation's scans are over:
+        // its L2 round trip hides under the search (T >= C / 4 threads: at most four columns each)
+        float nxt[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool pf = !cost_in_smem && cur + 1 < R && C <= 4 * T;
+        if (pf) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (tid + q * T < C) nxt[q] = __ldg(cost_g + (long long)(cur + 1) * C + tid + q * T);
+        }
         while (true) {
             const int i = s_i, nrem = s_nrem;
             const double mv = s_min, ui = w.u[i];
@@ -403,11 +424,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                 c.val = s; c.key = w.row4col[j] == -1 ? C - 1 - it : C + it;
                 if (lsap_better(c, best)) best = c;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const LsapBest other = lsap_shfl(best, o);
-                if (lsap_better(other, best)) best = other;
-            }
+            best = lsap_warp_min(best);
             if (T > 32) {
                 if ((tid & 31) == 0) s_part[tid >> 5] = best;
                 __syncthreads();
@@ -415,12 +432,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
                     LsapBest b2;
                     if (tid < T / 32) b2 = s_part[tid];
                     else { b2.val = CUDART_INF; b2.key = 0x7fffffff; }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const LsapBest other = lsap_shfl(b2, o);
-                        if (lsap_better(other, b2)) b2 = other;
-                    }
-                    best = b2;
+                    best = lsap_warp_min(b2);
                 }
             }
             if (tid == 0) {
@@ -457,9 +469,13 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
             const int j = w.vis_col[e];
             w.v[j] -= mv - w.spc[j];
         }
-        // the next augmentation's first row, fetched under the bookkeeping below
-        if (!cost_in_smem && cur + 1 < R)
+        if (pf) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (tid + q * T < C) w.rowbuf[tid + q * T] = nxt[q];
+        } else if (!cost_in_smem && cur + 1 < R) {
             for (int j = tid; j < C; j += T) w.rowbuf[j] = __ldg(cost_g + (long long)(cur + 1) * C + j);
+        }
         bar();
         if (tid == 0) {
             w.u[cur] += mv;
