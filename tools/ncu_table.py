@@ -27,10 +27,11 @@ def main():
         v = num(r[ix[key]])
         u = units[ix[key]]
         if scale:
-            v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}.get(u, 1.0)
+            v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9,
+                  "second": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
         return v
     stall_keys = [k for k in hdr if "issue_stalled" in k and "per_issue_active" in k]
-    local_keys = [k for k in hdr if "local" in k and ("bytes" in k or "op_local" in k)]
+    local_keys = [k for k in ("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum") if k in ix]
     out = [f"# {title}\n", "Per-launch times under ncu are cold-cache and serialised (compare shares, not absolutes).  `tensor %` = "
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed; `dram MB` = dram__bytes_read.sum + dram__bytes_write.sum; stalls = "
            "smsp__average_warps_issue_stalled_*_per_issue_active.ratio (top two).\n",
@@ -44,7 +45,7 @@ def main():
         tens = col(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", False)
         dpct = col(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", False)
         regs = col(r, "launch__registers_per_thread", False)
-        loc = sum(col(r, k) for k in local_keys if "bytes" in k)
+        loc = sum(col(r, k, False) for k in local_keys) * 32.0          # 32-byte sectors
         stalls = sorted(((num(r[ix[k]]), k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for k in stall_keys
                          if r[ix[k]] not in ("", "n/a")), reverse=True)[:2]
         out.append(f"| {n} | {name} | {r[ix['Grid Size']]} | {dur * 1e6:.1f} | {tens:.1f} | {(rd + wr) / 1e6:.2f} | {dpct:.1f} | {(rd + wr) / dur / 1e9:.0f} | {regs:.0f} | "

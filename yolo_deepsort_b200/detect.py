@@ -118,19 +118,36 @@ class FrameReader:
 
 
 class VideoDetector:
+    """Mirror of yolo3/detect/video_detect.py:39-208.  Same constructor keywords, same generator contract
+    (`detect()` yields (bgr image with the overlay, held rows, actions) per frame, in order).  Two keywords of its own:
+      micro_batch   consecutive detection frames per Darknet / ReID forward when reading a FILE (default 8; results per frame are
+                    those of batch 1, tests/test_gpu_pipeline.py).  The reference's reader thread already decodes up to 128 frames
+                    ahead of the loop (video_detect.py:86), so the look-ahead stays inside its design; a live source (camera index)
+                    always runs batch 1 with one frame of look-ahead, where latency matters.
+      draw_workers  overlay + colour conversion of up to this many frames run on worker threads (cv2 releases the GIL) while the
+                    main thread collects the next results; frames are still yielded in order."""
+
     def __init__(self, model, class_path, thickness=2, font_path=None, font_size=10, thres=0.7, nms_thres=0.4, skip_frames=-1,
                  fourcc=cv2.VideoWriter_fourcc('m', 'p', '4', 'v'), class_mask=None, win_size=None, overlap=0.15, tracker=None,
-                 action_id=None, half=False):
+                 action_id=None, half=False, micro_batch=8, draw_workers=4):
         self.thickness, self.skip_frames, self.class_mask, self.fourcc = thickness, skip_frames, class_mask, fourcc
         self.image_detector = ImageDetector(model, class_path, thickness=thickness, thres=thres, nms_thres=nms_thres,
                                             win_size=win_size, overlap=overlap, half=half)
         self.classes = self.image_detector.classes
         self.label_drawer = LabelDrawer(self.classes, font_path, font_size, thickness, img_size=model.img_size)
         self.tracker, self.action_id = tracker, action_id
-        self._pipeline = None
+        self.micro_batch, self.draw_workers = max(1, int(micro_batch)), max(1, int(draw_workers))
+        self._model, self._thres, self._nms_thres = model, thres, nms_thres
+        self._pipelines = {}
         # (the sliding-window mode goes through ImageDetector.detect + tracker.update, like the reference loop)
-        if isinstance(tracker, DeepSort) and isinstance(tracker.extractor, Extractor) and win_size is None:
-            self._pipeline = FramePipeline(model, tracker, thres, nms_thres, class_mask)
+        self._fused = isinstance(tracker, DeepSort) and isinstance(tracker.extractor, Extractor) and win_size is None
+        self._pipeline = self._pipeline_for(1) if self._fused else None
+
+    def _pipeline_for(self, micro_batch):
+        if micro_batch not in self._pipelines:
+            self._pipelines[micro_batch] = FramePipeline(self._model, self.tracker, self._thres, self._nms_thres, self.class_mask,
+                                                         micro_batch=micro_batch)
+        return self._pipelines[micro_batch]
 
     def _track(self, frame):
         """One detection step; returns `hold_detections` exactly as the reference loop would set it
@@ -150,16 +167,18 @@ class VideoDetector:
         return detections
 
     def _draw(self, frame, hold):
-        """The overlay of the reference loop (yolo3/detect/video_detect.py:159-169): drawn INTO the frame, as there."""
-        if hold is None:
-            return frame
-        if self.tracker is not None:
-            image, _, _ = self.label_drawer.draw_labels_by_trackers(frame, hold, only_rect=False)
-        else:
-            image, _, _ = self.label_drawer.draw_labels(frame, hold, only_rect=False)
-        return image
+        """The overlay of the reference loop (yolo3/detect/video_detect.py:159-172): drawn INTO the frame, as there, then RGB -> BGR."""
+        if hold is not None:
+            hold = hold.cpu().numpy() if isinstance(hold, torch.Tensor) and self.tracker is not None else hold
+            if self.tracker is not None:
+                frame, _, _ = self.label_drawer.draw_labels_by_trackers(frame, hold, only_rect=False)
+            else:
+                frame, _, _ = self.label_drawer.draw_labels(frame, hold, only_rect=False)
+        return cv2.cvtColor(frame, cv2.COLOR_RGB2BGR)
 
     def detect(self, video_path, output_path=None, skip_secs=0, real_show=False, show_fps=True):
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
         logging.info("Detect video: " + str(video_path))
         vid = cv2.VideoCapture(video_path)
         if not vid.isOpened():
@@ -175,68 +194,85 @@ class VideoDetector:
         if real_show:
             cv2.namedWindow("result", cv2.WINDOW_NORMAL)
             cv2.resizeWindow("result", 960, 540)
-        accum_time, curr_fps, fps, prev_time = 0, 0, "FPS: ??", time.time()
-        hold_detections, actions, frames = None, [], 0
-        H, W = self.image_detector.model.img_size
-
+        state = {"accum": 0.0, "curr_fps": 0, "fps": "FPS: ??", "prev": time.time()}
         reader = FrameReader(vid).start()
-        read_rgb = reader.read
+        live = not isinstance(video_path, str)
+        B = 1 if live else self.micro_batch
+        pipe = self._pipeline_for(B) if self._fused else None
+        # frames of look-ahead: the pipeline's three slots for a file, ONE frame for a live source
+        max_ahead = 2 if live else 10 ** 9
+        pool = ThreadPoolExecutor(max_workers=self.draw_workers)
+        skip = self.skip_frames
 
-        # One frame of look-ahead (the reference's reader thread decodes ahead as well, video_detect.py:86,112): when every
-        # frame is a detection frame and the fused pipeline applies, the detector of frame t+1 is submitted before the
-        # ReID + association of frame t is collected, so the two halves overlap on the GPU.  Results are unchanged.
-        lookahead = self._pipeline is not None and self.skip_frames in (-1, 1) and self.action_id is None
-        nxt = read_rgb()
-        submitted = False
+        def finish(result):
+            """Main-thread tail of one frame, in order: FPS read-out, show / write (yolo3/detect/video_detect.py:174-198)."""
+            now = time.time()
+            state["accum"] += now - state["prev"]
+            state["prev"] = now
+            state["curr_fps"] += 1
+            if state["accum"] > 1:
+                state["accum"] -= 1
+                state["fps"] = "FPS: " + str(state["curr_fps"])
+                state["curr_fps"] = 0
+                print(state["fps"])
+            if show_fps:
+                cv2.putText(result, text=state["fps"], org=(3, 15), fontFace=cv2.FONT_HERSHEY_SIMPLEX, fontScale=0.6, color=(255, 0, 0),
+                            thickness=self.thickness)
+            if real_show:
+                cv2.imshow("result", result)
+            if out is not None:
+                out.write(result)
+            return result
+
+        waiting, drawing = deque(), deque()                  # frames read but not collected | frames being drawn
+        hold_detections, frames, eof = None, 0, False
         try:
-            while nxt is not None:
-                frame, nxt = nxt, read_rgb()
-                if lookahead:
-                    if not submitted:
-                        self._pipeline.submit(frame, want_dets=False)
-                    submitted = nxt is not None
-                    if submitted:
-                        self._pipeline.submit(nxt, want_dets=False)
-                    detections, _ = self._pipeline.collect(want_dets=False)
-                    actions = []
-                    hold_detections = detections
-                    frames = 0
-                elif frames % self.skip_frames == 0:
-                    detections = self._track(frame)
-                    if detections is not None and self.tracker is not None and self.action_id is not None:
-                        actions = self.action_id.update(detections)
-                    else:
-                        actions = []
-                    hold_detections = detections
-                    frames = 0
-                else:
-                    actions = []
-                hold = hold_detections.cpu().numpy() if isinstance(hold_detections, torch.Tensor) and self.tracker is not None \
-                    else hold_detections
-                result = cv2.cvtColor(self._draw(frame, hold), cv2.COLOR_RGB2BGR)
-                frames += 1
-                curr_time = time.time()
-                accum_time += curr_time - prev_time
-                prev_time = curr_time
-                curr_fps += 1
-                if accum_time > 1:
-                    accum_time -= 1
-                    fps = "FPS: " + str(curr_fps)
-                    curr_fps = 0
-                    print(fps)
-                if show_fps:
-                    cv2.putText(result, text=fps, org=(3, 15), fontFace=cv2.FONT_HERSHEY_SIMPLEX, fontScale=0.6, color=(255, 0, 0),
-                                thickness=self.thickness)
-                if real_show:
-                    cv2.imshow("result", result)
-                if out is not None:
-                    out.write(result)
-                yield result, hold_detections, actions
-                if real_show and cv2.waitKey(1) & 0xFF == ord('q'):
+            while True:
+                # ---- read ahead: every frame the reference loop would run the detector on goes into the pipeline ----
+                while not eof and len(waiting) < max_ahead and (pipe is None or pipe.can_submit() or not waiting):
+                    frame = reader.read()
+                    if frame is None:
+                        eof = True
+                        break
+                    is_det = frames % skip == 0                # (python: x % -1 == 0 for every x, i.e. skip_frames=-1 detects on every frame)
+                    if is_det:
+                        frames = 0
+                        if pipe is not None:
+                            if not pipe.can_submit():          # (only reached when nothing is waiting: cannot happen, kept as a guard)
+                                break
+                            pipe.submit(frame, want_dets=False)
+                    frames += 1
+                    waiting.append((frame, is_det))
+                    if pipe is None:
+                        break                                  # no look-ahead without the fused pipeline
+                if not waiting and not drawing:
                     break
+                # ---- oldest frame: collect its result (detection frames), hand it to a drawing thread ----
+                if waiting:
+                    frame, is_det = waiting.popleft()
+                    actions = []
+                    if is_det:
+                        if pipe is not None:
+                            detections, _ = pipe.collect(want_dets=False)
+                        else:
+                            detections = self._track(frame)
+                        if detections is not None and self.tracker is not None and self.action_id is not None:
+                            actions = self.action_id.update(detections)
+                        hold_detections = detections
+                    drawing.append((pool.submit(self._draw, frame, hold_detections), hold_detections, actions))
+                # ---- yield finished frames in order (keep up to draw_workers frames in the drawing threads) ----
+                while drawing and (drawing[0][0].done() or len(drawing) > self.draw_workers or not waiting):
+                    fut, hold, actions = drawing.popleft()
+                    result = finish(fut.result())
+                    yield result, hold, actions
+                    if real_show and cv2.waitKey(1) & 0xFF == ord('q'):
+                        eof = True
+                        waiting.clear()
+                        break
         finally:
-            if self._pipeline is not None:
-                self._pipeline.drain()
+            for p_ in self._pipelines.values():
+                p_.drain()
+            pool.shutdown(wait=True)
             reader.stop()
             vid.release()
             if out is not None:
