@@ -699,7 +699,13 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         return true;
     };
 
+    // Register re-allocation: two co-resident CTAs cap every warp at 96 registers at launch (30 720 per CTA).  The two single-thread
+    // warps (one warpgroup) shrink to 24, the eight epilogue warps -- two 16-column accumulator blocks in flight, scale/bias,
+    // residual -- grow to 112: 64 * 24 + 256 * 112 = 30 208 <= 30 720, so the .inc never waits on registers that do not exist.
+    // (ptxas only honours the new budget for code dominated by the instruction, so each role issues its own.)
+    constexpr bool kRealloc = !kPers && !kPair;
     if (warp == kProdWarp) {
+        if constexpr (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (elect_one()) {
             // ================= TMA producer =================
             int sa = 0, sb = 0, loaded_tn = -1;
@@ -777,6 +783,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             prefetch_next_weights(p);
         }
     } else if (warp == kMmaWarp) {
+        if constexpr (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (elect_one()) {
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
@@ -871,6 +878,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         }
     } else {
         // ================= epilogue =================
+        if constexpr (kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int eg = kPers ? warp >> 2 : 0;                  // persistent: the warpgroups alternate tiles
         const int half = kPers ? 0 : warp >> 2;                // otherwise: both work on the one tile (wide epilogue), or the second idles
         const int tid = threadIdx.x & 127, ebar = 1 + eg;
