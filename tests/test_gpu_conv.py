@@ -36,9 +36,15 @@ CASES = [
     ("persistent_1x1_152", 1, 152, 152, 128, 64, 1, 1, True, 1, 0, False),
     ("persistent_two_n_tiles_batch20", 20, 32, 16, 128, 256, 3, 1, True, 1, 1, False),
     ("persistent_f32_out", 2, 152, 152, 64, 48, 1, 1, False, 0, 0, True),
+    ("persistent_narrow_32", 2, 152, 152, 64, 32, 1, 1, True, 1, 0, False),
+    ("persistent_mish_res", 6, 76, 76, 64, 64, 3, 1, True, 2, 1, False),
+    ("persistent_linear_bias", 4, 76, 76, 128, 128, 1, 1, False, 0, 0, False),
+    ("persistent_relu_res_two_groups", 40, 32, 16, 128, 128, 3, 1, True, 3, 2, False),
     ("mpair_reid_64x32_batch24_odd_tiles", 24, 64, 32, 64, 64, 3, 1, True, 3, 2, False),
     ("mpair_1x1_304_batch2", 2, 304, 304, 64, 64, 1, 1, True, 1, 0, False),
     ("mpair_3x3_76_batch8_two_n_tiles", 8, 76, 76, 128, 256, 3, 1, True, 1, 1, False),
+    ("mpair_persistent_reid_32x16_batch60_res", 60, 32, 16, 128, 128, 3, 1, True, 3, 2, False),
+    ("mpair_persistent_1x1_152_batch3_odd", 3, 152, 152, 128, 64, 1, 1, True, 1, 0, False),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),
@@ -47,13 +53,15 @@ CASES = [
 
 @pytest.fixture(autouse=True)
 def _opt_in_tilings(request, monkeypatch):
-    """The persistent tile loop and the M-pair tiles are opt-in (YDST_PERSISTENT / YDST_MPAIR): the cases named after them
-    switch them on so that those kernel instantiations stay covered."""
+    """By default the persistent tile loop only takes weight-stationary layers with many tiles, and M-pair tiles are opt-in
+    (YDST_PERSISTENT=2 / YDST_MPAIR / YDST_FORCE_MPAIR): the cases named after them widen the planner's choice so that those
+    kernel instantiations stay covered on small shapes."""
     name = request.node.name
     if "persistent" in name or "mpair" in name:
-        monkeypatch.setenv("YDST_PERSISTENT", "1")
+        monkeypatch.setenv("YDST_PERSISTENT", "2")
     if "mpair" in name:
         monkeypatch.setenv("YDST_MPAIR", "1")
+        monkeypatch.setenv("YDST_FORCE_MPAIR", "2")
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])

@@ -449,6 +449,146 @@ __device__ __forceinline__ void epilogue_tile_wide(const ConvTcParams& p, const 
     }
 }
 
+// Persistent-loop epilogue (conv_tc2_kernel<.., kPers = true, kPair = false>).  Two teams of four warps alternate tiles: team e
+// drains accumulator buffer e of tiles e, e + 2, ... while the MMA issuer fills the other one.  A thread owns one output row and
+// walks the tile's 64-column groups; the TMEM load of the next 16-column block is in flight while the current one is finished
+// (scale/bias, activation, residual -- all compile-time -- fp16 pack) and written into a 128B-swizzled 16 KB staging buffer that
+// one thread hands to the TMA store unit.  Staging buffers rotate per team (nbuf = 2 or 3):
+//   nbuf = 3: after issuing store q the team's thread 0 waits until store q - 1 has been read, which frees buffer (q + 2) % 3;
+//             the other threads learn it at the staging barrier of group q + 1, one group before they write that buffer.  With a
+//             residual, thread 0 then TMA-loads the residual tile of group q + 2 into the freed buffer (two groups of lead), and
+//             the result overwrites the residual in place;
+//   nbuf = 2: (no residual, shared memory tight) thread 0 waits for store q - 2 at the top of group q, plus one more barrier.
+// kAct / kRes < 0: activation and residual mode read from the parameters at run time (the rare combinations).
+template <bool kMish, int kAct, int kRes, int kMp>
+__device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const CUtensorMap* out_map, const CUtensorMap* res_map,
+                                                    unsigned char* smem_generic, uint32_t smem_generic_u32, uint32_t stage_u32,
+                                                    uint32_t tmem_base, int team, float* s_sbt, uint32_t bar_tfull, uint32_t bar_tempty,
+                                                    uint32_t bar_res) {
+    const int tid = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3, row = tid, x = row & 7;
+    const int bn = p.block_n, ngroups = bn >> 6, nbuf = p.nbuf, ebar = 1 + team;
+    const int total_tiles = p.m_tiles * p.n_tiles, G = (int)gridDim.x;
+    const bool has_res = kRes < 0 ? p.res_mode != 0 : kRes != 0;
+    const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
+    const bool tr = p.trace && p.trace_tiles && blockIdx.x == 0 && tid == 0;
+    // team-local group index -> coordinates of its 128 x 64 output block (false: past this CTA's last tile)
+    auto coords = [&](int q, int& p0, int& c0) -> bool {
+        const int j = q / (ngroups * kMp), r = q - j * (ngroups * kMp);
+        const int h = r / ngroups, g = r - h * ngroups;
+        const int t = (int)blockIdx.x + (2 * j + team) * G;
+        if (t >= total_tiles) return false;
+        const int tn = t / p.m_tiles, tm = t - tn * p.m_tiles;
+        p0 = (tm * kMp + h) * kBlockM; c0 = tn * bn + g * 64;
+        return true;
+    };
+    auto fetch_res = [&](int q) {                                  // thread 0 of the team only
+        int p0, c0;
+        if (!coords(q, p0, c0)) return;
+        const uint32_t b = (uint32_t)(q % nbuf);
+        mbar_arrive_expect_tx(bar_res + 8u * b, kBlockM * 128u);
+        tma_load_2d(stage_u32 + b * (kBlockM * 128u), res_map, bar_res + 8u * b, p.res_coff + c0, p0);
+    };
+    if (has_res && tid == 0) { fetch_res(0); fetch_res(1); }
+    int q = 0, staged_tn = -1;
+    for (int j = 0;; ++j) {
+        const int it = 2 * j + team;
+        const int t = (int)blockIdx.x + it * G;
+        if (t >= total_tiles) break;
+        const int tn = t / p.m_tiles, tm = t - tn * p.m_tiles;
+        const int n0 = tn * bn;
+        if (tn != staged_tn) {                                      // M runs fastest: the column block (and its scale/bias) rarely changes
+            if (staged_tn >= 0) epi_bar_sync(ebar);                 // everyone is done with the previous tile's scale/bias
+            stage_scale_bias(p, n0, s_sbt, tid, ebar);
+            staged_tn = tn;
+        }
+        const int ab = it & 1;
+        {
+            const uint32_t bar = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
+            uint32_t spins = 0;
+            while (!mbar_try_wait(bar, par)) { __nanosleep(32); if (++spins > (1u << 26)) __trap(); }
+        }
+        tcgen05_fence_after();
+        if (tr && it < 16) p.trace[16 + it * 8 + 2] = (unsigned long long)clock64();
+#pragma unroll 1
+        for (int h = 0; h < kMp; ++h) {                             // the 128-row accumulators of this tile, one after the other
+        const int p0 = (tm * kMp + h) * kBlockM;
+        const long long pp = (long long)p0 + row;
+        const int rem = (int)(pp % HpWp);
+        const int y = rem / Wp, xx = rem - y * Wp;
+        const bool valid = pp < p.P_total && (p.gemm || (y >= 1 && y <= p.Ho && xx >= 1 && xx <= p.Wo));
+        const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;             // border pixels are stored as zeros (branch-free)
+        const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * kMp + h) * bn);
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g, ++q) {
+            const uint32_t b = (uint32_t)(q % nbuf);
+            // the whole 64-column group is read out of TMEM first (64 registers; one CTA per SM leaves room for them), so the
+            // accumulator goes back to the MMA issuer ~300 clocks after it was complete instead of after three quarters of the
+            // group's arithmetic: with short tiles (1x1, K = 64) that wait was the tile period
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            const uint32_t tg = tbase + (uint32_t)(g * 64);
+            __syncwarp();
+            tmem_ld_32x32b_x16(tg, v0);
+            tmem_ld_32x32b_x16(tg + 16u, v1);
+            tmem_ld_32x32b_x16(tg + 32u, v2);
+            tmem_ld_32x32b_x16(tg + 48u, v3);
+            if (nbuf == 2 && q >= 2) {                              // the buffer about to be refilled was handed to the TMA two groups ago
+                if (tid == 0) tma_store_wait_read<1>();
+                epi_bar_sync(ebar);
+            }
+            uint4* rbase = reinterpret_cast<uint4*>(smem_generic + (stage_u32 - smem_generic_u32) + (size_t)b * (kBlockM * 128u) + (size_t)row * 128u);
+            tcgen05_wait_ld();
+            if (g + 1 == ngroups && h == kMp - 1) {                 // last read of this tile's accumulators: hand them back to the MMA issuer
+                tcgen05_fence_before();
+                mbar_arrive(bar_tempty + 8u * ab);
+                if (tr && it < 16) p.trace[16 + it * 8 + 5] = (unsigned long long)clock64();
+            }
+            if (has_res) {
+                const uint32_t bar = bar_res + 8u * b, par = ((uint32_t)(q / nbuf)) & 1u;
+                uint32_t spins = 0;
+                while (!mbar_try_wait(bar, par)) { if (++spins > (1u << 28)) __trap(); }
+            }
+            auto process = [&](const uint32_t (&v)[16], int sub) {
+                const int cl = g * 64 + sub * 16;
+                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, w0, w1;
+                if (has_res) { r0 = rbase[(2 * sub) ^ x]; r1 = rbase[(2 * sub + 1) ^ x]; }
+                if (kAct >= 0) {
+                    finish16_static<kAct, kRes>(v, s_sbt + cl, s_sbt + bn + cl, r0, r1, w0, w1);
+                } else {
+                    float acc[16], o[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+                    compute16<kMish>(p, acc, s_sbt + cl, s_sbt + bn + cl, r0, r1, o);
+                    pack16(o, w0, w1);
+                }
+                w0.x &= keep; w0.y &= keep; w0.z &= keep; w0.w &= keep;
+                w1.x &= keep; w1.y &= keep; w1.z &= keep; w1.w &= keep;
+                rbase[(2 * sub) ^ x] = w0;
+                rbase[(2 * sub + 1) ^ x] = w1;
+            };
+            process(v0, 0);
+            if (tr && it < 16 && g == 0 && h == 0 && it >= 8) p.trace[16 + it * 8 + 4] = (unsigned long long)clock64();   // (debug: first block done; tiles 8+ only)
+            process(v1, 1);
+            process(v2, 2);
+            process(v3, 3);
+            fence_proxy_async();                                    // generic-proxy smem writes -> visible to the TMA (async proxy)
+            if (tr && it < 16 && g == 0 && h == 0) p.trace[16 + it * 8 + 6] = (unsigned long long)clock64();
+            epi_bar_sync(ebar);
+            if (tr && it < 16 && g == 0 && h == 0) p.trace[16 + it * 8 + 7] = (unsigned long long)clock64();
+            if (tid == 0) {
+                tma_store_2d(out_map, stage_u32 + b * (kBlockM * 128u), p.out_coff + n0 + g * 64, p0);
+                tma_store_commit();
+                if (nbuf == 3) {
+                    tma_store_wait_read<1>();                       // store q - 1 has been read: buffer (q + 2) % 3 is free
+                    if (has_res) fetch_res(q + 2);
+                }
+            }
+        }
+        }   // h
+        if (tr && it < 16) p.trace[16 + it * 8 + 3] = (unsigned long long)clock64();
+    }
+    if (tid == 0) tma_store_wait_read<0>();                         // smem must outlive the bulk reads; writes are complete at grid end
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tap-per-stage kernel: stride-2 convolutions (parity sub-lattice tensor maps) and channel blocks narrower than 64.
 // ---------------------------------------------------------------------------------------------
@@ -456,7 +596,7 @@ template <bool kMish>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     const uint32_t row_bytes = (uint32_t)p.block_k * 2u;
     const uint32_t a_bytes = kBlockM * row_bytes;
@@ -507,34 +647,41 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     }
     const int num_kb = p.R * p.S * p.cin_blocks;
 
+    // (both issuing warps run warp-uniform loops; only TMA / expect_tx / tcgen05.mma / tcgen05.commit come from the elected lane:
+    //  see conv_tc2_kernel)
     if (warp == 4) {
-        if (elect_one()) {
+        const bool leader = elect_one();
+        {
             // ================= TMA producer =================
             grid_dep_wait();
             int s = 0, cb = 0, r = 0, sx = 0;
             uint32_t ph = 1;
+            const int cin_blocks = p.cin_blocks, block_k = p.block_k, S = p.S, mode = p.mode;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait_hot(bar_empty + 8u * s, ph);
                 const uint32_t full = bar_full + 8u * s;
-                mbar_arrive_expect_tx(full, a_bytes + b_bytes);
-                const int c0 = cb * p.block_k;
+                const int c0 = cb * block_k;
                 const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-                if (p.mode == 0) {
-                    const int row = p0 + (r - p.R / 2) * p.in_Wp + (sx - p.S / 2);
-                    tma_load_2d(a_dst, &maps.a[0], full, c0, row);
-                } else {
-                    const int Y = r + p.pad_shift, X = sx + p.pad_shift;
-                    tma_load_3d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1),
-                                img * p.in_Hp_half + yo0 + (Y >> 1));
+                if (leader) {
+                    mbar_arrive_expect_tx(full, a_bytes + b_bytes);
+                    if (mode == 0) {
+                        const int row = p0 + (r - p.R / 2) * p.in_Wp + (sx - S / 2);
+                        tma_load_2d(a_dst, &maps.a[0], full, c0, row);
+                    } else {
+                        const int Y = r + p.pad_shift, X = sx + p.pad_shift;
+                        tma_load_3d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1),
+                                    img * p.in_Hp_half + yo0 + (Y >> 1));
+                    }
+                    tma_load_2d(a_dst + a_bytes, &maps.b, full, (r * S + sx) * p.cin + c0, n0);
                 }
-                tma_load_2d(a_dst + a_bytes, &maps.b, full, (r * p.S + sx) * p.cin + c0, n0);
-                if (++cb == p.cin_blocks) { cb = 0; if (++sx == p.S) { sx = 0; ++r; } }
+                if (++cb == cin_blocks) { cb = 0; if (++sx == S) { sx = 0; ++r; } }
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            prefetch_next_weights(p);
+            if (leader) prefetch_next_weights(p);
         }
     } else if (warp == 5) {
-        if (elect_one()) {
+        const bool leader = elect_one();
+        {
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
             const uint32_t hi = desc_hi(row_bytes);
@@ -546,14 +693,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                 tcgen05_fence_after();
                 const uint32_t a_lo = desc_lo(smem_base + (uint32_t)s * stage_bytes);
                 const uint32_t b_lo = a_lo + (a_bytes >> 4);
-                for (int k = 0; k < ksteps; ++k) {
-                    umma_f16_lh(tmem_base, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
-                    acc = 1;
+                if (leader) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        umma_f16_lh(tmem_base, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
+                        acc = 1;
+                    }
+                    umma_commit(bar_empty + 8u * s);     // frees the smem stage once these MMAs retire
                 }
-                umma_commit(bar_empty + 8u * s);     // frees the smem stage once these MMAs retire
+                acc = 1;
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            umma_commit(bar_tmem);                   // accumulator complete
+            if (leader) umma_commit(bar_tmem);           // accumulator complete
         }
     } else {
         // ================= epilogue =================
@@ -610,7 +760,7 @@ template <bool kMish, bool kPers, bool kPair>
 __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // (warp-uniform for the compiler too)
     constexpr int kEpiGroups = 2;                              // epilogue warpgroups of 4 warps
     constexpr int kProdWarp = 4 * kEpiGroups, kMmaWarp = kProdWarp + 1;
     if (threadIdx.x == 0) trace_mark(p, 0);
@@ -624,7 +774,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
     // (they are being refilled for the next tile while the epilogue runs); otherwise the staging aliases the dead stages
-    const uint32_t stage_area = (kPers && p.store_tma) ? 4u * kBlockM * 128u : 0u;    // two 16 KB buffers per epilogue warpgroup
+    const uint32_t stage_area = kPers ? 2u * (uint32_t)p.nbuf * kBlockM * 128u : 0u;   // nbuf 16 KB buffers per epilogue team
     const uint32_t a_base = smem_base + stage_area;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     // the wide epilogue stages one 16 KB buffer per 64-column group over the (then dead) operand stages: keep the barriers clear of it
@@ -636,7 +786,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     const uint32_t bar_fullB = bar_emptyA + 8u * p.a_stages, bar_emptyB = bar_fullB + 8u * p.b_stages;
     const uint32_t bar_tfull = bar_emptyB + 8u * p.b_stages;   // [2] accumulator complete
     const uint32_t bar_tempty = bar_tfull + 16u;               // [2] accumulator drained by the epilogue (128 arrivals)
-    const uint32_t bar_res = bar_tempty + 16u;                 // [4] residual tile of a 64-column group has landed (wide epilogue)
+    const uint32_t bar_res = bar_tempty + 16u;                 // [8] residual tile of a 64-column group has landed (wide: [group]; persistent: [team][buffer])
     // Wide epilogue with a residual: the tiles are fetched by the PRODUCER into the weight stages as the last MMAs release them
     // (up to b_stages - 1 taps before the accumulator is complete), and the results are staged in place.  Group g lives in the
     // (g / gps)-th stage to be released after the last weight load, gps = 16 KB tiles per stage.
@@ -652,7 +802,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             if (++k == gps) { k = 0; if (++st == p.b_stages) st = 0; }
         }
     };
-    const uint32_t tmem_slot = bar_res + 32u, flag_slot = tmem_slot + 4u;
+    const uint32_t tmem_slot = bar_res + 64u, flag_slot = tmem_slot + 4u;
     float* s_sb = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.block_n * mp * (kPers ? 2 : 1)) tmem_cols <<= 1;
@@ -662,7 +812,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         for (int s = 0; s < p.a_stages; ++s) mbar_init(bar_emptyA + 8u * s, 1);
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, 128); }
-        for (int s = 0; s < 4; ++s) mbar_init(bar_res + 8u * s, 1);
+        for (int s = 0; s < 8; ++s) mbar_init(bar_res + 8u * s, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -670,7 +820,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
         if (p.store_tma) tma_prefetch_desc(&maps.a[1]);
-        if (wide && p.res_mode) tma_prefetch_desc(&maps.a[2]);
+        if ((wide || kPers) && p.res_mode) tma_prefetch_desc(&maps.a[2]);
     }
     if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, tmem_cols);
@@ -699,47 +849,53 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         return true;
     };
 
-    // Register re-allocation: two co-resident CTAs cap every warp at 96 registers at launch (30 720 per CTA).  The two single-thread
-    // warps (one warpgroup) shrink to 24, the eight epilogue warps -- two 16-column accumulator blocks in flight, scale/bias,
-    // residual -- grow to 112: 64 * 24 + 256 * 112 = 30 208 <= 30 720, so the .inc never waits on registers that do not exist.
-    // (ptxas only honours the new budget for code dominated by the instruction, so each role issues its own.)
-    constexpr bool kRealloc = !kPers && !kPair;
+    // The two issuing warps run their loops with ALL lanes (warp-uniform control flow and operands, so ring indices, phases and
+    // descriptor words live in uniform registers and feed UTCHMMA / UTMALDG directly); only the instructions that must come from one
+    // thread -- TMA, expect_tx, tcgen05.mma, tcgen05.commit -- are guarded by the elected lane.  With the whole loop inside
+    // `if (elect_one())` every descriptor word went through R2UR and the issue loop cost ~70 clk per MMA and ~900 clk of scalar
+    // bookkeeping per tile (measured, YDST_CONV_TRACE=1): more than an N = 64 MMA takes on the tensor pipe.
     if (warp == kProdWarp) {
-        if constexpr (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (elect_one()) {
+        const bool leader = elect_one();
+        {
             // ================= TMA producer =================
             int sa = 0, sb = 0, loaded_tn = -1;
             uint32_t pha = 1, phb = 1;
-            int tm, tn;
-            for (int it = 0; tile_at(it, tm, tn); ++it) {
+            const int a_stages = p.a_stages, b_stages = p.b_stages, tpb = p.tpb, a_boxes = p.a_boxes, a_box_rows = p.a_box_rows;
+            const int m_tiles = p.m_tiles, G = (int)gridDim.x;
+            const int total_b = nmacro * nbs;
+            int tm = kPers ? (int)blockIdx.x % m_tiles : (int)blockIdx.x, tn = kPers ? (int)blockIdx.x / m_tiles : (int)blockIdx.y;
+            for (int it = 0, t = (int)blockIdx.x; kPers ? t < total_tiles : it == 0; ++it, t += G) {
                 const int p0 = tm * kBlockM * mp, n0 = tn * p.block_n;
                 int jm = 0, js = 0;                            // next weight stage to issue: macro step jm, sub-stage js
-                const int total_b = nmacro * nbs;
                 auto issue_b = [&]() {
                     mbar_wait_hot(bar_emptyB + 8u * sb, phb);
                     const uint32_t full = bar_fullB + 8u * sb;
-                    mbar_arrive_expect_tx(full, b_stage_bytes);
-                    if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * p.tpb);
-                    else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * p.tpb);
+                    if (leader) {
+                        mbar_arrive_expect_tx(full, b_stage_bytes);
+                        if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * tpb);
+                        else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * tpb);
+                    }
                     if (++js == nbs) { js = 0; ++jm; }
-                    if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+                    if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                 };
                 auto load_a = [&](int i) {
                     mbar_wait_hot(bar_emptyA + 8u * sa, pha);
                     const uint32_t full = bar_fullA + 8u * (uint32_t)(sa * nab);
                     const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
-                    if (k3) {
-                        // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
-                        for (int b = 0; b < p.a_boxes; ++b) {
-                            mbar_arrive_expect_tx(full + 8u * b, (uint32_t)p.a_box_rows * 128u);
-                            tma_load_2d(dst + (uint32_t)(b * p.a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
-                                        p0 - p.halo + b * p.a_box_rows);
+                    if (leader) {
+                        if (k3) {
+                            // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
+                            for (int b = 0; b < a_boxes; ++b) {
+                                mbar_arrive_expect_tx(full + 8u * b, (uint32_t)a_box_rows * 128u);
+                                tma_load_2d(dst + (uint32_t)(b * a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
+                                            p0 - p.halo + b * a_box_rows);
+                            }
+                        } else {
+                            mbar_arrive_expect_tx(full, a_stage_bytes);
+                            tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * tpb);
                         }
-                    } else {
-                        mbar_arrive_expect_tx(full, a_stage_bytes);
-                        tma_load_3d(dst, &maps.a[0], full, 0, p0, cb0 + i * p.tpb);
                     }
-                    if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+                    if (++sa == a_stages) { sa = 0; pha ^= 1u; }
                 };
                 int issued = 0;
                 if (kPers && p.b_resident) {
@@ -754,17 +910,18 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                 if (it == 0) {
                     // weights never depend on the previous kernel: queue them before waiting on the grid dependency, so that
                     // under programmatic dependent launch they stream in while the producer of our input is still draining
-                    const int pre = p.pdl ? p.b_stages : 1;
+                    const int pre = p.pdl ? b_stages : 1;
                     for (; issued < total_b && issued < pre; ++issued) issue_b();
                     grid_dep_wait();                           // the activations are the previous kernel's output
-                    trace_mark(p, 2);
+                    if (leader) trace_mark(p, 2);
                 }
                 load_a(0);
                 for (int i = 0; i < nmacro; ++i) {
-                    if (p.a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
+                    if (a_stages > 1 && i + 1 < nmacro) load_a(i + 1);
                     for (; issued < (i + 1) * nbs; ++issued) issue_b();
-                    if (p.a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
+                    if (a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
                 }
+                if (kPers) { tm += G; while (tm >= m_tiles) { tm -= m_tiles; ++tn; } }
             }
             if (res_early) {
                 // sb / phb point at the next stage the ring would refill, i.e. the next one the MMAs release
@@ -773,112 +930,152 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                 group_addrs(gaddr, sb);
                 for (int g = 0; g < ngroups && n0 + g * 64 < p.cout; ++g) {
                     if (g % (int)gps == 0) {
-                        if (g) { if (++sb == p.b_stages) { sb = 0; phb ^= 1u; } }
+                        if (g) { if (++sb == b_stages) { sb = 0; phb ^= 1u; } }
                         mbar_wait_hot(bar_emptyB + 8u * sb, phb);
                     }
-                    mbar_arrive_expect_tx(bar_res + 8u * g, kBlockM * 128u);
-                    tma_load_2d(gaddr[g], &maps.a[2], bar_res + 8u * g, p.res_coff + n0 + g * 64, p0);
+                    if (leader) {
+                        mbar_arrive_expect_tx(bar_res + 8u * g, kBlockM * 128u);
+                        tma_load_2d(gaddr[g], &maps.a[2], bar_res + 8u * g, p.res_coff + n0 + g * 64, p0);
+                    }
                 }
             }
-            prefetch_next_weights(p);
+            if (leader) prefetch_next_weights(p);
         }
     } else if (warp == kMmaWarp) {
-        if constexpr (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (elect_one()) {
+        const bool leader = elect_one();
+        {
             // ================= MMA issuer =================
             const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
             const uint32_t hi = desc_hi(128);
             const uint32_t b_tile16 = b_tile_bytes >> 4;
-            int sa = 0, sb = 0, prev_tn = -1;
+            const int a_stages = p.a_stages, b_stages = p.b_stages, tpb = p.tpb, bn = p.block_n;
+            const int m_tiles = p.m_tiles, G = (int)gridDim.x;
+            const bool bo1 = p.bo_mode == 1;
+            const bool tr = kPers && p.trace && p.trace_tiles && blockIdx.x == 0;
+            // 3x3: filter row r reads chunk rows up to r*Wp + 2 + 127, i.e. needs the chunk's TMA boxes up to index need[r]
+            int need[3] = {0, 0, 0};
+            if (k3)
+                for (int r = 0; r < 3; ++r) need[r] = min(p.a_boxes - 1, (r * p.in_Wp + kBlockM * mp + 1) / p.a_box_rows);
+            const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;            // 16-byte units: next filter row
+            int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             const bool resident = kPers && p.b_resident;
-            int tm, tn;
-            for (int it = 0; tile_at(it, tm, tn); ++it) {
+            int tn = kPers ? (int)blockIdx.x / m_tiles : (int)blockIdx.y, tm = kPers ? (int)blockIdx.x % m_tiles : 0;
+            int prev_tn = -1;
+            for (int it = 0, t = (int)blockIdx.x; kPers ? t < total_tiles : it == 0; ++it, t += G) {
                 // weight-stationary tiles: wait for the slab only on its first use, release it only after its last use; the ring
                 // index restarts at 0 every tile (the slab occupies the whole ring) and the phase flips once per slab, not per tile
                 bool first_use = true, last_use = true;
+                int tm_next = tm, tn_next = tn;
+                if (kPers) { tm_next += G; while (tm_next >= m_tiles) { tm_next -= m_tiles; ++tn_next; } }
                 if (resident) {
-                    int tm2, tn2;
                     first_use = tn != prev_tn;
-                    last_use = !tile_at(it + 1, tm2, tn2) || tn2 != tn;
+                    last_use = t + G >= total_tiles || tn_next != tn;
                     prev_tn = tn;
                     sb = 0;
                 }
                 const int ab = it & 1;                         // accumulator buffer
-                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * p.block_n * mp);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * bn * mp);
                 if (kPers) mbar_wait_hot(bar_tempty + 8u * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
                 tcgen05_fence_after();
+                if (tr && leader && it < 8) p.trace[16 + it * 8 + 4] = (unsigned long long)clock64();
                 uint32_t acc = 0;
                 for (int i = 0; i < nmacro; ++i) {
                     const uint32_t fullA = bar_fullA + 8u * (uint32_t)(sa * nab);
                     mbar_wait_hot(fullA, pha);
+                    if (tr && leader && i == 0 && it < 16) p.trace[16 + it * 8] = (unsigned long long)clock64();
                     const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)sa * a_stage_bytes);
                     if (k3) {
-                        const uint32_t row_step = (uint32_t)p.in_Wp * 8u - 24u;        // 16-byte units: next filter row
                         uint32_t a_lo = a_lo0;
                         int t_in = 0, box_ready = 0;
                         uint32_t b_lo = 0;
+#pragma unroll
                         for (int r = 0; r < 3; ++r, a_lo += row_step) {
-                            // filter row r reads chunk rows up to r*Wp + 2 + 127
-                            const int need = min(p.a_boxes - 1, (r * p.in_Wp + kBlockM * mp + 1) / p.a_box_rows);
-                            while (box_ready < need) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
+                            while (box_ready < need[r]) mbar_wait_hot(fullA + 8u * (uint32_t)(++box_ready), pha);
+#pragma unroll
                             for (int sx = 0; sx < 3; ++sx, a_lo += 8u) {
                                 if (t_in == 0) {
                                     if (first_use) mbar_wait_hot(bar_fullB + 8u * sb, phb);
                                     tcgen05_fence_after();
-                                    if (acc == 0 && it == 0) trace_mark(p, 3);
+                                    if (leader && acc == 0 && it == 0) trace_mark(p, 3);
                                     b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
                                 }
                                 uint32_t hi_a = hi;
-                                if (p.bo_mode == 1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
+                                if (bo1) hi_a |= ((a_lo >> 3) & 7u) << 17;  // base_offset probe (bits 49..51)
+                                if (leader) {
 #pragma unroll
-                                for (int h = 0; h < mp; ++h) {         // the M tiles of the pair share this weight tile
-                                    const uint32_t td = tmem_d + (uint32_t)(h * p.block_n), al = a_lo + (uint32_t)h * (kBlockM * 8u);
-                                    umma_f16_lh(td, al, b_lo, hi_a, idesc, acc);
-                                    umma_f16_lh(td, al + 2u, b_lo + 2u, hi_a, idesc, 1u);
-                                    umma_f16_lh(td, al + 4u, b_lo + 4u, hi_a, idesc, 1u);
-                                    umma_f16_lh(td, al + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                                    for (int h = 0; h < mp; ++h) {         // the M tiles of the pair share this weight tile
+                                        const uint32_t td = tmem_d + (uint32_t)(h * bn), al = a_lo + (uint32_t)h * (kBlockM * 8u);
+                                        umma_f16_lh(td, al, b_lo, hi_a, idesc, acc);
+                                        umma_f16_lh(td, al + 2u, b_lo + 2u, hi_a, idesc, 1u);
+                                        umma_f16_lh(td, al + 4u, b_lo + 4u, hi_a, idesc, 1u);
+                                        umma_f16_lh(td, al + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                                    }
                                 }
                                 acc = 1u;
                                 b_lo += b_tile16;
-                                if (++t_in == p.tpb) {
+                                if (++t_in == tpb) {
                                     t_in = 0;
-                                    if (last_use) umma_commit(bar_emptyB + 8u * sb);
-                                    if (++sb == p.b_stages) { sb = 0; if (!resident) phb ^= 1u; }
+                                    if (last_use && leader) umma_commit(bar_emptyB + 8u * sb);
+                                    if (++sb == b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                                 }
                             }
                         }
                     } else {
                         if (first_use) mbar_wait_hot(bar_fullB + 8u * sb, phb);
                         tcgen05_fence_after();
-                        if (acc == 0 && it == 0) trace_mark(p, 3);
+                        if (leader && acc == 0 && it == 0) trace_mark(p, 3);
                         uint32_t a_lo = a_lo0, b_lo = desc_lo(b_base + (uint32_t)sb * b_stage_bytes);
-                        const int nsl = min(p.tpb, ncb - i * p.tpb);                  // the last group of a split may be short
-                        for (int t = 0; t < nsl; ++t, a_lo += a_tile_bytes >> 4, b_lo += b_tile16) {
+                        const int nsl = min(tpb, ncb - i * tpb);                      // the last group of a split may be short
+                        for (int tt = 0; tt < nsl; ++tt, a_lo += a_tile_bytes >> 4, b_lo += b_tile16) {
+                            if (leader) {
 #pragma unroll
-                            for (int h = 0; h < mp; ++h) {
-                                const uint32_t td = tmem_d + (uint32_t)(h * p.block_n), al = a_lo + (uint32_t)h * (kBlockM * 8u);
-                                umma_f16_lh(td, al, b_lo, hi, idesc, acc);
-                                umma_f16_lh(td, al + 2u, b_lo + 2u, hi, idesc, 1u);
-                                umma_f16_lh(td, al + 4u, b_lo + 4u, hi, idesc, 1u);
-                                umma_f16_lh(td, al + 6u, b_lo + 6u, hi, idesc, 1u);
+                                for (int h = 0; h < mp; ++h) {
+                                    const uint32_t td = tmem_d + (uint32_t)(h * bn), al = a_lo + (uint32_t)h * (kBlockM * 8u);
+                                    umma_f16_lh(td, al, b_lo, hi, idesc, acc);
+                                    umma_f16_lh(td, al + 2u, b_lo + 2u, hi, idesc, 1u);
+                                    umma_f16_lh(td, al + 4u, b_lo + 4u, hi, idesc, 1u);
+                                    umma_f16_lh(td, al + 6u, b_lo + 6u, hi, idesc, 1u);
+                                }
                             }
                             acc = 1u;
                         }
-                        if (last_use) umma_commit(bar_emptyB + 8u * sb);
-                        if (++sb == p.b_stages) { sb = 0; if (!resident) phb ^= 1u; }
+                        if (last_use && leader) umma_commit(bar_emptyB + 8u * sb);
+                        if (++sb == b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                     }
-                    umma_commit(bar_emptyA + 8u * sa);
-                    if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+                    if (leader) umma_commit(bar_emptyA + 8u * sa);
+                    if (++sa == a_stages) { sa = 0; pha ^= 1u; }
                 }
-                umma_commit(bar_tfull + 8u * ab);
+                if (leader) umma_commit(bar_tfull + 8u * ab);
+                if (tr && leader && it < 16) p.trace[16 + it * 8 + 1] = (unsigned long long)clock64();
                 if (resident && last_use) phb ^= 1u;           // the next slab lands in the next phase of every weight barrier
-                if (it == 0) trace_mark(p, 4);
+                if (leader && it == 0) trace_mark(p, 4);
+                tm = tm_next; tn = tn_next;
             }
         }
     } else {
         // ================= epilogue =================
-        if constexpr (kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        if constexpr (kPers) {
+            // persistent tile loop with TMA stores (the planner only makes store_tma launches persistent): two teams alternate tiles
+            const int team = warp >> 2;
+            grid_dep_wait();                                   // residual / output buffers belong to earlier kernels
+#define YDST_PERS(A, R) epilogue_persistent<kMish, A, R, mp>(p, &maps.a[1], &maps.a[2], smem_raw, smem_u32(smem_raw),                       \
+                                                         smem_base + (uint32_t)team * (uint32_t)p.nbuf * (kBlockM * 128u), tmem_base, team, \
+                                                         s_sb + team * 512, bar_tfull, bar_tempty, bar_res + 24u * team)
+            const int key = p.act * 4 + p.res_mode;            // warp-uniform: one specialised epilogue per common combination
+            if (kMish) {
+                if (key == ACT_MISH * 4 + 0) YDST_PERS(ACT_MISH, 0);
+                else if (key == ACT_MISH * 4 + 1) YDST_PERS(ACT_MISH, 1);
+                else YDST_PERS(-1, -1);
+            } else {
+                if (key == ACT_LEAKY * 4 + 0) YDST_PERS(ACT_LEAKY, 0);
+                else if (key == ACT_LEAKY * 4 + 1) YDST_PERS(ACT_LEAKY, 1);
+                else if (key == ACT_RELU * 4 + 0) YDST_PERS(ACT_RELU, 0);
+                else if (key == ACT_RELU * 4 + 2) YDST_PERS(ACT_RELU, 2);
+                else YDST_PERS(-1, -1);
+            }
+#undef YDST_PERS
+        } else {
         const int eg = kPers ? warp >> 2 : 0;                  // persistent: the warpgroups alternate tiles
         const int half = kPers ? 0 : warp >> 2;                // otherwise: both work on the one tile (wide epilogue), or the second idles
         const int tid = threadIdx.x & 127, ebar = 1 + eg;
@@ -1008,6 +1205,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             }   // h
         }
         if (p.store_tma && tid == 0) tma_store_wait_read<0>();    // smem must outlive the bulk reads; writes are complete at grid end
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -1069,9 +1267,10 @@ static int env_int(const char* name, int dflt) {
 //   * tensor time: a 128 x bn x 16 MMA takes ~max(16, bn/2) clocks;
 //   * barrier round trips of the single issuing thread (~150 clocks per stage).
 // Small-M layers may split K over channel blocks (grid.z); the fp32 partials then take a round trip through the workspace.
-ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets) {
+ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets, int res_mode,
+                                 bool allow_pers) {
     const int kSms = 148;
-    const double kFill = 42.0, kLat = 2100.0, kSetup = 900.0, kFirst = 2200.0, kStep = 600.0, kClkPerUs = 1900.0;
+    const double kFill = 42.0, kLat = 2100.0, kLatPers = 4000.0, kSetup = 900.0, kFirst = 2200.0, kStep = 600.0, kClkPerUs = 1900.0;
     // narrow layers (cout < 64) may use a 64-wide N tile: the weight rows past cout are zero-filled by TMA and the store is clipped
     // at the end of the layer's channel slice, so they too get the eight-warp TMA-store epilogue instead of thread-per-row stores
     const bool tma_store_ok = cout16 % 64 == 0 || cout16 < 64;
@@ -1083,14 +1282,16 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
     const int force_bn = env_int("YDST_FORCE_BN", 0);          // tuning aid: restrict the N tile (when the layer allows it)
     // measured on B200: neither M pairs nor the persistent tile loop beat the plain one-tile-per-CTA launch yet
     // (1163 / 1198 / 1226 frames/s for pair+persistent / persistent / neither at micro-batch 4), so both are opt-in
-    const int allow_pair = env_int("YDST_MPAIR", 0);
+    const int allow_pair = env_int("YDST_MPAIR", 0), force_mp = env_int("YDST_FORCE_MPAIR", 0);
+    const int pers_mode = env_int("YDST_PERSISTENT", 1);      // 0 off, 1 weight-stationary many-tile layers only, 2 wherever the clock model prefers it
     for (int mp = 1; mp <= 2; ++mp)
     for (int bn = bn_cap; bn >= 32; bn >>= 1) {
         if (force_bn && bn != std::min(force_bn, bn_cap)) continue;
         const int n_tiles = (cout16 + bn - 1) / bn;
         // a pair of M tiles per CTA shares every weight stage (half the weight traffic per output); only worth it when there are
         // tiles to spare, i.e. at least two waves of single tiles
-        if (mp == 2 && (!allow_pair || (long long)m_tiles128 * n_tiles < 2 * kSms || bn > 128)) continue;
+        if (mp == 2 && ((long long)m_tiles128 * n_tiles < 2 * kSms || bn > 128)) continue;
+        if (force_mp && mp != force_mp && !(mp == 1 && ((long long)m_tiles128 * n_tiles < 2 * kSms || bn > 128))) continue;   // test hook
         const int m_tiles = (m_tiles128 + mp - 1) / mp;
         int a_rows = kBlockM * mp + 2 * halo;
         { const int boxes = (a_rows + 255) / 256; a_rows = ((a_rows + boxes - 1) / boxes) * boxes; }
@@ -1107,6 +1308,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
             const long long ctas = tiles * ks;
             // two CTAs per SM: 227 KB of shared memory less 1 KB of system use per CTA -> 113 KB each
             const int budget_max = env_int("YDST_SMEM_BUDGET_KB", 200) * 1024, budget_2 = env_int("YDST_SMEM_BUDGET2_KB", 113) * 1024;
+            const int budget_pers = env_int("YDST_SMEM_BUDGET_PERS_KB", 225) * 1024;   // one CTA per SM: everything the SM has (227 KB less alignment slack)
             const int co_model = env_int("YDST_CO_MODEL", 2);
             // weight-stage granularity: one TMA instruction costs the producer thread ~200 clocks to issue, so boxes below
             // ~16 KB make the PRODUCER the bottleneck (measured: tpb = 1 everywhere cost 15 % end to end); the step term below
@@ -1125,23 +1327,36 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 const int a_stages_max = std::min(nmacro, taps == 9 ? 2 : 4);
                 // pass 0: leave room for a second CTA on the SM; pass 1: whole SM; pass 2: persistent -- one CTA per SM loops over
                 // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
-                for (int pass = 0; pass < 3; ++pass)
-                for (int a_stages = a_stages_max; a_stages >= 1; --a_stages) {
-                    if (a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
-                    const bool pers = pass == 2;
-                    if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !env_int("YDST_PERSISTENT", 0))) continue;
-                    const int staging = pers ? 64 * 1024 : 0;       // two 16 KB store buffers per epilogue warpgroup
-                    const int budget = (pass == 0 ? budget_2 : budget_max) - staging;
+                // (persistent: staging buffers per epilogue team -- three let a residual tile be prefetched and save a barrier per group)
+                // A persistent CTA's activation ring runs ACROSS tiles (the next tiles' chunks are in flight while this one computes), so its
+                // depth is bound by the load latency, not by the tile's own k-steps: measured ~2500 clk per TMA round trip under load.
+                const int a_stages_pers = taps == 9 ? 4 : 8;
+                for (int pass = 0; pass < 4; ++pass)
+                for (int a_stages = pass >= 2 ? a_stages_pers : a_stages_max; a_stages >= 1; --a_stages) {
+                    const bool pers = pass >= 2;
+                    if (!pers && a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
+                    if (pers && a_stages < 2) break;
+                    const int nbuf = pass == 2 ? 3 : 2;
+                    const bool st_ok = tma_store_ok && bn >= 64 && (cout16 % bn == 0 || cout16 < 64);
+                    if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !allow_pers || !pers_mode)) continue;
+                    if (pers && (!st_ok || (nbuf == 2 && res_mode))) continue;
+                    if (mp == 2 && !pers && !allow_pair) continue;   // (plain launches: pairs measured slower than two co-resident CTAs)
+                    const int staging = pers ? 2 * nbuf * 16 * 1024 : 0;   // 16 KB store buffers per epilogue team
+                    const int budget = (pass == 0 ? budget_2 : pers ? budget_pers : budget_max) - staging;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
                     // a persistent CTA prefetches the next tile's operands while the current one computes: two stages of each at least
                     const int a_st = pers ? std::max(2, a_stages) : a_stages;
                     const int fixed_p = a_st * a_stage + 6144;
                     int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
-                    if (b_stages < (pers ? 2 : 1)) continue;
                     // weight-stationary persistent tiles: the N tile's whole weight slab fits and is fetched once per column block
                     const bool resident = pers && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
                                           env_int("YDST_B_RESIDENT", 1);
                     if (resident) b_stages = total_b;
+                    if (b_stages < (pers && !resident ? 2 : 1)) continue;
+                    // Measured: the persistent loop pays where the weights stay in shared memory and a CTA walks many
+                    // tiles (ReID layer1: 172 -> 90 us per conv); with streamed weights or few waves it only trades the PDL overlap of
+                    // plain launches for its own tail, so the default mode keeps those layers on plain launches.
+                    if (pers && pers_mode == 1 && (!resident || (long long)m_tiles128 * n_tiles < 6 * kSms)) continue;
                     int smem = fixed_p + b_stages * b_stage + staging;
                     // the TMA-store epilogue stages 16 KB per 64-column group (two buffers in persistent / pair mode) at the start of smem
                     smem = std::max(smem, std::max(2, bn / 64) * 16 * 1024 + 6144);
@@ -1150,9 +1365,10 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const double tiles_per_cta = std::ceil((double)ctas / kSms);
                     // CTAs sharing an SM fill it together: the bytes in flight are those of all co-resident CTAs
                     const double co = co_model ? std::min((double)occ, tiles_per_cta) : 1.0;
-                    const double rate = std::min(kFill, co * inflight / kLat);
+                    const double lat = pers ? kLatPers : kLat;    // a persistent CTA's loads queue behind those of every other SM's ring
+                    const double rate = std::min(kFill, co * inflight / lat);
                     // the two operand streams are pipelined separately: each is also bound by its own bytes in flight
-                    const double rate_a = co * (double)a_st * a_stage / kLat, rate_b = co * (double)b_stages * b_stage / kLat;
+                    const double rate_a = co * (double)a_st * a_stage / lat, rate_b = co * (double)b_stages * b_stage / lat;
                     const double b_share = resident ? 1.0 / std::max(1.0, std::min(tiles_per_cta, (double)m_tiles)) : 1.0;   // slab amortised over the CTA's M tiles
                     const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * bn * 128);
                     // one 128 x bn x 16 MMA takes bn/2 tensor clocks but also reads 4 KB of A and 32*bn B of B from shared memory
@@ -1169,7 +1385,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const double epi = mp * (700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0));
                     const double per_sm = std::ceil((double)ctas / kSms);
                     double t = kSetup + kFirst + per_sm * main_clk + std::ceil(per_sm / occ) * epi;
-                    if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, epi) + epi;   // front paid once, epilogues hidden
+                    if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, mp == 1 ? 0.5 * epi : epi) + epi;   // front paid once, epilogues hidden (two teams alternate)
                     else if (per_sm > 1) t += (per_sm - 1) / occ * (kSetup + kFirst);          // every further wave pays the front again
                     if (ks > 1) t += 1500.0 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / 30.0;
                     t /= kClkPerUs;
@@ -1179,7 +1395,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
-                        best.mpair = mp; best.b_resident = resident ? 1 : 0;
+                        best.mpair = mp; best.b_resident = resident ? 1 : 0; best.nbuf = pers ? nbuf : 0;
                     }
                 }
             }
@@ -1231,7 +1447,8 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             // ---- halo kernel ----
             p.v2 = 1;
             p.halo = halo;
-            ConvTiling t = conv_tc_choose_tiling(m_tiles, p.cout, R * S, p.cin_blocks, halo, ws ? ws->partial_bytes : 0, ws ? ws->n_tickets : 0);
+            ConvTiling t = conv_tc_choose_tiling(m_tiles, p.cout, R * S, p.cin_blocks, halo, ws ? ws->partial_bytes : 0, ws ? ws->n_tickets : 0, res_mode,
+                                                 !out_f32 && env_int("YDST_TMA_STORE", 1));
             YDST_CHECK(t.bn >= 32, "no feasible tiling for this convolution");
             p.mpair = t.mpair;
             const int a_rows = kBlockM * t.mpair + 2 * halo;
@@ -1258,7 +1475,8 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             p.ws = ws ? ws->partial : nullptr; p.tickets = ws ? ws->tickets : nullptr;
             p.bo_mode = env_int("YDST_BO_MODE", 0);
             p.store_tma = (!out_f32 && (p.cout % 64 == 0 || p.cout < 64) && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
-            if (t.persistent && !p.store_tma) t.smem_bytes -= 64 * 1024;   // no staging area needed
+            YDST_CHECK(!t.persistent || p.store_tma, "persistent tiles need the TMA-store epilogue");
+            p.nbuf = t.nbuf;
             const int K = R * S * in.C;
             if (R == 3) {
                 cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1428,7 +1646,7 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         unsigned long long* trace_dev = g_trace_dev;
         ConvTcParams prm = L.p;
         prm.pdl = use_pdl;
-        if (trace_on == 1) { YDST_CUDA(cudaMemsetAsync(trace_dev, 0, 16 * 8, stream)); prm.trace = trace_dev; }
+        if (trace_on == 1) { YDST_CUDA(cudaMemsetAsync(trace_dev, 0, (16 + 4 * 32) * 8, stream)); prm.trace = trace_dev; prm.trace_tiles = 1; }
         if (trace_on == 2) {                                  // timeline mode: one slot per launch, no synchronisation
             const int slot = g_trace_next++ % kTraceSlots;
             prm.trace = trace_dev + (size_t)slot * 16;          // not re-zeroed: a memset node would break the PDL chain
@@ -1461,6 +1679,16 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
                             "acc_ready %lld epilogue_done %lld exit %lld clk | cta0 %.2f us, last CTA started +%.2f us\n",
                     L.p.R, L.p.cin, L.p.cout, L.p.N, L.p.Ho, L.p.Wo, L.grid.x, L.grid.y, L.grid.z, L.p.block_n, d(0, 1), d(0, 2), d(0, 3), d(0, 4),
                     d(0, 5), d(0, 6), d(0, 7), (h[9] - h[8]) * 1e-3, ((long long)h[10] - (long long)h[8]) * 1e-3);
+            if (L.p.persistent) {
+                unsigned long long tt[8 * 16];
+                YDST_CUDA(cudaMemcpy(tt, trace_dev + 16, sizeof(tt), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "    tiles of CTA 0 (clk since start): accumulator free (MMA; tiles 8+: first 16 columns finished) | operands landed | MMAs committed | accumulator seen by the "
+                                "epilogue | accumulator released | group 0 staged | barrier passed | tile stored\n");
+                for (int i = 0; i < 16 && tt[8 * i]; ++i) {
+                    auto d = [&](int k) { return tt[8 * i + k] ? (long long)(tt[8 * i + k] - h[0]) : -1LL; };
+                    fprintf(stderr, "      [%2d] %lld | %lld | %lld | %lld | %lld | %lld | %lld | %lld\n", i, d(4), d(0), d(1), d(2), d(5), d(6), d(7), d(3));
+                }
+            }
             if (h[11]) fprintf(stderr, "    epilogue thread 100, group 0: acc_ready %lld | 16 cols in registers +%lld, computed +%lld, staged +%lld, next 16 cols in registers +%lld, "
                                "group staged and barrier passed +%lld (res_mode %d)\n", d(0, 5), d(5, 11), d(11, 15), d(15, 12), d(12, 13), d(13, 14), L.p.res_mode);
         }
