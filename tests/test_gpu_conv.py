@@ -45,6 +45,11 @@ CASES = [
     ("mpair_3x3_76_batch8_two_n_tiles", 8, 76, 76, 128, 256, 3, 1, True, 1, 1, False),
     ("mpair_persistent_reid_32x16_batch60_res", 60, 32, 16, 128, 128, 3, 1, True, 3, 2, False),
     ("mpair_persistent_1x1_152_batch3_odd", 3, 152, 152, 128, 64, 1, 1, True, 1, 0, False),
+    ("cta2_3x3_76_batch2_res_odd_tiles", 2, 76, 76, 128, 256, 3, 1, True, 1, 1, False),
+    ("cta2_1x1_38_batch8", 8, 38, 38, 512, 256, 1, 1, True, 1, 0, False),
+    ("cta2_mish_3x3_38_batch4_res", 4, 38, 38, 256, 512, 3, 1, True, 2, 1, False),
+    ("cta2_reid_16x8_batch40_res", 40, 16, 8, 256, 256, 3, 1, True, 3, 2, False),
+    ("cta2_3x3_152_two_boxes_bn128", 2, 152, 152, 64, 128, 3, 1, True, 1, 0, False),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),
@@ -59,6 +64,8 @@ def _opt_in_tilings(request, monkeypatch):
     name = request.node.name
     if "persistent" in name or "mpair" in name:
         monkeypatch.setenv("YDST_PERSISTENT", "2")
+    if "cta2" in name:
+        monkeypatch.setenv("YDST_CTA2", "2")
     if "mpair" in name:
         monkeypatch.setenv("YDST_MPAIR", "1")
         monkeypatch.setenv("YDST_FORCE_MPAIR", "2")

@@ -1,10 +1,7 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 200 python -m pytest tests/test_gpu_conv.py -x -q --timeout 30 > gpurun_out/r2r_conv_all.log 2>&1; tail -3 gpurun_out/r2r_conv_all.log | cut -c1-400
-for sh in "8 304 304 64 32 1 0" "408 64 32 64 64 3 2"; do
-echo "== shape $sh"
-YDST_CONV_TRACE=1 timeout 60 python tools/conv_probe_one.py $sh 2>&1 | grep -A12 "conv_trace" | tail -13 | cut -c1-300
-done > gpurun_out/r2r_traces.txt 2>&1
-cat gpurun_out/r2r_traces.txt
-timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 --dump-ops gpurun_out/r2r_ops.csv > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err
-cut -c1-200 gpurun_out/r2r_bench.json; tail -3 gpurun_out/r2r_bench.err
+for C in 0 1; do
+YDST_CTA2=$C timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 --dump-ops gpurun_out/r2u_ops_c$C.csv > gpurun_out/r2u_bench_c$C.json 2> gpurun_out/r2u_bench_c$C.err
+cut -c1-200 gpurun_out/r2u_bench_c$C.json; tail -3 gpurun_out/r2u_bench_c$C.err
+done
+YDST_CTA2=1 YDST_DEBUG_PLAN=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-api --no-b1 2>&1 >/dev/null | grep "^conv_plan" | awk '!seen[$0]++' > gpurun_out/r2u_plan_c1.txt

@@ -68,6 +68,41 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- cta_group::2 forms (a pair of CTAs on two SMs shares one 256-row MMA; cute/arch/mma_sm100_umma.hpp, copy_sm100_tma.hpp,
+// cutlass/arch/barrier.h name the same instructions).  The leader is the even CTA of the cluster: a shared::cluster address with
+// bit 24 cleared names the leader's copy of a barrier.
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void umma_f16_lh_2cta(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs once all tcgen05 ops issued so far have completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((unsigned short)3)
+                 : "memory");
+}
+// TMA loads into this CTA's shared memory whose bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // lean wait for the hot loops (the one in common.cuh carries a printf and is kept for the epilogue)
 __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -756,7 +791,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // Persistent instantiations run TWO epilogue warpgroups (warps 0-3 and 4-7): tile i is drained by group i & 1, which also owns
 // accumulator buffer i & 1, so the epilogues of consecutive tiles overlap each other as well as the main loop.
 static constexpr int kThreads2 = 320;   // warps 0-7: epilogue (two per TMEM lane quarter), warp 8: TMA producer, warp 9: MMA issuer + TMEM owner
-template <bool kMish, bool kPers, bool kPair>
+// kCta2: launched as clusters of two CTAs along M.  The pair computes a 256 x block_n tile with ONE tcgen05.mma.cta_group::2 stream
+// issued by the leader (even) CTA: each CTA stages the activation chunk of its own 128 rows and only HALF of the weight tile
+// (block_n / 2 output channels), so the weight bytes an SM has to pull out of L2 -- what bounds the 3x3 layers, whose 128-row
+// tiles re-stream up to 2.3 MB of weights each against ~42 B/clk/SM of L2 bandwidth -- halve, and so do the tensor core's
+// shared-memory reads of B.  Each CTA keeps its own 128 x block_n accumulator in its own TMEM and runs the usual epilogue.
+//   * both producers fill their own stages; every load completes on the LEADER's "full" barrier (which expects both CTAs' bytes);
+//   * the leader's commits arrive on the "empty" / "accumulator complete" barriers of BOTH CTAs (multicast);
+//   * TMEM is allocated / freed with the cta_group::2 forms by the same warp of both CTAs; cluster barriers bracket the kernel
+//     (barrier init visible to the peer before the first remote arrive; nobody exits while the peer can still touch its memory).
+template <bool kMish, bool kPers, bool kPair, bool kCta2 = false>
 __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -770,7 +814,10 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     constexpr int mp = kPair ? 2 : 1;                          // 128-row accumulators per tile (compile time: the issue loops unroll)
     const uint32_t a_tile_bytes = (uint32_t)(kBlockM * mp) * 128u;
     const uint32_t a_stage_bytes = k3 ? (((uint32_t)(p.a_box_rows * p.a_boxes) * 128u + 1023u) & ~1023u) : (uint32_t)p.tpb * a_tile_bytes;
-    const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+    uint32_t cta_rank = 0;
+    if constexpr (kCta2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool lead_cta = cta_rank == 0;
+    const uint32_t b_tile_bytes = (uint32_t)(kCta2 ? p.block_n >> 1 : p.block_n) * 128u;   // rows of the weight tile THIS CTA stages
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
     // (they are being refilled for the next tile while the epilogue runs); otherwise the staging aliases the dead stages
@@ -791,7 +838,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     // (up to b_stages - 1 taps before the accumulator is complete), and the results are staged in place.  Group g lives in the
     // (g / gps)-th stage to be released after the last weight load, gps = 16 KB tiles per stage.
     const uint32_t gps = b_stage_bytes / (kBlockM * 128u);
-    const bool res_early = wide && p.res_mode && gps >= 1u && (uint32_t)(p.block_n >> 6) <= gps * (uint32_t)p.b_stages && env_res_early(p);
+    const bool res_early = !kCta2 && wide && p.res_mode && gps >= 1u && (uint32_t)(p.block_n >> 6) <= gps * (uint32_t)p.b_stages && env_res_early(p);
     // (every role that needs the group addresses computes them itself: the divisions stay off the common prologue)
     auto group_addrs = [&](uint32_t (&ga)[4], int first_stage) {
         int st = first_stage;
@@ -823,11 +870,16 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         if ((wide || kPers) && p.res_mode) tma_prefetch_desc(&maps.a[2]);
     }
     if (warp == kMmaWarp) {
-        tmem_alloc(tmem_slot, tmem_cols);
-        tmem_relinquish();
+        if constexpr (kCta2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            tmem_alloc(tmem_slot, tmem_cols);
+            tmem_relinquish();
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (kCta2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     if (threadIdx.x == 0) trace_mark(p, 1);
     grid_dep_launch();
@@ -871,9 +923,17 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                     mbar_wait_hot(bar_emptyB + 8u * sb, phb);
                     const uint32_t full = bar_fullB + 8u * sb;
                     if (leader) {
-                        mbar_arrive_expect_tx(full, b_stage_bytes);
-                        if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * tpb);
-                        else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * tpb);
+                        if constexpr (kCta2) {
+                            // this CTA's half of the weight tile, counted on the leader's barrier (which expects both halves)
+                            const int nh = n0 + (int)cta_rank * (p.block_n >> 1);
+                            if (lead_cta) mbar_arrive_expect_tx(full, 2u * b_stage_bytes);
+                            if (k3) tma_load_3d_2cta(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, nh, js * tpb);
+                            else tma_load_3d_2cta(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, nh, cb0 + jm * tpb);
+                        } else {
+                            mbar_arrive_expect_tx(full, b_stage_bytes);
+                            if (k3) tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, (cb0 + jm) * 64, n0, js * tpb);
+                            else tma_load_3d(b_base + (uint32_t)sb * b_stage_bytes, &maps.b, full, 0, n0, cb0 + jm * tpb);
+                        }
                     }
                     if (++js == nbs) { js = 0; ++jm; }
                     if (++sb == b_stages) { sb = 0; phb ^= 1u; }
@@ -883,7 +943,18 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                     const uint32_t full = bar_fullA + 8u * (uint32_t)(sa * nab);
                     const uint32_t dst = a_base + (uint32_t)sa * a_stage_bytes;
                     if (leader) {
-                        if (k3) {
+                        if constexpr (kCta2) {
+                            if (k3) {
+                                for (int b = 0; b < a_boxes; ++b) {
+                                    if (lead_cta) mbar_arrive_expect_tx(full + 8u * b, 2u * (uint32_t)a_box_rows * 128u);
+                                    tma_load_2d_2cta(dst + (uint32_t)(b * a_box_rows) * 128u, &maps.a[0], full + 8u * b, (cb0 + i) * 64,
+                                                     p0 - p.halo + b * a_box_rows);
+                                }
+                            } else {
+                                if (lead_cta) mbar_arrive_expect_tx(full, 2u * a_stage_bytes);
+                                tma_load_3d_2cta(dst, &maps.a[0], full, 0, p0, cb0 + i * tpb);
+                            }
+                        } else if (k3) {
                             // one barrier per box: the first filter row only needs the first box, so the MMAs start a box earlier
                             for (int b = 0; b < a_boxes; ++b) {
                                 mbar_arrive_expect_tx(full + 8u * b, (uint32_t)a_box_rows * 128u);
@@ -943,14 +1014,18 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         }
     } else if (warp == kMmaWarp) {
         const bool leader = elect_one();
-        {
+        if (!kCta2 || lead_cta) {                              // (a pair's MMAs all come from its leader CTA)
             // ================= MMA issuer =================
-            const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
+            const uint32_t idesc = make_idesc_f16(kCta2 ? 2 * kBlockM : kBlockM, p.block_n);
             const uint32_t hi = desc_hi(128);
             const uint32_t b_tile16 = b_tile_bytes >> 4;
             const int a_stages = p.a_stages, b_stages = p.b_stages, tpb = p.tpb, bn = p.block_n;
             const int m_tiles = p.m_tiles, G = (int)gridDim.x;
             const bool bo1 = p.bo_mode == 1;
+            auto mma = [&](uint32_t td, uint32_t al, uint32_t bl, uint32_t h, uint32_t accu) {
+                if constexpr (kCta2) umma_f16_lh_2cta(td, al, bl, h, idesc, accu); else umma_f16_lh(td, al, bl, h, idesc, accu);
+            };
+            auto commit = [&](uint32_t bar) { if constexpr (kCta2) umma_commit_2cta(bar); else umma_commit(bar); };
             const bool tr = kPers && p.trace && p.trace_tiles && blockIdx.x == 0;
             // 3x3: filter row r reads chunk rows up to r*Wp + 2 + 127, i.e. needs the chunk's TMA boxes up to index need[r]
             int need[3] = {0, 0, 0};
@@ -1006,17 +1081,17 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
 #pragma unroll
                                     for (int h = 0; h < mp; ++h) {         // the M tiles of the pair share this weight tile
                                         const uint32_t td = tmem_d + (uint32_t)(h * bn), al = a_lo + (uint32_t)h * (kBlockM * 8u);
-                                        umma_f16_lh(td, al, b_lo, hi_a, idesc, acc);
-                                        umma_f16_lh(td, al + 2u, b_lo + 2u, hi_a, idesc, 1u);
-                                        umma_f16_lh(td, al + 4u, b_lo + 4u, hi_a, idesc, 1u);
-                                        umma_f16_lh(td, al + 6u, b_lo + 6u, hi_a, idesc, 1u);
+                                        mma(td, al, b_lo, hi_a, acc);
+                                        mma(td, al + 2u, b_lo + 2u, hi_a, 1u);
+                                        mma(td, al + 4u, b_lo + 4u, hi_a, 1u);
+                                        mma(td, al + 6u, b_lo + 6u, hi_a, 1u);
                                     }
                                 }
                                 acc = 1u;
                                 b_lo += b_tile16;
                                 if (++t_in == tpb) {
                                     t_in = 0;
-                                    if (last_use && leader) umma_commit(bar_emptyB + 8u * sb);
+                                    if (last_use && leader) commit(bar_emptyB + 8u * sb);
                                     if (++sb == b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                                 }
                             }
@@ -1032,21 +1107,21 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
 #pragma unroll
                                 for (int h = 0; h < mp; ++h) {
                                     const uint32_t td = tmem_d + (uint32_t)(h * bn), al = a_lo + (uint32_t)h * (kBlockM * 8u);
-                                    umma_f16_lh(td, al, b_lo, hi, idesc, acc);
-                                    umma_f16_lh(td, al + 2u, b_lo + 2u, hi, idesc, 1u);
-                                    umma_f16_lh(td, al + 4u, b_lo + 4u, hi, idesc, 1u);
-                                    umma_f16_lh(td, al + 6u, b_lo + 6u, hi, idesc, 1u);
+                                    mma(td, al, b_lo, hi, acc);
+                                    mma(td, al + 2u, b_lo + 2u, hi, 1u);
+                                    mma(td, al + 4u, b_lo + 4u, hi, 1u);
+                                    mma(td, al + 6u, b_lo + 6u, hi, 1u);
                                 }
                             }
                             acc = 1u;
                         }
-                        if (last_use && leader) umma_commit(bar_emptyB + 8u * sb);
+                        if (last_use && leader) commit(bar_emptyB + 8u * sb);
                         if (++sb == b_stages) { sb = 0; if (!resident) phb ^= 1u; }
                     }
-                    if (leader) umma_commit(bar_emptyA + 8u * sa);
+                    if (leader) commit(bar_emptyA + 8u * sa);
                     if (++sa == a_stages) { sa = 0; pha ^= 1u; }
                 }
-                if (leader) umma_commit(bar_tfull + 8u * ab);
+                if (leader) commit(bar_tfull + 8u * ab);
                 if (tr && leader && it < 16) p.trace[16 + it * 8 + 1] = (unsigned long long)clock64();
                 if (resident && last_use) phb ^= 1u;           // the next slab lands in the next phase of every weight barrier
                 if (leader && it == 0) trace_mark(p, 4);
@@ -1208,10 +1283,11 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (kCta2) cluster_sync_all(); else __syncthreads();
     if (warp == kMmaWarp) {
         __syncwarp();
-        tmem_dealloc(tmem_base, tmem_cols);
+        if constexpr (kCta2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else tmem_dealloc(tmem_base, tmem_cols);
     }
     if (threadIdx.x == 0) trace_mark(p, 7);
 }
@@ -1283,6 +1359,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
     // measured on B200: neither M pairs nor the persistent tile loop beat the plain one-tile-per-CTA launch yet
     // (1163 / 1198 / 1226 frames/s for pair+persistent / persistent / neither at micro-batch 4), so both are opt-in
     const int allow_pair = env_int("YDST_MPAIR", 0), force_mp = env_int("YDST_FORCE_MPAIR", 0);
+    const int cta2_mode = env_int("YDST_CTA2", 0);            // 0 off, 1 3x3 layers where the clock model prefers it, 2 wherever legal (test hook)
     const int pers_mode = env_int("YDST_PERSISTENT", 1);      // 0 off, 1 weight-stationary many-tile layers only, 2 wherever the clock model prefers it
     for (int mp = 1; mp <= 2; ++mp)
     for (int bn = bn_cap; bn >= 32; bn >>= 1) {
@@ -1323,7 +1400,13 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 const int nbs = taps == 9 ? 9 / tpb : 1;
                 const int total_b = nmacro * nbs;
                 const int a_stage = taps == 9 ? chunk_bytes : tpb * kBlockM * mp * 128;
-                const int b_stage = tpb * bn * 128;
+                // c2 = 1: clusters of two CTAs share one cta_group::2 MMA stream -- each stages half of the weight tile (conv_tc2_kernel)
+                for (int c2 = 0; c2 <= (cta2_mode ? 1 : 0); ++c2) {
+                if (c2 && (mp != 1 || ks != 1 || bn < 128 || !allow_pers || m_tiles128 < 2 || !(tma_store_ok && (cout16 % bn == 0)) ||
+                           (cta2_mode == 1 && taps != 9)))
+                    continue;
+                if (!c2 && cta2_mode == 2 && mp == 1 && ks == 1 && bn >= 128 && allow_pers && m_tiles128 >= 2 && tma_store_ok && cout16 % bn == 0) continue;   // test hook: force pairs
+                const int b_stage = (tpb * bn * 128) >> c2;
                 const int a_stages_max = std::min(nmacro, taps == 9 ? 2 : 4);
                 // pass 0: leave room for a second CTA on the SM; pass 1: whole SM; pass 2: persistent -- one CTA per SM loops over
                 // the tiles with two TMEM accumulators, so the epilogue of tile i runs under the main loop of tile i+1
@@ -1334,6 +1417,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 for (int pass = 0; pass < 4; ++pass)
                 for (int a_stages = pass >= 2 ? a_stages_pers : a_stages_max; a_stages >= 1; --a_stages) {
                     const bool pers = pass >= 2;
+                    if (pers && c2) break;
                     if (!pers && a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
                     if (pers && a_stages < 2) break;
                     const int nbuf = pass == 2 ? 3 : 2;
@@ -1370,10 +1454,10 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     // the two operand streams are pipelined separately: each is also bound by its own bytes in flight
                     const double rate_a = co * (double)a_st * a_stage / lat, rate_b = co * (double)b_stages * b_stage / lat;
                     const double b_share = resident ? 1.0 / std::max(1.0, std::min(tiles_per_cta, (double)m_tiles)) : 1.0;   // slab amortised over the CTA's M tiles
-                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * bn * 128);
+                    const double bytes = (double)cps * ((taps == 9 ? a_rows * 128.0 : kBlockM * mp * 128.0) + b_share * taps * (bn >> c2) * 128);
                     // one 128 x bn x 16 MMA takes bn/2 tensor clocks but also reads 4 KB of A and 32*bn B of B from shared memory
                     // (128 B/clk): narrow N tiles are shared-memory-bound (bn = 32: 40 clk instead of 16, bn = 64: 48 instead of 32)
-                    const double mma_step = std::max(bn / 2.0, (4096.0 + 32.0 * bn) / 128.0);
+                    const double mma_step = std::max(bn / 2.0, (4096.0 + 32.0 * (bn >> c2)) / 128.0);
                     const double mma = (double)cps * taps * 4 * mp * mma_step;
                     const double steps = taps == 9 ? (double)cps * (nbs + 1) : 2.0 * nmacro;
                     double main_clk = std::max(std::max(bytes / rate, mma), steps * kStep);
@@ -1395,16 +1479,17 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
-                        best.mpair = mp; best.b_resident = resident ? 1 : 0; best.nbuf = pers ? nbuf : 0;
+                        best.mpair = mp; best.b_resident = resident ? 1 : 0; best.nbuf = pers ? nbuf : 0; best.cta2 = c2;
                     }
                 }
+                }   // c2
             }
         }
     }
     if (getenv("YDST_DEBUG_PLAN"))
-        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d pers %d mpair %d model %.1f us\n", m_tiles128,
+        fprintf(stderr, "  tiling m_tiles %d cout %d taps %d cin_blocks %d -> bn %d ks %d cps %d tpb %d a_st %d b_st %d smem %d occ %d pers %d mpair %d cta2 %d model %.1f us\n", m_tiles128,
                 cout16, taps, cin_blocks, best.bn, best.ksplit, best.cbs_per_split, best.tpb, best.a_stages, best.b_stages, best.smem_bytes,
-                best.occupancy, best.persistent, best.mpair, best.model_us);
+                best.occupancy, best.persistent, best.mpair, best.cta2, best.model_us);
     return best;
 }
 
@@ -1477,6 +1562,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             p.store_tma = (!out_f32 && (p.cout % 64 == 0 || p.cout < 64) && t.bn >= 64 && t.ksplit == 1 && env_int("YDST_TMA_STORE", 1)) ? 1 : 0;
             YDST_CHECK(!t.persistent || p.store_tma, "persistent tiles need the TMA-store epilogue");
             p.nbuf = t.nbuf;
+            p.cta2 = t.cta2;
             const int K = R * S * in.C;
             if (R == 3) {
                 cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1485,7 +1571,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 encode(&L.tmA[0], in.base + in.coff, 2, dims, strides, box, 128);
                 cuuint64_t bdims[3] = {(cuuint64_t)in.C, (cuuint64_t)p.cout, 9};
                 cuuint64_t bstrides[2] = {(cuuint64_t)K * 2, (cuuint64_t)in.C * 2};
-                cuuint32_t bbox[3] = {64u, (cuuint32_t)t.bn, (cuuint32_t)t.tpb};
+                cuuint32_t bbox[3] = {64u, (cuuint32_t)(t.bn >> t.cta2), (cuuint32_t)t.tpb};
                 encode(&L.tmB, w_packed, 3, bdims, bstrides, bbox, 128);
             } else {
                 cuuint64_t dims[3] = {64, (cuuint64_t)p.P_total, (cuuint64_t)p.cin_blocks};
@@ -1494,7 +1580,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 encode(&L.tmA[0], in.base + in.coff, 3, dims, strides, box, 128);
                 cuuint64_t bdims[3] = {64, (cuuint64_t)p.cout, (cuuint64_t)p.cin_blocks};
                 cuuint64_t bstrides[2] = {(cuuint64_t)K * 2, 128};
-                cuuint32_t bbox[3] = {64u, (cuuint32_t)t.bn, (cuuint32_t)t.tpb};
+                cuuint32_t bbox[3] = {64u, (cuuint32_t)(t.bn >> t.cta2), (cuuint32_t)t.tpb};
                 encode(&L.tmB, w_packed, 3, bdims, bstrides, bbox, 128);
             }
             if (p.store_tma) {
@@ -1513,10 +1599,14 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             L.smem_bytes = t.smem_bytes + 1024;
             L.grid = dim3((unsigned)p.m_tiles, (unsigned)p.n_tiles, (unsigned)t.ksplit);
             if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
+            if (p.cta2) {
+                YDST_CHECK(p.store_tma && !p.persistent && t.mpair == 1 && t.ksplit == 1, "CTA pairs need the one-tile-per-CTA TMA-store path");
+                L.grid.x = (L.grid.x + 1u) & ~1u;                // clusters of two along M: an odd tail tile gets an idle partner (all rows out of range)
+            }
             if (getenv("YDST_DEBUG_PLAN"))
-                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d res %d model %.1fus\n",
+                fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d res %d cta2 %d model %.1fus\n",
                         R, in.C, p.cout, out.N, out.H, out.W, L.grid.x, L.grid.y, L.grid.z, t.bn, t.cbs_per_split, t.tpb, t.a_stages, t.b_stages,
-                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, p.mpair, p.b_resident, t.model_us);
+                        p.a_box_rows * p.a_boxes, L.smem_bytes, p.store_tma, p.persistent, p.mpair, p.b_resident, p.cta2, t.model_us);
             return;
         }
         cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1623,7 +1713,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         static bool attr2_set = false;
         static int use_pdl = 1;
         if (!attr2_set) {
-            const void* fns[8] = {(const void*)conv_tc2_kernel<false, false, false>, (const void*)conv_tc2_kernel<false, true, false>,
+            const void* fns[10] = {(const void*)conv_tc2_kernel<false, false, false, true>, (const void*)conv_tc2_kernel<true, false, false, true>,
+                                  (const void*)conv_tc2_kernel<false, false, false>, (const void*)conv_tc2_kernel<false, true, false>,
                                   (const void*)conv_tc2_kernel<true, false, false>,  (const void*)conv_tc2_kernel<true, true, false>,
                                   (const void*)conv_tc2_kernel<false, false, true>,  (const void*)conv_tc2_kernel<false, true, true>,
                                   (const void*)conv_tc2_kernel<true, false, true>,   (const void*)conv_tc2_kernel<true, true, true>};
@@ -1655,12 +1746,23 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = L.grid; cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = (size_t)L.smem_bytes; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-        const int variant = (L.p.act == ACT_MISH ? 1 : 0) | (L.p.persistent ? 2 : 0) | (L.p.mpair == 2 ? 4 : 0);
+        cudaLaunchAttribute at[2];
+        int nat = 0;
+        if (use_pdl) {
+            at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[nat].val.programmaticStreamSerializationAllowed = 1;
+            ++nat;
+        }
+        if (L.p.cta2) {
+            at[nat].id = cudaLaunchAttributeClusterDimension;
+            at[nat].val.clusterDim.x = 2; at[nat].val.clusterDim.y = 1; at[nat].val.clusterDim.z = 1;
+            ++nat;
+        }
+        cfg.attrs = at; cfg.numAttrs = nat;
+        const int variant = L.p.cta2 ? (L.p.act == ACT_MISH ? 9 : 8) : (L.p.act == ACT_MISH ? 1 : 0) | (L.p.persistent ? 2 : 0) | (L.p.mpair == 2 ? 4 : 0);
         switch (variant) {
+            case 8: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, false, true>, maps, prm)); break;
+            case 9: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false, false, true>, maps, prm)); break;
             case 0: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, false>, maps, prm)); break;
             case 1: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false, false>, maps, prm)); break;
             case 2: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true, false>, maps, prm)); break;
