@@ -50,6 +50,10 @@ CASES = [
     ("cta2_mish_3x3_38_batch4_res", 4, 38, 38, 256, 512, 3, 1, True, 2, 1, False),
     ("cta2_reid_16x8_batch40_res", 40, 16, 8, 256, 256, 3, 1, True, 3, 2, False),
     ("cta2_3x3_152_two_boxes_bn128", 2, 152, 152, 64, 128, 3, 1, True, 1, 0, False),
+    ("cta2_persistent_3x3_76_batch8_res_odd", 8, 76, 76, 128, 256, 3, 1, True, 1, 1, False),
+    ("cta2_persistent_mish_38_batch8_res", 8, 38, 38, 256, 512, 3, 1, True, 2, 1, False),
+    ("cta2_persistent_reid_8x4_batch200_res", 200, 8, 4, 512, 512, 3, 1, True, 3, 2, False),
+    ("cta2_persistent_1x1_76_batch8", 8, 76, 76, 256, 128, 1, 1, True, 1, 0, False),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),

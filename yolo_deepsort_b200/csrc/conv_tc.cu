@@ -100,6 +100,10 @@ __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap
         ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// arrive on the copy of a barrier that lives in CTA `rank` of the cluster (cutlass::arch::ClusterBarrier::arrive(cta_id))
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -495,14 +499,17 @@ __device__ __forceinline__ void epilogue_tile_wide(const ConvTcParams& p, const 
 //             the result overwrites the residual in place;
 //   nbuf = 2: (no residual, shared memory tight) thread 0 waits for store q - 2 at the top of group q, plus one more barrier.
 // kAct / kRes < 0: activation and residual mode read from the parameters at run time (the rare combinations).
-template <bool kMish, int kAct, int kRes, int kMp>
+template <bool kMish, int kAct, int kRes, int kMp, bool kCta2>
 __device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const CUtensorMap* out_map, const CUtensorMap* res_map,
                                                     unsigned char* smem_generic, uint32_t smem_generic_u32, uint32_t stage_u32,
                                                     uint32_t tmem_base, int team, float* s_sbt, uint32_t bar_tfull, uint32_t bar_tempty,
-                                                    uint32_t bar_res) {
+                                                    uint32_t bar_res, int cta_rank) {
     const int tid = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3, row = tid, x = row & 7;
     const int bn = p.block_n, ngroups = bn >> 6, nbuf = p.nbuf, ebar = 1 + team;
-    const int total_tiles = p.m_tiles * p.n_tiles, G = (int)gridDim.x;
+    // scheduling units: tiles, or (kCta2) pairs of M tiles shared by the two CTAs of a cluster -- CTA `rank` takes tile 2 * um + rank
+    const int nteams = p.nteams;
+    const int unit0 = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustride = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int units_m = kCta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles, total_units = units_m * p.n_tiles;
     const bool has_res = kRes < 0 ? p.res_mode != 0 : kRes != 0;
     const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
     const bool tr = p.trace && p.trace_tiles && blockIdx.x == 0 && tid == 0;
@@ -510,9 +517,10 @@ __device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const
     auto coords = [&](int q, int& p0, int& c0) -> bool {
         const int j = q / (ngroups * kMp), r = q - j * (ngroups * kMp);
         const int h = r / ngroups, g = r - h * ngroups;
-        const int t = (int)blockIdx.x + (2 * j + team) * G;
-        if (t >= total_tiles) return false;
-        const int tn = t / p.m_tiles, tm = t - tn * p.m_tiles;
+        const int u = unit0 + (nteams * j + team) * ustride;
+        if (u >= total_units) return false;
+        const int tn = u / units_m, um = u - tn * units_m;
+        const int tm = kCta2 ? 2 * um + cta_rank : um;
         p0 = (tm * kMp + h) * kBlockM; c0 = tn * bn + g * 64;
         return true;
     };
@@ -526,10 +534,11 @@ __device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const
     if (has_res && tid == 0) { fetch_res(0); fetch_res(1); }
     int q = 0, staged_tn = -1;
     for (int j = 0;; ++j) {
-        const int it = 2 * j + team;
-        const int t = (int)blockIdx.x + it * G;
-        if (t >= total_tiles) break;
-        const int tn = t / p.m_tiles, tm = t - tn * p.m_tiles;
+        const int it = nteams * j + team;
+        const int u = unit0 + it * ustride;
+        if (u >= total_units) break;
+        const int tn = u / units_m, um = u - tn * units_m;
+        const int tm = kCta2 ? 2 * um + cta_rank : um;
         const int n0 = tn * bn;
         if (tn != staged_tn) {                                      // M runs fastest: the column block (and its scale/bias) rarely changes
             if (staged_tn >= 0) epi_bar_sync(ebar);                 // everyone is done with the previous tile's scale/bias
@@ -574,7 +583,8 @@ __device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const
             tcgen05_wait_ld();
             if (g + 1 == ngroups && h == kMp - 1) {                 // last read of this tile's accumulators: hand them back to the MMA issuer
                 tcgen05_fence_before();
-                mbar_arrive(bar_tempty + 8u * ab);
+                if constexpr (kCta2) mbar_arrive_remote(bar_tempty + 8u * ab, 0u);   // the pair's MMAs come from the leader: both CTAs release there
+                else mbar_arrive(bar_tempty + 8u * ab);
                 if (tr && it < 16) p.trace[16 + it * 8 + 5] = (unsigned long long)clock64();
             }
             if (has_res) {
@@ -821,7 +831,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     const uint32_t b_stage_bytes = (uint32_t)p.tpb * b_tile_bytes;
     // persistent mode keeps a dedicated 2 x 16 KB staging area for the TMA-store epilogue in front of the operand stages
     // (they are being refilled for the next tile while the epilogue runs); otherwise the staging aliases the dead stages
-    const uint32_t stage_area = kPers ? 2u * (uint32_t)p.nbuf * kBlockM * 128u : 0u;   // nbuf 16 KB buffers per epilogue team
+    const uint32_t stage_area = kPers ? (uint32_t)(p.nteams * p.nbuf) * kBlockM * 128u : 0u;   // nbuf 16 KB buffers per epilogue team
     const uint32_t a_base = smem_base + stage_area;
     const uint32_t b_base = a_base + (uint32_t)p.a_stages * a_stage_bytes;
     // the wide epilogue stages one 16 KB buffer per 64-column group over the (then dead) operand stages: keep the barriers clear of it
@@ -858,7 +868,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         for (int s = 0; s < p.a_stages * nab; ++s) mbar_init(bar_fullA + 8u * s, 1);
         for (int s = 0; s < p.a_stages; ++s) mbar_init(bar_emptyA + 8u * s, 1);
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(bar_fullB + 8u * s, 1); mbar_init(bar_emptyB + 8u * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, kCta2 ? 256 : 128); }
         for (int s = 0; s < 8; ++s) mbar_init(bar_res + 8u * s, 1);
         fence_barrier_init();
         fence_proxy_async();
@@ -893,6 +903,9 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
     const int nbs = k3 ? 9 / p.tpb : 1;                        // weight stages per macro step
     // tile iteration: a normal launch owns tile (blockIdx.x, blockIdx.y); a persistent CTA strides over all tiles, M fastest
     const int total_tiles = p.m_tiles * p.n_tiles;
+    // persistent scheduling units: tiles, or (kCta2) pairs of M tiles shared by the two CTAs of a cluster
+    const int unit0 = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ustride = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int units_m = kCta2 ? (p.m_tiles + 1) >> 1 : p.m_tiles, total_units = units_m * p.n_tiles;
     auto tile_at = [&](int it, int& tm, int& tn) -> bool {
         if (!kPers) { tm = blockIdx.x; tn = blockIdx.y; return it == 0; }
         const int t = blockIdx.x + it * gridDim.x;
@@ -913,10 +926,10 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             int sa = 0, sb = 0, loaded_tn = -1;
             uint32_t pha = 1, phb = 1;
             const int a_stages = p.a_stages, b_stages = p.b_stages, tpb = p.tpb, a_boxes = p.a_boxes, a_box_rows = p.a_box_rows;
-            const int m_tiles = p.m_tiles, G = (int)gridDim.x;
             const int total_b = nmacro * nbs;
-            int tm = kPers ? (int)blockIdx.x % m_tiles : (int)blockIdx.x, tn = kPers ? (int)blockIdx.x / m_tiles : (int)blockIdx.y;
-            for (int it = 0, t = (int)blockIdx.x; kPers ? t < total_tiles : it == 0; ++it, t += G) {
+            int um = kPers ? unit0 % units_m : (int)blockIdx.x, tn = kPers ? unit0 / units_m : (int)blockIdx.y;
+            for (int it = 0, u = unit0; kPers ? u < total_units : it == 0; ++it, u += ustride) {
+                const int tm = (kPers && kCta2) ? 2 * um + (int)cta_rank : um;
                 const int p0 = tm * kBlockM * mp, n0 = tn * p.block_n;
                 int jm = 0, js = 0;                            // next weight stage to issue: macro step jm, sub-stage js
                 auto issue_b = [&]() {
@@ -992,7 +1005,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                     for (; issued < (i + 1) * nbs; ++issued) issue_b();
                     if (a_stages == 1 && i + 1 < nmacro) load_a(i + 1);
                 }
-                if (kPers) { tm += G; while (tm >= m_tiles) { tm -= m_tiles; ++tn; } }
+                if (kPers) { um += ustride; while (um >= units_m) { um -= units_m; ++tn; } }
             }
             if (res_early) {
                 // sb / phb point at the next stage the ring would refill, i.e. the next one the MMAs release
@@ -1020,7 +1033,6 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             const uint32_t hi = desc_hi(128);
             const uint32_t b_tile16 = b_tile_bytes >> 4;
             const int a_stages = p.a_stages, b_stages = p.b_stages, tpb = p.tpb, bn = p.block_n;
-            const int m_tiles = p.m_tiles, G = (int)gridDim.x;
             const bool bo1 = p.bo_mode == 1;
             auto mma = [&](uint32_t td, uint32_t al, uint32_t bl, uint32_t h, uint32_t accu) {
                 if constexpr (kCta2) umma_f16_lh_2cta(td, al, bl, h, idesc, accu); else umma_f16_lh(td, al, bl, h, idesc, accu);
@@ -1035,17 +1047,17 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             const bool resident = kPers && p.b_resident;
-            int tn = kPers ? (int)blockIdx.x / m_tiles : (int)blockIdx.y, tm = kPers ? (int)blockIdx.x % m_tiles : 0;
+            int tn = kPers ? unit0 / units_m : (int)blockIdx.y, um = kPers ? unit0 % units_m : 0;
             int prev_tn = -1;
-            for (int it = 0, t = (int)blockIdx.x; kPers ? t < total_tiles : it == 0; ++it, t += G) {
+            for (int it = 0, u = unit0; kPers ? u < total_units : it == 0; ++it, u += ustride) {
                 // weight-stationary tiles: wait for the slab only on its first use, release it only after its last use; the ring
                 // index restarts at 0 every tile (the slab occupies the whole ring) and the phase flips once per slab, not per tile
                 bool first_use = true, last_use = true;
-                int tm_next = tm, tn_next = tn;
-                if (kPers) { tm_next += G; while (tm_next >= m_tiles) { tm_next -= m_tiles; ++tn_next; } }
+                int um_next = um, tn_next = tn;
+                if (kPers) { um_next += ustride; while (um_next >= units_m) { um_next -= units_m; ++tn_next; } }
                 if (resident) {
                     first_use = tn != prev_tn;
-                    last_use = t + G >= total_tiles || tn_next != tn;
+                    last_use = u + ustride >= total_units || tn_next != tn;
                     prev_tn = tn;
                     sb = 0;
                 }
@@ -1125,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                 if (tr && leader && it < 16) p.trace[16 + it * 8 + 1] = (unsigned long long)clock64();
                 if (resident && last_use) phb ^= 1u;           // the next slab lands in the next phase of every weight barrier
                 if (leader && it == 0) trace_mark(p, 4);
-                tm = tm_next; tn = tn_next;
+                um = um_next; tn = tn_next;
             }
         }
     } else {
@@ -1134,11 +1146,13 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             // persistent tile loop with TMA stores (the planner only makes store_tma launches persistent): two teams alternate tiles
             const int team = warp >> 2;
             grid_dep_wait();                                   // residual / output buffers belong to earlier kernels
-#define YDST_PERS(A, R) epilogue_persistent<kMish, A, R, mp>(p, &maps.a[1], &maps.a[2], smem_raw, smem_u32(smem_raw),                       \
+#define YDST_PERS(A, R) epilogue_persistent<kMish, A, R, mp, kCta2>(p, &maps.a[1], &maps.a[2], smem_raw, smem_u32(smem_raw),                \
                                                          smem_base + (uint32_t)team * (uint32_t)p.nbuf * (kBlockM * 128u), tmem_base, team, \
-                                                         s_sb + team * 512, bar_tfull, bar_tempty, bar_res + 24u * team)
+                                                         s_sb + team * 512, bar_tfull, bar_tempty, bar_res + 24u * team, (int)cta_rank)
             const int key = p.act * 4 + p.res_mode;            // warp-uniform: one specialised epilogue per common combination
-            if (kMish) {
+            if (team >= p.nteams) {
+                // (wide tiles: one team keeps up with the MMAs and the second team's staging buffers buy another weight stage)
+            } else if (kMish) {
                 if (key == ACT_MISH * 4 + 0) YDST_PERS(ACT_MISH, 0);
                 else if (key == ACT_MISH * 4 + 1) YDST_PERS(ACT_MISH, 1);
                 else YDST_PERS(-1, -1);
@@ -1321,6 +1335,8 @@ static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
 }
 
+static void ensure_conv_tc2_attrs();
+static int max_active_clusters(bool mish, int smem_bytes);
 static int g_num_sms = 0;
 static int num_sms() {
     if (!g_num_sms) {
@@ -1359,7 +1375,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
     // measured on B200: neither M pairs nor the persistent tile loop beat the plain one-tile-per-CTA launch yet
     // (1163 / 1198 / 1226 frames/s for pair+persistent / persistent / neither at micro-batch 4), so both are opt-in
     const int allow_pair = env_int("YDST_MPAIR", 0), force_mp = env_int("YDST_FORCE_MPAIR", 0);
-    const int cta2_mode = env_int("YDST_CTA2", 0);            // 0 off, 1 3x3 layers where the clock model prefers it, 2 wherever legal (test hook)
+    const int cta2_mode = env_int("YDST_CTA2", 1);            // 0 off, 1 3x3 layers where the clock model prefers it, 2 wherever legal (test hook)
     const int pers_mode = env_int("YDST_PERSISTENT", 1);      // 0 off, 1 weight-stationary many-tile layers only, 2 wherever the clock model prefers it
     for (int mp = 1; mp <= 2; ++mp)
     for (int bn = bn_cap; bn >= 32; bn >>= 1) {
@@ -1417,15 +1433,20 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                 for (int pass = 0; pass < 4; ++pass)
                 for (int a_stages = pass >= 2 ? a_stages_pers : a_stages_max; a_stages >= 1; --a_stages) {
                     const bool pers = pass >= 2;
-                    if (pers && c2) break;
                     if (!pers && a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
                     if (pers && a_stages < 2) break;
+                    // measured: pairs + the persistent loop make the 3x3 layers tensor-bound in steady state, which pays
+                    // from ~2.5 tiles per SM on; between one and 2.5 waves the pair helps plain launches (38x38 256->512: 26.5 -> 22.6 us)
+                    if (c2 && cta2_mode == 1 && (pers ? 2 * tiles < 5 * kSms : (tiles <= kSms || 2 * tiles >= 5 * kSms))) break;
+                    // persistent: two epilogue teams alternate tiles; wide tiles whose MMAs outlast an epilogue get by with one, and its
+                    // staging buffers buy weight stages instead
+                    for (int nt = pers ? 2 : 1; nt >= 1; --nt) {
                     const int nbuf = pass == 2 ? 3 : 2;
                     const bool st_ok = tma_store_ok && bn >= 64 && (cout16 % bn == 0 || cout16 < 64);
                     if (pers && (ks > 1 || tiles <= kSms || bn * mp > 256 || !allow_pers || !pers_mode)) continue;
                     if (pers && (!st_ok || (nbuf == 2 && res_mode))) continue;
                     if (mp == 2 && !pers && !allow_pair) continue;   // (plain launches: pairs measured slower than two co-resident CTAs)
-                    const int staging = pers ? 2 * nbuf * 16 * 1024 : 0;   // 16 KB store buffers per epilogue team
+                    const int staging = pers ? nt * nbuf * 16 * 1024 : 0;   // 16 KB store buffers per epilogue team
                     const int budget = (pass == 0 ? budget_2 : pers ? budget_pers : budget_max) - staging;
                     if (pass == 0 && ctas <= kSms) continue;      // one CTA per SM anyway: use the whole shared memory
                     // a persistent CTA prefetches the next tile's operands while the current one computes: two stages of each at least
@@ -1433,14 +1454,15 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const int fixed_p = a_st * a_stage + 6144;
                     int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
                     // weight-stationary persistent tiles: the N tile's whole weight slab fits and is fetched once per column block
-                    const bool resident = pers && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
+                    const bool resident = pers && !c2 && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
                                           env_int("YDST_B_RESIDENT", 1);
                     if (resident) b_stages = total_b;
                     if (b_stages < (pers && !resident ? 2 : 1)) continue;
+                    if (pers && mp == 2 && resident) continue;    // pairs exist to halve streamed weights; stationary ones gain nothing
                     // Measured: the persistent loop pays where the weights stay in shared memory and a CTA walks many
                     // tiles (ReID layer1: 172 -> 90 us per conv); with streamed weights or few waves it only trades the PDL overlap of
                     // plain launches for its own tail, so the default mode keeps those layers on plain launches.
-                    if (pers && pers_mode == 1 && (!resident || (long long)m_tiles128 * n_tiles < 6 * kSms)) continue;
+                    if (pers && pers_mode == 1 && !(resident && (long long)m_tiles128 * n_tiles >= 6 * kSms) && !(c2 && taps == 9)) continue;
                     int smem = fixed_p + b_stages * b_stage + staging;
                     // the TMA-store epilogue stages 16 KB per 64-column group (two buffers in persistent / pair mode) at the start of smem
                     smem = std::max(smem, std::max(2, bn / 64) * 16 * 1024 + 6144);
@@ -1469,7 +1491,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const double epi = mp * (700.0 + ((bn + 63) / 64) * (st ? 700.0 : 2200.0));
                     const double per_sm = std::ceil((double)ctas / kSms);
                     double t = kSetup + kFirst + per_sm * main_clk + std::ceil(per_sm / occ) * epi;
-                    if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, mp == 1 ? 0.5 * epi : epi) + epi;   // front paid once, epilogues hidden (two teams alternate)
+                    if (pers) t = kSetup + kFirst + per_sm * std::max(main_clk, epi / nt) + epi;   // front paid once, epilogues hidden (teams alternate)
                     else if (per_sm > 1) t += (per_sm - 1) / occ * (kSetup + kFirst);          // every further wave pays the front again
                     if (ks > 1) t += 1500.0 + per_sm * (double)(ks + 1) * kBlockM * bn * 4 / 30.0;
                     t /= kClkPerUs;
@@ -1479,8 +1501,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;
-                        best.mpair = mp; best.b_resident = resident ? 1 : 0; best.nbuf = pers ? nbuf : 0; best.cta2 = c2;
+                        best.mpair = mp; best.b_resident = resident ? 1 : 0; best.nbuf = pers ? nbuf : 0; best.cta2 = c2; best.nteams = pers ? nt : 2;
                     }
+                    }   // nt
                 }
                 }   // c2
             }
@@ -1563,6 +1586,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             YDST_CHECK(!t.persistent || p.store_tma, "persistent tiles need the TMA-store epilogue");
             p.nbuf = t.nbuf;
             p.cta2 = t.cta2;
+            p.nteams = t.nteams ? t.nteams : 2;
             const int K = R * S * in.C;
             if (R == 3) {
                 cuuint64_t dims[2] = {(cuuint64_t)in.C, (cuuint64_t)p.P_total};
@@ -1600,8 +1624,15 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             L.grid = dim3((unsigned)p.m_tiles, (unsigned)p.n_tiles, (unsigned)t.ksplit);
             if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
             if (p.cta2) {
-                YDST_CHECK(p.store_tma && !p.persistent && t.mpair == 1 && t.ksplit == 1, "CTA pairs need the one-tile-per-CTA TMA-store path");
-                L.grid.x = (L.grid.x + 1u) & ~1u;                // clusters of two along M: an odd tail tile gets an idle partner (all rows out of range)
+                YDST_CHECK(p.store_tma && t.mpair == 1 && t.ksplit == 1, "CTA pairs need the TMA-store path");
+                if (p.persistent) {
+                    // one cluster per SM pair strides over the pairs of M tiles; no more clusters than can be resident at once
+                    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+                    const int clusters = std::min(pairs, max_active_clusters(act == ACT_MISH, L.smem_bytes));
+                    L.grid = dim3(2u * (unsigned)clusters, 1, 1);
+                } else {
+                    L.grid.x = (L.grid.x + 1u) & ~1u;            // clusters of two along M: an odd tail tile gets an idle partner (all rows out of range)
+                }
             }
             if (getenv("YDST_DEBUG_PLAN"))
                 fprintf(stderr, "conv_plan2 k%d cin %d cout %d out %dx%dx%d grid %ux%ux%u bn %d cps %d tpb %d a_st %d b_st %d a_rows %d smem %d tma_st %d pers %d mpair %d res %d cta2 %d model %.1fus\n",
@@ -1659,6 +1690,39 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                 out.N, out.H, out.W, L.grid.x, L.grid.y, bn, p.block_k, stages, L.smem_bytes);
 }
 
+static void ensure_conv_tc2_attrs() {
+    static bool attr2_set = false;
+    if (attr2_set) return;
+    const void* fns[12] = {(const void*)conv_tc2_kernel<false, false, false, true>, (const void*)conv_tc2_kernel<true, false, false, true>,
+                           (const void*)conv_tc2_kernel<false, true, false, true>,  (const void*)conv_tc2_kernel<true, true, false, true>,
+                           (const void*)conv_tc2_kernel<false, false, false>, (const void*)conv_tc2_kernel<false, true, false>,
+                           (const void*)conv_tc2_kernel<true, false, false>,  (const void*)conv_tc2_kernel<true, true, false>,
+                           (const void*)conv_tc2_kernel<false, false, true>,  (const void*)conv_tc2_kernel<false, true, true>,
+                           (const void*)conv_tc2_kernel<true, false, true>,   (const void*)conv_tc2_kernel<true, true, true>};
+    for (const void* fn : fns) {
+        YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
+        YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    attr2_set = true;
+}
+
+// how many clusters of two persistent CTAs the device can hold at once (GPC boundaries may leave an SM without a partner)
+static int max_active_clusters(bool mish, int smem_bytes) {
+    ensure_conv_tc2_attrs();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)num_sms(), 1, 1); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    const void* fn = mish ? (const void*)conv_tc2_kernel<true, true, false, true> : (const void*)conv_tc2_kernel<false, true, false, true>;
+    YDST_CUDA(cudaOccupancyMaxActiveClusters(&n, fn, &cfg));
+    YDST_CHECK(n > 0, "no cluster of two persistent CTAs fits (smem %d)", smem_bytes);
+    return std::min(n, num_sms() / 2);
+}
+
 static constexpr int kTraceSlots = 1024;
 static int g_trace_on = -1, g_trace_next = 0;
 static unsigned long long* g_trace_dev = nullptr;
@@ -1710,22 +1774,9 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
     memcpy(maps.a, L.tmA, sizeof(maps.a));
     maps.b = L.tmB;
     if (L.p.v2) {
-        static bool attr2_set = false;
-        static int use_pdl = 1;
-        if (!attr2_set) {
-            const void* fns[10] = {(const void*)conv_tc2_kernel<false, false, false, true>, (const void*)conv_tc2_kernel<true, false, false, true>,
-                                  (const void*)conv_tc2_kernel<false, false, false>, (const void*)conv_tc2_kernel<false, true, false>,
-                                  (const void*)conv_tc2_kernel<true, false, false>,  (const void*)conv_tc2_kernel<true, true, false>,
-                                  (const void*)conv_tc2_kernel<false, false, true>,  (const void*)conv_tc2_kernel<false, true, true>,
-                                  (const void*)conv_tc2_kernel<true, false, true>,   (const void*)conv_tc2_kernel<true, true, true>};
-            for (const void* fn : fns) {
-                YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-                // without this the driver may size the L1/shared split for ONE resident CTA; multi-wave layers want two per SM
-                YDST_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            }
-            use_pdl = env_int("YDST_PDL", 1);
-            attr2_set = true;
-        }
+        static int use_pdl = -1;
+        ensure_conv_tc2_attrs();
+        if (use_pdl < 0) use_pdl = env_int("YDST_PDL", 1);
         if (g_trace_on < 0) {
             g_trace_on = env_int("YDST_CONV_TRACE", 0);
             if (g_trace_on) {
@@ -1759,8 +1810,10 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
             ++nat;
         }
         cfg.attrs = at; cfg.numAttrs = nat;
-        const int variant = L.p.cta2 ? (L.p.act == ACT_MISH ? 9 : 8) : (L.p.act == ACT_MISH ? 1 : 0) | (L.p.persistent ? 2 : 0) | (L.p.mpair == 2 ? 4 : 0);
+        const int variant = L.p.cta2 ? (L.p.act == ACT_MISH ? 9 : 8) + (L.p.persistent ? 2 : 0) : (L.p.act == ACT_MISH ? 1 : 0) | (L.p.persistent ? 2 : 0) | (L.p.mpair == 2 ? 4 : 0);
         switch (variant) {
+            case 10: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true, false, true>, maps, prm)); break;
+            case 11: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true, false, true>, maps, prm)); break;
             case 8: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, false, true>, maps, prm)); break;
             case 9: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false, false, true>, maps, prm)); break;
             case 0: YDST_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false, false>, maps, prm)); break;

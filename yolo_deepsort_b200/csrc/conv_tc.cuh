@@ -43,6 +43,7 @@ struct ConvTcParams {
     int tpb;              // 64-channel K slices per weight stage (3x3: filter taps, 1 | 3 | 9; 1x1: channel blocks)
     int store_tma;        // 1: epilogue stages 64-column groups in swizzled smem and writes them with TMA bulk stores
     int cta2;             // 1: clusters of two CTAs along M share one tcgen05.mma.cta_group::2 stream; each stages half of the weight tile
+    int nteams;           // persistent: epilogue teams of four warps that alternate tiles (2; 1 for wide tiles, whose MMAs outlast an epilogue)
     int nbuf;             // persistent: 16 KB staging buffers per epilogue team (3 when a residual tile is prefetched into them, else 2 or 3)
     int trace_tiles;      // debug: the persistent loop also records per-tile milestones of CTA 0 (YDST_CONV_TRACE=1 only)
     float* ws;            // split-K partials [tile][split][chunk][128][16] fp32
@@ -79,7 +80,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
                   const float* scale, const float* bias, int act, int res_mode, const Act* res, float* out_f32, int cout_real,
                   const ConvWorkspace* ws = nullptr);
 // the tiling the planner would pick for a stride-1 conv on the halo kernel (pure host function, no CUDA): for the planner test
-struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair, b_resident, nbuf, cta2; double model_us; };
+struct ConvTiling { int bn, ksplit, cbs_per_split, tpb, a_stages, b_stages, occupancy, smem_bytes, persistent, mpair, b_resident, nbuf, cta2, nteams; double model_us; };
 ConvTiling conv_tc_choose_tiling(int m_tiles, int cout16, int taps, int cin_blocks, int halo, size_t ws_bytes, int max_tickets, int res_mode = 0,
                                  bool allow_pers = true);
 // Plain GEMM on the same kernel: out[rows][ncols] (fp32, row stride ncols) = A[rows][K] * B[ncols][K]^T * scale[col] + bias[col], A and B
