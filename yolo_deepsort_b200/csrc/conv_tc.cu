@@ -278,6 +278,53 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, uint32_t tm
     }
 }
 
+// fp32 output (the three YOLO head convolutions; flat mode, no residual): the rows of a warp are consecutive pixels, so each
+// 16-column block is transposed through a warp-private 2.5 KB patch of the (dead) operand stages and written as 16-byte stores
+// that cover 8 rows x 64 contiguous bytes per instruction instead of 32 rows x 16 bytes (32 cache lines per instruction, which
+// together with the spills of the generic path made the 76x76 head the slowest launch of the forward: 73 us for 1.5 GFLOP).
+template <bool kMish>
+__device__ __forceinline__ void epilogue_tile_f32(const ConvTcParams& p, uint32_t tmem_base, int wq, int n0, long long row0, bool valid,
+                                                  const float* s_sb, uint32_t bar_tmem, uint32_t parity, float* patch) {
+    const int lane = threadIdx.x & 31;
+    constexpr int kPitch = 20;                                     // floats per patch row: 16 + 4 keeps float4 rows on distinct banks
+    mbar_wait(bar_tmem, parity);
+    tcgen05_fence_after();
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16);
+    for (int cl = 0; cl < p.block_n; cl += 16) {
+        const int c = n0 + cl;
+        if (c >= p.cout) break;                                    // warp-uniform
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld_32x32b_x16(tbase + (uint32_t)cl, v);
+        tcgen05_wait_ld();
+        float o[16];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_sb + cl);
+        const float4* bi4 = reinterpret_cast<const float4*>(s_sb + p.block_n + cl);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 sc = sc4[q], bi = bi4[q];
+            o[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, bi.x);
+            o[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, bi.y);
+            o[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, bi.z);
+            o[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, bi.w);
+        }
+        act16<kMish>(o, p.act);
+        float4* mine = reinterpret_cast<float4*>(patch + lane * kPitch);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mine[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2), ch = lane & 3;
+            if ((vmask >> r) & 1u) {
+                const float4 t = *reinterpret_cast<const float4*>(patch + r * kPitch + ch * 4);
+                *reinterpret_cast<float4*>(p.out_f32 + (row0 + r) * p.cout + c + ch * 4) = t;
+            }
+        }
+    }
+}
+
 // TMA-store variant (halo kernel, cout % 64 == 0, fp16 output): every thread-per-row global store of the direct epilogue
 // touches its own 128-byte line (32 lines per warp instruction), which costs ~2000 clocks per 64-column group in the LSU.
 // Here each 64-column group is written to a 128B-swizzled [128 rows][64 cols] staging tile in shared memory (the operand
@@ -1227,6 +1274,9 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
                         }
 #undef YDST_WIDE
                     }
+                    else if (p.out_f32 && p.mode == 0)          // the operand stages are dead once the accumulator is complete: warp-private patches
+                        epilogue_tile_f32<kMish>(p, tmem_d, wq, n0, (long long)p0 + wq * 32, valid, s_sbg, bar_full, par,
+                                                 reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + wq * 640);
                     else epilogue_tile<kMish>(p, tmem_d, wq, n0, pp, valid, s_sbg, bar_full, par, bar_rel);
                 } else if (p.store_tma)
                     epilogue_tile_tma<kMish>(p, &maps.a[1], stage_g, smem_raw + (stage_g - smem_u32(smem_raw)), tmem_d, wq, n0, p0, pp, valid,
@@ -1436,8 +1486,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     if (!pers && a_stages < a_stages_max && (pass != 0 || !co_model)) break;   // fewer activation stages only to fit two CTAs per SM
                     if (pers && a_stages < 2) break;
                     // measured: pairs + the persistent loop make the 3x3 layers tensor-bound in steady state, which pays
-                    // from ~2.5 tiles per SM on; between one and 2.5 waves the pair helps plain launches (38x38 256->512: 26.5 -> 22.6 us)
-                    if (c2 && cta2_mode == 1 && (pers ? 2 * tiles < 5 * kSms : (tiles <= kSms || 2 * tiles >= 5 * kSms))) break;
+                    // from two tiles per SM on (ReID layer4 at 348 tiles: 117 -> 83 us; 76x76 128->256 at 381: 44 -> 25 us; but 38x38
+                    // 256->512 at 200 tiles: 23 -> 36 us); between one and two waves the pair helps plain launches
+                    if (c2 && cta2_mode == 1 && (pers ? tiles < 2 * kSms : (tiles <= kSms || tiles >= 2 * kSms))) break;
                     // persistent: two epilogue teams alternate tiles; wide tiles whose MMAs outlast an epilogue get by with one, and its
                     // staging buffers buy weight stages instead
                     for (int nt = pers ? 2 : 1; nt >= 1; --nt) {
@@ -1498,6 +1549,9 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     // measured: where an N = 256 tile still leaves >= 96 CTAs it beats the model's pick -- the 128 x 256 MMA is
                     // the only shape whose operand reads fit the shared-memory bandwidth -- so it gets a bonus the clock model lacks
                     if (env_int("YDST_PREFER_BN256", 1) && bn == 256 && ctas >= 96 && ks == 1) t *= 0.5;
+                    // measured: a deep 3x3 layer whose 128 x 256 tiles do not even fill one wave (19x19 512->1024: 112 tiles, 36 900 tensor
+                    // clocks each) runs faster as paired 128 x 128 tiles, two per SM (34.4 -> 29.4 us)
+                    if (c2 && !pers && cta2_mode == 1 && bn == 128 && taps == 9 && cin_blocks >= 8 && (long long)m_tiles128 * ((cout16 + 255) / 256) <= kSms) t *= 0.4;
                     if (t < best.model_us * 0.98) {              // near-ties go to the earlier (larger bn, fewer splits) candidate
                         best.bn = bn; best.ksplit = ks; best.cbs_per_split = cps; best.tpb = tpb; best.a_stages = a_st;
                         best.b_stages = b_stages; best.occupancy = occ; best.smem_bytes = smem; best.model_us = t; best.persistent = pers;

@@ -685,20 +685,15 @@ __device__ __forceinline__ void axis_coeff(int d, int n_dst, int n_src, bool cla
     w0 = __float2int_rn((1.f - fr) * 2048.f);
 }
 
-__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, const float* __restrict__ tlwh,
-                                                          int m, float* __restrict__ out, int* err_flag) {
+// one output pixel (dx, dy) of crop b of `frame`, written to o[0..2]
+__device__ __forceinline__ void crop_resize_pixel(const uint8_t* __restrict__ frame, int H, int W, const float* __restrict__ tlwh, int b, int dx, int dy,
+                                                  float* __restrict__ o, int* err_flag) {
     const int DW = 64, DH = 128;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)m * DH * DW) return;
-    const int dx = (int)(idx % DW);
-    const int dy = (int)((idx / DW) % DH);
-    const int b = (int)(idx / (DW * DH));
     const float bx = tlwh[b * 4 + 0], by = tlwh[b * 4 + 1], bw = tlwh[b * 4 + 2], bh = tlwh[b * 4 + 3];
     // DeepSort._s_tlwh_to_xyxy: int() truncation toward zero; x+w and y+h are fp32 sums; note the -1
     const int x1 = max((int)bx, 0), x2 = min((int)(bx + bw), W - 1);
     const int y1 = max((int)by, 0), y2 = min((int)(by + bh), H - 1);
     const int sw = x2 - x1, sh = y2 - y1;
-    float* o = out + idx * 3;
     if (sw <= 0 || sh <= 0) {
         if (dx == 0 && dy == 0) atomicExch(err_flag, 1);
         o[0] = o[1] = o[2] = 0.f;
@@ -725,6 +720,25 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c] = ((float)v[c] / 255.f - mean[c]) / stdv[c];
+}
+
+__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, const float* __restrict__ tlwh,
+                                                          int m, float* __restrict__ out, int* err_flag) {
+    const int DW = 64, DH = 128;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * DH * DW) return;
+    crop_resize_pixel(frame, H, W, tlwh, (int)(idx / (DW * DH)), (int)(idx % DW), (int)((idx / DW) % DH), out + idx * 3, err_flag);
+}
+// the crops of up to 8 frames of a micro-batch in ONE launch (eight 9-us launches of ~50 crops each were latency, not bandwidth)
+__global__ void __launch_bounds__(256) crop_resize_multi_kernel(const CropBatch cb, float* __restrict__ out) {
+    const int DW = 64, DH = 128;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)cb.start[cb.n] * DH * DW) return;
+    const int g = (int)(idx / (DW * DH));                    // crop index within the launch; a block of 256 threads never straddles crops
+    int f = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) f += (i < cb.n && g >= cb.start[i]) ? 1 : 0;
+    crop_resize_pixel(cb.frame[f], cb.H[f], cb.W[f], cb.tlwh[f], g - cb.start[f], (int)(idx % DW), (int)((idx / DW) % DH), out + idx * 3, cb.err[f]);
 }
 // Whole-frame ingest (next to the hot path): the reader thread's BGR->RGB (yolo3/detect/video_detect.py:33-36) and
 // ImageDetector's cv2.resize(img, (W, H), INTER_LINEAR) (yolo3/detect/img_detect.py:70) on the device, with the same
@@ -776,6 +790,12 @@ __global__ void __launch_bounds__(256) window_boxes_kernel(float* __restrict__ p
 }
 void launch_window_boxes(float* pred, int tiles, int rows, int nf, const float* geo_dev, cudaStream_t st) {
     window_boxes_kernel<<<cdiv((long long)tiles * rows, 256), 256, 0, st>>>(pred, tiles, rows, nf, geo_dev);
+    YDST_CUDA(cudaGetLastError());
+}
+
+void launch_crop_resize_multi(const CropBatch& cb, float* out, cudaStream_t st) {
+    if (cb.n == 0 || cb.start[cb.n] == 0) return;
+    crop_resize_multi_kernel<<<cdiv((long long)cb.start[cb.n] * 128 * 64, 256), 256, 0, st>>>(cb, out);
     YDST_CUDA(cudaGetLastError());
 }
 

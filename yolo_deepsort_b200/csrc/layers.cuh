@@ -50,5 +50,15 @@ void launch_avgpool_l2(const Act& in, float* out, cudaStream_t st);
 void launch_resize_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, int swap_rb, cudaStream_t st, long long pitch = 0);
 void launch_window_boxes(float* pred, int tiles, int rows, int nf, const float* geo_dev, cudaStream_t st);   // geo: [tiles][4] = rw, rh, ox, oy
 void launch_crop_resize(const uint8_t* frame, int H, int W, const float* tlwh, int m, float* out, int* err_flag, cudaStream_t st);
+// crops of up to 8 frames in one launch: segment f holds crops [start[f], start[f+1]) of the launch, cut from frame[f]
+struct CropBatch {
+    const uint8_t* frame[8];
+    const float* tlwh[8];
+    int* err[8];
+    int H[8], W[8];
+    int start[9];
+    int n;
+};
+void launch_crop_resize_multi(const CropBatch& cb, float* out, cudaStream_t st);
 
 }  // namespace ydst

@@ -553,20 +553,35 @@ void Reid::extract_multi(const uint8_t* const* frames_dev, const int* H, const i
     // has no limit on the number of detections (deep_sort/deep_sort.py:133-146), so neither a busy frame nor a micro-batch of B
     // frames may overflow -- they just take more than one forward.  Stream order makes the reuse of in_f32_ / feat_ safe.
     int done = 0, fill = 0;                                 // feature rows written so far | crops staged for the current chunk
+    CropBatch cb{};                                         // crop segments (one per frame) queued for the next launch
+    int cb_first = 0;                                       // chunk position of the first queued crop
+    auto launch_crops = [&]() {
+        if (cb.n == 0) return;
+        launch_crop_resize_multi(cb, in_f32_ + (size_t)cb_first * 128 * 64 * 3, st);
+        count_launch();
+        cb.n = 0;
+        cb_first = fill;
+    };
     auto flush = [&]() {
+        launch_crops();
         if (fill == 0) return;
         forward(in_f32_, fill, feat_out ? feat_out + (size_t)done * 512 : nullptr, st);
         done += fill;
         fill = 0;
+        cb_first = 0;
     };
     for (int b = 0; b < nb; ++b) {
         int first = 0;
         while (first < m[b]) {
             const int take = std::min(m[b] - first, max_batch - fill);
-            launch_crop_resize(frames_dev[b], H[b], W[b], tlwh_dev[b] + (size_t)first * 4, take, in_f32_ + (size_t)fill * 128 * 64 * 3, err_flag + (b & 7), st);
-            count_launch();
+            if (cb.n == 0) cb.start[0] = 0;
+            cb.frame[cb.n] = frames_dev[b]; cb.tlwh[cb.n] = tlwh_dev[b] + (size_t)first * 4; cb.err[cb.n] = err_flag + (b & 7);
+            cb.H[cb.n] = H[b]; cb.W[cb.n] = W[b];
+            cb.start[cb.n + 1] = cb.start[cb.n] + take;
+            ++cb.n;
             first += take;
             fill += take;
+            if (cb.n == 8) launch_crops();
             if (fill == max_batch) flush();
         }
     }
