@@ -14,9 +14,11 @@ Timing.  A WINDOW is exactly K steps between two CUDA events on the launching st
 synchronize on both sides.  The stream is in steady state: the look-ahead pipeline stays primed across windows (the reference's
 reader thread keeps up to 128 decoded frames queued, yolo3/detect/video_detect.py:86), every window COLLECTS exactly K frames
 and submits as many new ones as free slots allow (K on average).  Windows are repeated until at least --min-seconds (2 s) have
-been timed, whatever K is; `value` and `ms_per_step` are all timed steps / all timed time (max over ranks per window) -- with a K
-that is not a multiple of the micro-batch single windows alternate between two lengths, so their median is reported in `windows`
-(with count, min, max) but not used.  Legs (rank 0 prints ONE JSON line):
+been timed, whatever K is, back to back inside ONE barrier + synchronize bracket (a look-ahead pipeline keeps working through a
+synchronize, so windows separated by one would each start with frames computed outside any timed interval); `value` and
+`ms_per_step` are all timed steps / the whole region (max over ranks); `windows` holds the count and the median / min / max of
+the single windows (host-loop time stamps; with a K that is not a multiple of the micro-batch they alternate between two
+lengths).  Legs (rank 0 prints ONE JSON line):
   value   frames already resident in HBM (FramePipeline.submit of CUDA tensors / collect).
   e2e     HOST frames through the same reference-facing calls: the pinned 1.1 MB host->device copy of every frame and the
           device->host read of its track rows are inside the window.
@@ -199,28 +201,36 @@ class Stream:
 
 
 def timed_windows(run_k, K, min_seconds, device, max_windows=2000):
-    """Repeat the K-step window until min_seconds have been timed.  Returns (per-window ms: max over ranks, this rank's own ms)."""
+    """Time R consecutive K-step windows as ONE region: barrier + device synchronize, then R x K steps back to back, then
+    synchronize -- R chosen from an untimed calibration window so that the region lasts at least min_seconds.  There is NO
+    synchronisation between the windows: a look-ahead pipeline keeps working through a synchronize, so windows separated by one
+    each start with up to `look-ahead` frames already computed outside any timed interval (measured: the same code read 2651 /
+    2225 / 2083 frames/s at K = 20 / 64 / 256 that way).  Window boundaries are events recorded on the (idle) launching stream,
+    i.e. time stamps of the host loop.  Returns (per-window ms scaled so that their sum is the max over ranks of the region, this
+    rank's own per-window ms)."""
     import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wins, own, total = [], [], 0.0
-    while True:
-        barrier(device); torch.cuda.synchronize()
-        e0.record()
+    barrier(device); torch.cuda.synchronize()
+    e0.record(); run_k(K); e1.record(); torch.cuda.synchronize()          # calibration (untimed work, keeps the pipeline primed)
+    est = max_over_ranks(max(e0.elapsed_time(e1), 1e-3), device)
+    R = int(min(max_windows, max(1, np.ceil(min_seconds * 1e3 / est))))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    barrier(device); torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(R):
         run_k(K)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        own.append(ms)
-        wins.append(max_over_ranks(ms, device))               # every rank sees the same list, so all stop after the same window
-        total += wins[-1]
-        if total >= min_seconds * 1e3 or len(wins) >= max_windows:
-            return wins, own
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    own = [ev[i].elapsed_time(ev[i + 1]) for i in range(R)]
+    total_own = ev[0].elapsed_time(ev[R])
+    total = max_over_ranks(total_own, device)
+    scale = total / max(total_own, 1e-9)
+    return [w * scale for w in own], own
 
 
 def window_stats(wins, K, world):
-    """The reported rate is ALL timed steps / ALL timed time (the pipeline stays primed across windows, so this is the steady-state
-    rate whatever K is).  A K that is not a multiple of the micro-batch makes single windows alternate between holding one forward
-    more or less -- their median would pick one of the two modes -- so median / min / max are reported beside it, not used."""
+    """The reported rate is ALL timed steps / the whole timed region (timed_windows).  A K that is not a multiple of the micro-batch
+    makes single windows alternate between holding one forward more or less, so median / min / max are reported beside it, not used."""
     med, mean = float(np.median(wins)), float(np.sum(wins)) / len(wins)
     return {"count": len(wins), "steps_per_window": K, "timed_s": round(float(np.sum(wins)) / 1e3, 3),
             "ms_per_step_mean": round(mean / K, 4), "ms_per_step_median": round(med / K, 4), "ms_per_step_min": round(float(np.min(wins)) / K, 4),

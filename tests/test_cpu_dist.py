@@ -43,12 +43,14 @@ def test_world_size_2_aggregation():
 
 
 def test_window_statistics():
-    """value / ms_per_step come from the MEDIAN window; count, min and max are reported next to it."""
+    """value / ms_per_step come from ALL timed steps over the whole timed region (the windows are contiguous); count, median, min
+    and max of the single windows are reported next to it."""
     sys.path.insert(0, ROOT)
     import bench
     st, fps, ms_step = bench.window_stats([10.0, 12.0, 50.0], 20, 2)
     assert st["count"] == 3 and st["ms_per_step_median"] == 0.6 and st["ms_per_step_min"] == 0.5 and st["ms_per_step_max"] == 2.5
-    assert abs(fps - 2 * 20 / 0.012) < 1e-6 and abs(ms_step - 0.6) < 1e-12
+    assert st["ms_per_step_mean"] == 1.2 and st["timed_s"] == 0.072
+    assert abs(fps - 2 * 3 * 20 / 0.072) < 1e-6 and abs(ms_step - 1.2) < 1e-12
 
 
 def test_reference_arm_non_zero_ranks_do_nothing():

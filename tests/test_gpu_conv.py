@@ -22,6 +22,9 @@ CASES = [
     ("3x3_s2_bk32", 1, 64, 64, 32, 64, 3, 2, True, 2, 0, False),
     ("3x3_s2_odd_tiles", 2, 38, 38, 128, 256, 3, 2, True, 1, 0, False),
     ("1x1_s2_batch3", 3, 64, 32, 64, 128, 1, 2, True, 0, 0, False),
+    ("3x3_s2_small_images_batch10", 10, 16, 8, 256, 512, 3, 2, True, 3, 0, False),
+    ("1x1_s2_small_images_batch7", 7, 16, 8, 256, 512, 1, 2, False, 0, 0, False),
+    ("3x3_s2_tiny_images_batch33", 33, 8, 8, 64, 64, 3, 2, True, 1, 0, False),
     ("head_255_f32", 1, 19, 19, 1024, 255, 1, 1, False, 0, 0, True),
     ("res_after_act", 1, 38, 38, 128, 256, 3, 1, True, 1, 1, False),
     ("res_before_relu_batch5", 5, 32, 16, 128, 128, 3, 1, True, 3, 2, False),

@@ -1,7 +1,13 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -q -m gpu --timeout 120 > gpurun_out/r2z_tests.log 2>&1; tail -5 gpurun_out/r2z_tests.log | cut -c1-300
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 --dump-ops gpurun_out/r2z_ops.csv > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err
-cut -c1-200 gpurun_out/r2z_bench.json; tail -3 gpurun_out/r2z_bench.err
-YDST_DEBUG_PLAN=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-api --no-b1 2>&1 >/dev/null | grep "^conv_plan" | awk '!seen[$0]++' > gpurun_out/r2z_plan.txt
+timeout 300 python -m pytest tests/test_gpu_conv.py tests/test_gpu_reid.py -q -x --timeout 120 2>&1 | tail -2 | cut -c1-300
+for K in 20 64 256; do
+timeout 200 python bench.py --steps $K --warmup 5 --no-cpu-baseline --no-api --no-b1 > gpurun_out/r3d_bench_$K.json 2> gpurun_out/r3d_bench_$K.err
+python - gpurun_out/r3d_bench_$K.json <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    if l.startswith('{'):
+        d=json.loads(l); print(sys.argv[1], d['value'], d['e2e']['value'], d['roofline']['achieved'], d['stage_ms'], d['windows'])
+PY
+tail -2 gpurun_out/r3d_bench_$K.err
+done

@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     } else {
         int t = blockIdx.x;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y; img = t / p.tiles_y;
+        const int ty = t % p.tiles_y; img = (t / p.tiles_y) * p.TN;     // a tile covers TN whole images when they are small
         yo0 = ty * p.TH; xo0 = tx * p.TW;
     }
     const int num_kb = p.R * p.S * p.cin_blocks;
@@ -761,8 +761,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
                         tma_load_2d(a_dst, &maps.a[0], full, c0, row);
                     } else {
                         const int Y = r + p.pad_shift, X = sx + p.pad_shift;
-                        tma_load_3d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1),
-                                    img * p.in_Hp_half + yo0 + (Y >> 1));
+                        tma_load_4d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1), yo0 + (Y >> 1), img);
                     }
                     tma_load_2d(a_dst + a_bytes, &maps.b, full, (r * S + sx) * p.cin + c0, n0);
                 }
@@ -811,10 +810,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
             pix = pp;
         } else {
-            const int ly = row / p.TW, lx = row - ly * p.TW;
+            const int per = p.TH * p.TW;
+            const int ln = row / per, rr = row - ln * per;
+            const int ly = rr / p.TW, lx = rr - ly * p.TW;
             const int yo = yo0 + ly, xo = xo0 + lx;
-            valid = yo < p.Ho && xo < p.Wo;
-            pix = ((long long)img * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
+            valid = img + ln < p.N && yo < p.Ho && xo < p.Wo;
+            pix = ((long long)(img + ln) * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
         }
         grid_dep_wait();
         // (measured: staging the rows in shared memory for coalesced 16-byte stores is SLOWER here than the thread-per-row stores --
@@ -1549,6 +1550,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     // measured: where an N = 256 tile still leaves >= 96 CTAs it beats the model's pick -- the 128 x 256 MMA is
                     // the only shape whose operand reads fit the shared-memory bandwidth -- so it gets a bonus the clock model lacks
                     if (env_int("YDST_PREFER_BN256", 1) && bn == 256 && ctas >= 96 && ks == 1) t *= 0.5;
+                    if (pers && pers_mode == 3) t *= 0.05;        // tuning hook: take the persistent loop wherever it is feasible
                     // measured: a deep 3x3 layer whose 128 x 256 tiles do not even fill one wave (19x19 512->1024: 112 tiles, 36 900 tensor
                     // clocks each) runs faster as paired 128 x 128 tiles, two per SM (34.4 -> 29.4 us)
                     if (c2 && !pers && cta2_mode == 1 && bn == 128 && taps == 9 && cin_blocks >= 8 && (long long)m_tiles128 * ((cout16 + 255) / 256) <= kSms) t *= 0.4;
@@ -1709,15 +1711,22 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             const long long t = (long long)((out.W + c[0] - 1) / c[0]) * ((out.H + c[1] - 1) / c[1]);
             if (best < 0 || t < best) { best = t; p.TW = c[0]; p.TH = c[1]; }
         }
+        // small images (ReID layer4's 8 x 4 outputs): a 128-row tile over ONE image would be 3/4 padding, so it takes TN whole images
+        p.TN = 1;
+        if (out.H * out.W <= 64 && (out.W & (out.W - 1)) == 0 && (out.H & (out.H - 1)) == 0) {
+            p.TW = out.W; p.TH = out.H; p.TN = kBlockM / (out.W * out.H);
+        }
         p.tiles_x = (out.W + p.TW - 1) / p.TW;
         p.tiles_y = (out.H + p.TH - 1) / p.TH;
-        m_tiles = p.tiles_x * p.tiles_y * out.N;
+        m_tiles = p.tiles_x * p.tiles_y * ((out.N + p.TN - 1) / p.TN);
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px) {
-                cuuint64_t dims[3] = {(cuuint64_t)in.C, (cuuint64_t)((in.W + 2 - px + 1) / 2), (cuuint64_t)in.N * p.in_Hp_half};
-                cuuint64_t strides[2] = {(cuuint64_t)2 * in.ctot * 2, (cuuint64_t)2 * (in.W + 2) * in.ctot * 2};
-                cuuint32_t box[3] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH};
-                encode(&L.tmA[py * 2 + px], in.base + ((long long)py * (in.W + 2) + px) * in.ctot + in.coff, 3, dims, strides, box, row_bytes);
+                // parity sub-lattice (py, px) of the padded input: (channel, half-column, half-row, image)
+                cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)((in.W + 2 - px + 1) / 2), (cuuint64_t)p.in_Hp_half, (cuuint64_t)in.N};
+                cuuint64_t strides[3] = {(cuuint64_t)2 * in.ctot * 2, (cuuint64_t)2 * (in.W + 2) * in.ctot * 2,
+                                         (cuuint64_t)(in.H + 2) * (in.W + 2) * in.ctot * 2};
+                cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+                encode(&L.tmA[py * 2 + px], in.base + ((long long)py * (in.W + 2) + px) * in.ctot + in.coff, 4, dims, strides, box, row_bytes);
             }
     }
     // N tile: the largest of {128,64,32,16} that still yields >= one CTA per SM; otherwise the smallest useful one.
@@ -1740,8 +1749,8 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
     L.smem_bytes = stages * stage_bytes + 16 * stages + 16 + 2048 + 1024;   // + scale/bias staging, alignment slack
     L.grid = dim3((unsigned)m_tiles, (unsigned)((p.cout + bn - 1) / bn), 1);
     if (getenv("YDST_DEBUG_PLAN"))
-        fprintf(stderr, "conv_plan k%d s%d cin %d cout %d out %dx%dx%d grid %ux%u bn %d bk %d stages %d smem %d\n", R, stride, in.C, p.cout,
-                out.N, out.H, out.W, L.grid.x, L.grid.y, bn, p.block_k, stages, L.smem_bytes);
+        fprintf(stderr, "conv_plan k%d s%d cin %d cout %d out %dx%dx%d grid %ux%u bn %d bk %d stages %d smem %d tile %dx%dx%d\n", R, stride, in.C, p.cout,
+                out.N, out.H, out.W, L.grid.x, L.grid.y, bn, p.block_k, stages, L.smem_bytes, p.TN, p.TH, p.TW);
 }
 
 static void ensure_conv_tc2_attrs() {

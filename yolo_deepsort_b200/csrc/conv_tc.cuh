@@ -20,6 +20,7 @@ struct ConvTcParams {
     int in_Hp_half;    // patch mode: padded input height / 2
     long long P_total; // flat mode: N * (Ho+2) * (Wo+2)
     int TW, TH, tiles_x, tiles_y;   // patch mode
+    int TN;            // patch mode: whole images per tile (> 1 when TW x TH covers a small image)
     int pad_shift;     // patch mode: 1 - pad  (3x3: 0, 1x1: 1)
     // --- epilogue ---
     const float* scale;   // [cout rounded up to block_n]  BN gamma/sqrt(var+eps)   (1 if no BN)

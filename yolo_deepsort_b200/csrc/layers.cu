@@ -145,14 +145,20 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
     const long long total = (long long)N * H * W;
     const long long ntiles = (total + 127) / 128;
     const uint32_t sw = (uint32_t)((t >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3
-    const int chunks = cout >> 3;
+    const int chunks = cout >> 3, chunk_sh = 31 - __clz(chunks);
+    const bool chunk_p2 = (chunks & (chunks - 1)) == 0;
     uint32_t parity = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1u) {
         // ---- this thread's im2col row ----
         const long long idx = tile * 128 + t;
         const bool live = idx < total;
         int xo = 0, yo = 0, n = 0;
-        if (live) { xo = (int)(idx % W); const long long q = idx / W; yo = (int)(q % H); n = (int)(q / H); }
+        if (live) {                                        // (32-bit divisions: the launcher checks N*H*W < 2^31; the 64-bit ones cost ~400 instructions per pixel)
+            const unsigned u = (unsigned)idx, q = u / (unsigned)W;
+            xo = (int)(u - q * (unsigned)W);
+            n = (int)(q / (unsigned)H);
+            yo = (int)(q - (unsigned)n * (unsigned)H);
+        }
         float v[32];
 #pragma unroll
         for (int k = 27; k < 32; ++k) v[k] = 0.f;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
         tcgen05_fence_before();                            // the accumulator has been read: the next tile's MMAs may overwrite it
         __syncthreads();
         for (int item = t; item < 128 * chunks; item += 128) {
-            const int row = item / chunks, c = item - row * chunks;
+            const int row = chunk_p2 ? item >> chunk_sh : item / chunks, c = item - row * chunks;
             const long long pix = rowpix[row];
             if (pix < 0) continue;
             const uint4 v4 = *reinterpret_cast<const uint4*>(sm + (size_t)row * 128u + (size_t)((c ^ (row & 7)) << 4));
@@ -457,6 +463,7 @@ void launch_conv_first(const float* in, int N, int H, int W, const float* w, con
     static const bool tc_ok = !(getenv("YDST_STEM_TC") && atoi(getenv("YDST_STEM_TC")) == 0);
     if (tc_ok && w_hilo && stride == 1 && cout % 16 == 0 && act != ACT_MISH) {
         const long long tot = (long long)N * H * W;
+        YDST_CHECK(tot < (1LL << 31), "first-layer conv: %lld pixels per launch exceed the 32-bit index arithmetic", tot);
         // persistent: 8 CTAs per SM (26 KB of shared memory, <= 64 TMEM columns each) stride over the tiles
         static const int per_sm = getenv("YDST_STEM_CTAS_PER_SM") ? atoi(getenv("YDST_STEM_CTAS_PER_SM")) : 8;
         const long long ntiles = cdiv(tot, 128), cap = 148LL * (per_sm > 0 ? per_sm : 8);

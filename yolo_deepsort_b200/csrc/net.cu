@@ -488,14 +488,25 @@ const Plan& Reid::plan_for(int m) {
         plan.ops.push_back(op);
         plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
     } else {
-        {
-            Op op; op.kind = OP_CONV_FIRST; op.fsrc = in_f32_; op.out = view(0); op.w = weights_[wi++].get();
+        // The stem output (1.1 MB per crop) is written and read back once by the max-pool.  YDST_STEM_CHUNK=n does both in chunks of n
+        // crops that share ONE scratch region smaller than the L2, so that the pool reads hit the L2 and the scratch lines are
+        // overwritten there before they are evicted.  Measured (r2): SLOWER -- 1.60 / 1.69 / 1.61 ms per 408 crops at n = 48 / 24 / 96
+        // against 1.56 ms unchunked: both kernels are latency-bound, not HBM-bound, and the extra launches cost more than the
+        // traffic saves.  Off by default; kept as a knob.
+        static const int chunk_env = getenv("YDST_STEM_CHUNK") ? atoi(getenv("YDST_STEM_CHUNK")) : 0;
+        const int chunk = chunk_env > 0 ? chunk_env : m;
+        const ConvWeights* w0 = weights_[wi++].get();
+        for (int n0 = 0; n0 < m; n0 += chunk) {
+            const int cnt = std::min(chunk, m - n0);
+            Act scratch = bufs_[0]; scratch.N = cnt;                    // the same rows for every chunk
+            Act dst = x; dst.N = cnt; dst.base = x.base + (long long)n0 * x.Hp() * x.Wp() * x.ctot;
+            Op op; op.kind = OP_CONV_FIRST; op.fsrc = in_f32_ + (size_t)n0 * 128 * 64 * 3; op.out = scratch; op.w = w0;
             op.i0 = 128; op.i1 = 64; op.i2 = 1; op.i3 = ACT_RELU;
             plan.ops.push_back(op);
-            plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
+            Op pl; pl.kind = OP_MAXPOOL; pl.a = scratch; pl.out = dst; pl.i0 = 3; pl.i1 = 2; pl.i2 = 0;
+            plan.ops.push_back(pl);
         }
-        Op op; op.kind = OP_MAXPOOL; op.a = view(0); op.out = x; op.i0 = 3; op.i1 = 2; op.i2 = 0;
-        plan.ops.push_back(op);
+        plan.flops += 2.0 * m * 128 * 64 * 64 * 27;
     }
     for (int s = 0; s < 4; ++s) {
         const int base = 1 + 4 * s;
