@@ -57,6 +57,11 @@ CASES = [
     ("cta2_persistent_mish_38_batch8_res", 8, 38, 38, 256, 512, 3, 1, True, 2, 1, False),
     ("cta2_persistent_reid_8x4_batch200_res", 200, 8, 4, 512, 512, 3, 1, True, 3, 2, False),
     ("cta2_persistent_1x1_76_batch8", 8, 76, 76, 256, 128, 1, 1, True, 1, 0, False),
+    ("tap_persistent_s2_bk32_batch6", 6, 128, 128, 32, 64, 3, 2, True, 1, 0, False),
+    ("tap_persistent_s1_bk32_res_batch2", 2, 104, 104, 32, 64, 3, 1, True, 1, 1, False),
+    ("tap_persistent_s2_two_n_tiles_batch40", 40, 64, 32, 64, 256, 3, 2, True, 3, 0, False),
+    ("tap_persistent_1x1_s2_small_images_batch300", 300, 16, 8, 256, 512, 1, 2, False, 0, 0, False),
+    ("tap_persistent_mish_s2_batch3", 3, 152, 152, 64, 128, 3, 2, True, 2, 0, False),
     ("first_s1", 1, 64, 48, 3, 32, 3, 1, True, 1, 0, False),
     ("first_s2_64", 2, 32, 32, 3, 64, 3, 2, True, 3, 0, False),
     ("first_bias", 1, 16, 16, 3, 16, 3, 1, False, 0, 0, False),
@@ -71,6 +76,8 @@ def _opt_in_tilings(request, monkeypatch):
     name = request.node.name
     if "persistent" in name or "mpair" in name:
         monkeypatch.setenv("YDST_PERSISTENT", "2")
+    if "tap_persistent" in name:
+        monkeypatch.setenv("YDST_TAP_PERSISTENT", "2")
     if "cta2" in name:
         monkeypatch.setenv("YDST_CTA2", "2")
     if "mpair" in name:

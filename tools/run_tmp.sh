@@ -1,13 +1,5 @@
 mkdir -p gpurun_out
-export PYTHONUNBUFFERED=1
-timeout 300 python -m pytest tests/test_gpu_conv.py tests/test_gpu_reid.py -q -x --timeout 120 2>&1 | tail -2 | cut -c1-300
-for K in 20 64 256; do
-timeout 200 python bench.py --steps $K --warmup 5 --no-cpu-baseline --no-api --no-b1 > gpurun_out/r3d_bench_$K.json 2> gpurun_out/r3d_bench_$K.err
-python - gpurun_out/r3d_bench_$K.json <<'PY'
-import json,sys
-for l in open(sys.argv[1]):
-    if l.startswith('{'):
-        d=json.loads(l); print(sys.argv[1], d['value'], d['e2e']['value'], d['roofline']['achieved'], d['stage_ms'], d['windows'])
-PY
-tail -2 gpurun_out/r3d_bench_$K.err
+for T in 1 0; do
+YDST_TAP_PERSISTENT=$T timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 --dump-ops gpurun_out/r3g_ops_$T.csv > gpurun_out/r3g_bench_$T.json 2> gpurun_out/r3g_bench_$T.err
 done
+YDST_DEBUG_PLAN=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-api --no-b1 2>&1 >/dev/null | grep "^conv_plan k" | grep persistent | awk '!seen[$0]++' | cut -c1-220

@@ -831,6 +831,196 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent form of the tap-per-stage kernel, for layers with many short tiles (the 304x304 front of Darknet: 5 800 tiles of
+// 18 MMAs each, where a CTA's ~10 000 clocks of setup, first-load latency and epilogue bought ~900 clocks of tensor work).  One
+// CTA per SM strides over the tiles: the (A tap, B tap) stage ring runs across tiles, TMEM holds two accumulators, two epilogue
+// teams of four warps alternate tiles (direct stores: the stride-2 tiles are TH x TW patches, not runs of rows).  When the N
+// tile's whole weight slab fits beside the ring it is loaded once per column block (weight-stationary) and the stages only
+// carry activations.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kThreadsP = 320;   // warps 0-7: two epilogue teams, warp 8: TMA producer, warp 9: MMA issuer + TMEM owner
+template <bool kMish>
+__global__ void __launch_bounds__(kThreadsP, 1) conv_tc_pers_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcParams p, const int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)p.block_k * 2u;
+    const uint32_t a_bytes = kBlockM * row_bytes;
+    const uint32_t b_bytes = (uint32_t)p.block_n * row_bytes;
+    const int num_kb = p.R * p.S * p.cin_blocks;
+    const bool resident = p.b_resident != 0;                   // the weight slab [num_kb][block_n rows] sits in front of the ring
+    const uint32_t slab_bytes = resident ? (((uint32_t)num_kb * b_bytes + 1023u) & ~1023u) : 0u;
+    const uint32_t stage_bytes = ((resident ? a_bytes : a_bytes + b_bytes) + 1023u) & ~1023u;
+    const uint32_t ring_base = smem_base + slab_bytes;
+    const uint32_t bar_base = ring_base + (uint32_t)stages * stage_bytes;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * stages, bar_tfull = bar_base + 16u * stages, bar_tempty = bar_tfull + 16u;
+    const uint32_t bar_slab = bar_tempty + 16u, bar_slab_free = bar_slab + 8u, tmem_slot = bar_slab_free + 8u;
+    float* s_sb = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // [team][2 * block_n]
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * p.block_n) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8u * s, 1); mbar_init(bar_tempty + 8u * s, 128); }
+        mbar_init(bar_slab, 1); mbar_init(bar_slab_free, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 8 && lane == 0) { tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.b); }
+    if (warp == 9) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    grid_dep_launch();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int m_tiles = p.m_tiles, total_tiles = p.m_tiles * p.n_tiles, G = (int)gridDim.x;
+    // tile t -> (tm, tn), M fastest; flat mode: 128 padded-pixel rows; patch mode: TN images x TH x TW output pixels
+    auto tile_geom = [&](int tm, int& p0, int& img, int& yo0, int& xo0) {
+        p0 = 0; img = 0; yo0 = 0; xo0 = 0;
+        if (p.mode == 0) { p0 = tm * kBlockM; return; }
+        int t = tm;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; img = (t / p.tiles_y) * p.TN;
+        yo0 = ty * p.TH; xo0 = tx * p.TW;
+    };
+
+    if (warp == 8) {
+        const bool leader = elect_one();
+        // ================= TMA producer =================
+        grid_dep_wait();
+        int s = 0, loaded_tn = -1;
+        uint32_t ph = 1, ph_slab = 1;
+        const int cin_blocks = p.cin_blocks, block_k = p.block_k, S = p.S, mode = p.mode;
+        int tm = (int)blockIdx.x % m_tiles, tn = (int)blockIdx.x / m_tiles;
+        for (int t = (int)blockIdx.x; t < total_tiles; t += G) {
+            int p0, img, yo0, xo0;
+            tile_geom(tm, p0, img, yo0, xo0);
+            const int n0 = tn * p.block_n;
+            if (resident && tn != loaded_tn) {                 // new column block: wait until the MMAs of the old slab are done, reload
+                mbar_wait_hot(bar_slab_free, ph_slab);
+                ph_slab ^= 1u;
+                if (leader) {
+                    mbar_arrive_expect_tx(bar_slab, (uint32_t)num_kb * b_bytes);
+                    int cb = 0, tap = 0;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        tma_load_2d(smem_base + (uint32_t)kb * b_bytes, &maps.b, bar_slab, tap * p.cin + cb * block_k, n0);
+                        if (++cb == cin_blocks) { cb = 0; ++tap; }
+                    }
+                }
+                loaded_tn = tn;
+            }
+            int cb = 0, r = 0, sx = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_hot(bar_empty + 8u * s, ph);
+                const uint32_t full = bar_full + 8u * s;
+                const int c0 = cb * block_k;
+                const uint32_t a_dst = ring_base + (uint32_t)s * stage_bytes;
+                if (leader) {
+                    mbar_arrive_expect_tx(full, resident ? a_bytes : a_bytes + b_bytes);
+                    if (mode == 0) {
+                        const int row = p0 + (r - p.R / 2) * p.in_Wp + (sx - S / 2);
+                        tma_load_2d(a_dst, &maps.a[0], full, c0, row);
+                    } else {
+                        const int Y = r + p.pad_shift, X = sx + p.pad_shift;
+                        tma_load_4d(a_dst, &maps.a[(Y & 1) * 2 + (X & 1)], full, c0, xo0 + (X >> 1), yo0 + (Y >> 1), img);
+                    }
+                    if (!resident) tma_load_2d(a_dst + a_bytes, &maps.b, full, (r * S + sx) * p.cin + c0, n0);
+                }
+                if (++cb == cin_blocks) { cb = 0; if (++sx == S) { sx = 0; ++r; } }
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            tm += G; while (tm >= m_tiles) { tm -= m_tiles; ++tn; }
+        }
+        if (leader) prefetch_next_weights(p);
+    } else if (warp == 9) {
+        const bool leader = elect_one();
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n);
+        const uint32_t hi = desc_hi(row_bytes);
+        const int ksteps = p.block_k >> 4, bn = p.block_n;
+        int s = 0, it = 0, loaded_tn = -1;
+        uint32_t ph = 0, ph_slab = 0;
+        int tm = (int)blockIdx.x % m_tiles, tn = (int)blockIdx.x / m_tiles;
+        for (int t = (int)blockIdx.x; t < total_tiles; t += G, ++it) {
+            const int ab = it & 1;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * bn);
+            int tm_next = tm + G, tn_next = tn;
+            while (tm_next >= m_tiles) { tm_next -= m_tiles; ++tn_next; }
+            if (resident && tn != loaded_tn) { mbar_wait_hot(bar_slab, ph_slab); ph_slab ^= 1u; loaded_tn = tn; }
+            mbar_wait_hot(bar_tempty + 8u * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            uint32_t acc = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_hot(bar_full + 8u * s, ph);
+                tcgen05_fence_after();
+                const uint32_t a_lo = desc_lo(ring_base + (uint32_t)s * stage_bytes);
+                const uint32_t b_lo = resident ? desc_lo(smem_base + (uint32_t)kb * b_bytes) : a_lo + (a_bytes >> 4);
+                if (leader) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        umma_f16_lh(tmem_d, a_lo + 2u * k, b_lo + 2u * k, hi, idesc, acc);
+                        acc = 1;
+                    }
+                    umma_commit(bar_empty + 8u * s);
+                }
+                acc = 1;
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            if (leader) {
+                umma_commit(bar_tfull + 8u * ab);
+                // the slab may be overwritten once the MMAs of the LAST tile that uses it have completed
+                if (resident && (t + G >= total_tiles || tn_next != tn)) umma_commit(bar_slab_free);
+            }
+            tm = tm_next; tn = tn_next;
+        }
+    } else {
+        // ================= epilogue: two teams alternate tiles =================
+        const int team = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127, ebar = 1 + team;
+        float* s_sbt = s_sb + team * 256;                      // block_n <= 128: 2 * block_n floats per team
+        grid_dep_wait();
+        int staged_tn = -1;
+        for (int it = team;; it += 2) {
+            const int t = (int)blockIdx.x + it * G;
+            if (t >= total_tiles) break;
+            const int tn = t / m_tiles, tm = t - tn * m_tiles;
+            const int n0 = tn * p.block_n;
+            int p0, img, yo0, xo0;
+            tile_geom(tm, p0, img, yo0, xo0);
+            if (tn != staged_tn) {
+                if (staged_tn >= 0) epi_bar_sync(ebar);
+                stage_scale_bias(p, n0, s_sbt, tid, ebar);
+                staged_tn = tn;
+            }
+            const int row = tid;
+            long long pix;
+            bool valid;
+            if (p.mode == 0) {
+                const long long pp = (long long)p0 + row;
+                const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
+                const int rem = (int)(pp % HpWp);
+                const int y = rem / Wp, x = rem - y * Wp;
+                valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
+                pix = pp;
+            } else {
+                const int per = p.TH * p.TW;
+                const int ln = row / per, rr = row - ln * per;
+                const int ly = rr / p.TW, lx = rr - ly * p.TW;
+                const int yo = yo0 + ly, xo = xo0 + lx;
+                valid = img + ln < p.N && yo < p.Ho && xo < p.Wo;
+                pix = ((long long)(img + ln) * (p.Ho + 2) + yo + 1) * (p.Wo + 2) + xo + 1;
+            }
+            const int ab = it & 1;
+            epilogue_tile<kMish>(p, tmem_base + (uint32_t)(ab * p.block_n), wq, n0, pix, valid, s_sbt, bar_tfull + 8u * ab, ((uint32_t)(it >> 1)) & 1u,
+                                 bar_tempty + 8u * ab);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 9) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Halo kernel (stride 1, 64-channel blocks).
 //   * the activation chunk of one channel block -- the tile's 128 padded-pixel rows plus (Wp + 1) halo rows on each
 //     side -- is fetched ONCE and all nine taps read it through row-shifted UMMA descriptors (tap (r,s) starts
@@ -1678,13 +1868,17 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
             L.stages = 0;
             L.smem_bytes = t.smem_bytes + 1024;
             L.grid = dim3((unsigned)p.m_tiles, (unsigned)p.n_tiles, (unsigned)t.ksplit);
-            if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, num_sms()), 1, 1);
+            // A persistent CTA owns its SM's shared memory for the whole launch, so a kernel of another stream (the association's
+            // single-CTA LSAP runs ~70 us) that lands on an SM between two persistent launches holds back ONE CTA of the next launch --
+            // and with it the launch.  YDST_PERS_SPARE_SMS SMs are therefore left out of every persistent grid.
+            const int pers_sms = std::max(2, num_sms() - env_int("YDST_PERS_SPARE_SMS", 0));
+            if (p.persistent) L.grid = dim3((unsigned)std::min(p.m_tiles * p.n_tiles, pers_sms), 1, 1);
             if (p.cta2) {
                 YDST_CHECK(p.store_tma && t.mpair == 1 && t.ksplit == 1, "CTA pairs need the TMA-store path");
                 if (p.persistent) {
                     // one cluster per SM pair strides over the pairs of M tiles; no more clusters than can be resident at once
                     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-                    const int clusters = std::min(pairs, max_active_clusters(act == ACT_MISH, L.smem_bytes));
+                    const int clusters = std::min(std::min(pairs, pers_sms / 2), max_active_clusters(act == ACT_MISH, L.smem_bytes));
                     L.grid = dim3(2u * (unsigned)clusters, 1, 1);
                 } else {
                     L.grid.x = (L.grid.x + 1u) & ~1u;            // clusters of two along M: an odd tail tile gets an idle partner (all rows out of range)
@@ -1733,6 +1927,16 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
     int bn = 128;
     while (bn > 16 && (bn > p.cout || (long long)m_tiles * ((p.cout + bn - 1) / bn) < num_sms())) bn >>= 1;
     if (bn < 32 && p.cout >= 32) bn = 32;
+    // many short tiles (tap_pers_mode 1: at least four per SM; 2: more tiles than SMs, for the tests): the persistent form, with the
+    // widest N tile (fewer re-fetches of the activation taps) -- conv_tc_pers_kernel
+    const int tap_pers_mode = env_int("YDST_TAP_PERSISTENT", 1);
+    bool tap_pers = false;
+    if (tap_pers_mode && !out_f32) {
+        int bnp = 128;
+        while (bnp > 32 && bnp > p.cout) bnp >>= 1;
+        const long long tiles = (long long)m_tiles * ((p.cout + bnp - 1) / bnp);
+        if (p.cout % bnp == 0 && tiles >= (tap_pers_mode >= 2 ? num_sms() + 1 : 4 * num_sms())) { tap_pers = true; bn = bnp; }
+    }
     p.block_n = bn;
     {
         const int K = R * S * in.C;
@@ -1741,8 +1945,26 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
         cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)bn};
         encode(&L.tmB, w_packed, 2, dims, strides, box, row_bytes);
     }
-    const int stage_bytes = (kBlockM * row_bytes + bn * row_bytes + 1023) & ~1023;
     const int num_kb = R * S * p.cin_blocks;
+    if (tap_pers) {
+        const int budget = 216 * 1024, fixed = 4096 + 1024;            // barriers + two teams' scale/bias, alignment slack
+        const int slab = (num_kb * bn * row_bytes + 1023) & ~1023;
+        // weight-stationary when the slab leaves room for at least six activation stages
+        const bool res = slab + 6 * ((kBlockM * row_bytes + 1023) & ~1023) + fixed <= budget;
+        const int st_bytes = ((res ? kBlockM * row_bytes : kBlockM * row_bytes + bn * row_bytes) + 1023) & ~1023;
+        const int stages_p = std::max(2, std::min(16, (budget - fixed - (res ? slab : 0)) / st_bytes));
+        p.persistent = 1; p.b_resident = res ? 1 : 0;
+        p.m_tiles = m_tiles; p.n_tiles = (p.cout + bn - 1) / bn;
+        L.stages = stages_p;
+        L.smem_bytes = (res ? slab : 0) + stages_p * st_bytes + fixed;
+        L.grid = dim3((unsigned)std::min((long long)num_sms(), (long long)p.m_tiles * p.n_tiles), 1, 1);
+        if (getenv("YDST_DEBUG_PLAN"))
+            fprintf(stderr, "conv_plan k%d s%d cin %d cout %d out %dx%dx%d grid %ux1 bn %d bk %d stages %d smem %d tile %dx%dx%d persistent resident %d tiles %dx%d\n",
+                    R, stride, in.C, p.cout, out.N, out.H, out.W, L.grid.x, bn, p.block_k, stages_p, L.smem_bytes, p.TN, p.TH, p.TW, p.b_resident,
+                    p.m_tiles, p.n_tiles);
+        return;
+    }
+    const int stage_bytes = (kBlockM * row_bytes + bn * row_bytes + 1023) & ~1023;
     int stages = std::max(2, std::min(8, (100 * 1024) / stage_bytes));
     stages = std::min(stages, std::max(num_kb, 1));
     L.stages = stages;
@@ -1910,6 +2132,18 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
             if (h[11]) fprintf(stderr, "    epilogue thread 100, group 0: acc_ready %lld | 16 cols in registers +%lld, computed +%lld, staged +%lld, next 16 cols in registers +%lld, "
                                "group staged and barrier passed +%lld (res_mode %d)\n", d(0, 5), d(5, 11), d(11, 15), d(15, 12), d(12, 13), d(13, 14), L.p.res_mode);
         }
+        return;
+    }
+    if (L.p.persistent) {
+        static bool attrp_set = false;
+        if (!attrp_set) {
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            YDST_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            attrp_set = true;
+        }
+        if (L.p.act == ACT_MISH) conv_tc_pers_kernel<true><<<L.grid, kThreadsP, L.smem_bytes, stream>>>(maps, L.p, L.stages);
+        else conv_tc_pers_kernel<false><<<L.grid, kThreadsP, L.smem_bytes, stream>>>(maps, L.p, L.stages);
+        YDST_CUDA(cudaGetLastError());
         return;
     }
     if (L.p.act == ACT_MISH) conv_tc_kernel<true><<<L.grid, kThreads, L.smem_bytes, stream>>>(maps, L.p, L.stages);
