@@ -238,7 +238,7 @@ def run_assoc(args):
     K, Wm = (args.steps or 8), ASSOC_WARM
     L = lib()
     max_windows = max(2, 160 // K)                           # the crowd never rewinds: every timed update sees a fresh frame
-    n_frames = Wm + 2 + 4 + 2 * max_windows * K
+    n_frames = Wm + 2 + 4 + 2 * (max_windows + 1) * K          # two timed regions, each one calibration window + up to max_windows
     frames = assoc_frames(n, n_frames, seed=rank)
     trk = TrackerHandle(device=str(device), cap_tracks=4096, cap_dets=2048, **{"max_dist": 0.3, "max_iou_distance": 0.7, "max_age": 30, "n_init": 3, "nn_budget": 30})
     dev = [(torch.from_numpy(tl).to(device), torch.from_numpy(ft).to(device)) for tl, ft, _ in frames]
