@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-for T in 1 0; do
-YDST_TAP_PERSISTENT=$T timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 --dump-ops gpurun_out/r3g_ops_$T.csv > gpurun_out/r3g_bench_$T.json 2> gpurun_out/r3g_bench_$T.err
-done
-YDST_DEBUG_PLAN=1 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-api --no-b1 2>&1 >/dev/null | grep "^conv_plan k" | grep persistent | awk '!seen[$0]++' | cut -c1-220
+timeout 200 python bench.py --steps 64 --warmup 16 --no-cpu-baseline --no-api --no-b1 > gpurun_out/r3h_bench.json 2> gpurun_out/r3h_bench.err
+python - gpurun_out/r3h_bench.json <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    if l.startswith('{'):
+        d=json.loads(l); print(sys.argv[1], d['value'], d['e2e']['value'], d['roofline']['achieved'], d['stage_ms'], d['config']['latency_frames'])
+PY
+tail -2 gpurun_out/r3h_bench.err
+timeout 300 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_e2e.py -q -x --timeout 200 2>&1 | tail -2
