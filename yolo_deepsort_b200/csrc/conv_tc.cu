@@ -1976,7 +1976,10 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
 }
 
 static void ensure_conv_tc2_attrs() {
-    static bool attr2_set = false;
+    static bool attr2_set_dev[64] = {false};                  // the shared-memory opt-in is a per-device attribute of the kernel
+    int dev = 0;
+    YDST_CUDA(cudaGetDevice(&dev));
+    bool& attr2_set = attr2_set_dev[dev & 63];
     if (attr2_set) return;
     const void* fns[12] = {(const void*)conv_tc2_kernel<false, false, false, true>, (const void*)conv_tc2_kernel<true, false, false, true>,
                            (const void*)conv_tc2_kernel<false, true, false, true>,  (const void*)conv_tc2_kernel<true, true, false, true>,
@@ -2047,7 +2050,10 @@ void conv_tc_trace_dump() {
 }
 
 void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};
+    int dev_id = 0;
+    YDST_CUDA(cudaGetDevice(&dev_id));
+    bool& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
         YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         YDST_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2135,7 +2141,8 @@ void conv_tc_run(const ConvTcLaunch& L, cudaStream_t stream) {
         return;
     }
     if (L.p.persistent) {
-        static bool attrp_set = false;
+        static bool attrp_set_dev[64] = {false};
+        bool& attrp_set = attrp_set_dev[dev_id & 63];
         if (!attrp_set) {
             YDST_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             YDST_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
