@@ -274,6 +274,39 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
     }
     pred = (float*)arena_.alloc((size_t)batch * rows * fields * sizeof(float));
 
+    // Zero-copy concatenation: a multi-source route reads a buffer that its producers wrote into directly -- each eligible source
+    // layer's output IS a channel slice of the route's buffer (every kernel takes (ctot, coff) views), so no copy kernel runs for
+    // it.  yolov4's CSP blocks concatenate up to 304x304x128 tensors: 22 copy launches, 0.59 ms of a 4.1 ms forward, before this.
+    // Eligible: a convolution (not the first layer, not a YOLO head), max-pool, upsample or shortcut that is not yet part of
+    // another concatenation; anything else (aliases of earlier layers, grouped routes) is copied into its slice as before.
+    struct Slice { int route = -1, coff = 0; };
+    std::vector<Slice> slice(n);
+    static const bool zero_copy = !(getenv("YDST_ZERO_COPY_ROUTE") && atoi(getenv("YDST_ZERO_COPY_ROUTE")) == 0);
+    if (zero_copy)
+        for (int l = 0; l < n; ++l) {
+            if (L[l].type != YDST_ROUTE || L[l].n_src < 2 || L[l].groups > 0) continue;
+            int coff = 0;
+            for (int k = 0; k < L[l].n_src; ++k) {
+                const int sidx = L[l].src[k];
+                const int t = L[sidx].type;
+                const bool head = t == YDST_CONV && sidx + 1 < n && L[sidx + 1].type == YDST_YOLO;
+                const bool ok = (t == YDST_CONV && sidx > 0 && !head) || t == YDST_MAXPOOL || t == YDST_UPSAMPLE || t == YDST_SHORTCUT;
+                bool dup = false;
+                for (int j = 0; j < k; ++j) dup = dup || L[l].src[j] == sidx;
+                if (ok && !dup && slice[sidx].route < 0 && shp[sidx].C % 8 == 0 && coff % 8 == 0) { slice[sidx].route = l; slice[sidx].coff = coff; }
+                coff += shp[sidx].C;
+            }
+        }
+    std::vector<Act> concat(n);                              // the route buffers, allocated when their first producer needs them
+    auto alloc_out = [&](int l) -> Act {
+        if (slice[l].route < 0) return make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+        const int r = slice[l].route;
+        if (!concat[r].base) concat[r] = make_act(arena_, batch, shp[r].H, shp[r].W, shp[r].C);
+        Act v = concat[r];
+        v.C = shp[l].C; v.coff = slice[l].coff;
+        return v;
+    };
+
     // second pass: buffers + ops
     std::vector<Act> out(n);
     std::vector<float*> head_f32(n, nullptr);
@@ -313,7 +346,8 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
                                  head_f32[l], d.filters, &ws_);
                     out[l] = geo;
                 } else {
-                    out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                    // (a convolution with a fused shortcut writes the shortcut layer's tensor: that layer's slice, if it has one)
+                    out[l] = (fuse_sc && slice[l + 1].route >= 0 && slice[l].route < 0) ? alloc_out(l + 1) : alloc_out(l);
                     if (first) {
                         op.kind = OP_CONV_FIRST;
                         op.fsrc = in_f32_; op.out = out[l]; op.w = cw;
@@ -333,14 +367,14 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
                 break;
             }
             case YDST_MAXPOOL: {
-                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                out[l] = alloc_out(l);
                 op.kind = OP_MAXPOOL; op.a = out[l - 1]; op.out = out[l];
                 op.i0 = d.size; op.i1 = d.stride; op.i2 = (d.size == 2 && d.stride == 1) ? 1 : 0;
                 plan.ops.push_back(op);
                 break;
             }
             case YDST_UPSAMPLE: {
-                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                out[l] = alloc_out(l);
                 op.kind = OP_UPSAMPLE; op.a = out[l - 1]; op.out = out[l]; op.i0 = d.size;
                 plan.ops.push_back(op);
                 break;
@@ -355,21 +389,26 @@ void Detector::build(const ydst_layer_desc* L, int n, const float* weights, size
                     }
                 } else {
                     YDST_CHECK(d.groups <= 0, "grouped multi-source route is not supported (layer %d)", l);
-                    out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                    if (!concat[l].base) concat[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                    out[l] = concat[l];
                     int coff = 0;
                     for (int s = 0; s < d.n_src; ++s) {
-                        Op cp;
-                        cp.layer = l; cp.kind = OP_COPY; cp.a = out[d.src[s]];
-                        cp.out = out[l]; cp.out.C = cp.a.C; cp.out.coff = coff;
-                        coff += cp.a.C;
-                        plan.ops.push_back(cp);
+                        const Act& src = out[d.src[s]];
+                        const bool in_place = src.base == out[l].base && src.coff == coff && src.ctot == out[l].ctot;   // written there by its producer
+                        if (!in_place) {
+                            Op cp;
+                            cp.layer = l; cp.kind = OP_COPY; cp.a = src;
+                            cp.out = out[l]; cp.out.C = cp.a.C; cp.out.coff = coff;
+                            plan.ops.push_back(cp);
+                        }
+                        coff += src.C;
                     }
                 }
                 break;
             }
             case YDST_SHORTCUT: {
                 if (fused_away[l]) { out[l] = out[l - 1]; break; }            // produced by the conv epilogue
-                out[l] = make_act(arena_, batch, shp[l].H, shp[l].W, shp[l].C);
+                out[l] = alloc_out(l);
                 op.kind = OP_ADD; op.a = out[l - 1]; op.b = out[d.src[0]]; op.out = out[l];
                 plan.ops.push_back(op);
                 break;
