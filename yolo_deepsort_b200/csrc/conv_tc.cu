@@ -535,7 +535,8 @@ __device__ __forceinline__ void epilogue_tile_wide(const ConvTcParams& p, const 
     }
 }
 
-// Persistent-loop epilogue (conv_tc2_kernel<.., kPers = true, kPair = false>).  Two teams of four warps alternate tiles: team e
+// Persistent-loop epilogue (conv_tc2_kernel<.., kPers = true, ..>; kMp accumulators per tile, kCta2: the CTA is half of a pair).
+// Two teams of four warps alternate tiles (one team when the planner says the MMAs of a tile outlast its epilogue): team e
 // drains accumulator buffer e of tiles e, e + 2, ... while the MMA issuer fills the other one.  A thread owns one output row and
 // walks the tile's 64-column groups; the TMEM load of the next 16-column block is in flight while the current one is finished
 // (scale/bias, activation, residual -- all compile-time -- fp16 pack) and written into a 128B-swizzled 16 KB staging buffer that
@@ -1403,8 +1404,9 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             }
 #undef YDST_PERS
         } else {
-        const int eg = kPers ? warp >> 2 : 0;                  // persistent: the warpgroups alternate tiles
-        const int half = kPers ? 0 : warp >> 2;                // otherwise: both work on the one tile (wide epilogue), or the second idles
+        // one tile per CTA: both warpgroups work on it (wide epilogue), or the second one idles (direct-store, split-K, M-pair tiles)
+        constexpr int eg = 0;
+        const int half = warp >> 2;
         const int tid = threadIdx.x & 127, ebar = 1 + eg;
         const int wq = warp & 3;                               // TMEM lane quarter of this warp
         const int row = tid;
@@ -1420,8 +1422,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
         }
         int tm, tn;
         for (int it = 0; tile_at(it, tm, tn); ++it) {
-            if (kPers && (it & 1) != eg) continue;             // the other warpgroup drains this tile
-            if (!kPers && !wide && half) break;                // direct-store and split-K epilogues use one warpgroup
+            if (!wide && half) break;                          // direct-store and split-K epilogues use one warpgroup
             const int n0 = tn * p.block_n;
             const int ab = it & 1;
             const uint32_t bar_full = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
@@ -1439,14 +1440,14 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             for (int h = 0; h < mp; ++h) {                     // the 128-row accumulators of this tile, one after the other
             const int p0 = (tm * mp + h) * kBlockM;
             const uint32_t tmem_d = tmem_base + (uint32_t)((ab * mp + h) * p.block_n);
-            const uint32_t bar_rel = (kPers && h == mp - 1) ? bar_tempty + 8u * ab : 0u;
+            constexpr uint32_t bar_rel = 0u;                       // (no second tile: nobody waits for the accumulator)
             const long long pp = (long long)p0 + row;
             const int rem = (int)(pp % HpWp);
             const int y = rem / Wp, x = rem - y * Wp;
             const bool valid = pp < p.P_total && (p.gemm || (y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo));
             if (p.ksplit == 1) {
                 if (it == 0 && h == 0 && threadIdx.x == 0 && p.trace) { mbar_wait(bar_full, par); trace_mark(p, 5); }
-                if constexpr (!kPers && !kPair) {
+                if constexpr (!kPair) {
                     if (wide) {
 #define YDST_WIDE(A, R) epilogue_tile_wide<kMish, A, R>(p, &maps.a[1], &maps.a[2], gaddr, smem_raw, smem_u32(smem_raw), tmem_d, wq, half, row, n0, p0, \
                                                         valid, s_sbg, bar_full, bar_res, res_early)

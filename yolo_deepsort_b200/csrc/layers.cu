@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(128) conv_first_tc_kernel(const float* __restr
         float v[32];
 #pragma unroll
         for (int k = 27; k < 32; ++k) v[k] = 0.f;
-#pragma unroll
         {
             const bool rok[3] = {live && yo >= 1, live, live && yo + 1 < H}, cok[3] = {xo >= 1, true, xo + 1 < W};
             const float* ctr = in + (((long long)n * H + yo) * W + xo) * 3;      // never dereferenced unless the tap is inside
