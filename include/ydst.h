@@ -168,6 +168,22 @@ int ydst_iou_cost(const float* mean_dev, const int* tsu_dev, int n, const float*
 int ydst_lsap(const float* cost_dev, int nr, int nc, float max_dist, int* rows_host, int* cols_host, int* over_max_host,
               void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * ActionIdentify: the rule-based action recognition on the (K,6) track rows.
+ * Replaces action/action_Identify.py:15-47 (ActionIdentify.update), action/orbit.py:5-26 (Orbit) and the rules of
+ * action/actions.py:23-150.  Rule kinds: 0 TakeOff(class_id, delta=(p0,p1)), 1 Landing(class_id, delta), 2 Glide(class_id,
+ * delta), 3 FastCrossing(class_id, speed=p0), 4 BreakInto(class_id, timeout=p0).  The orbit cache lives on the device.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ydst_action ydst_action;
+int ydst_action_create(int max_age, int max_size, const int* kinds, const int* class_ids, const double* p0, const double* p1,
+                       int n_rules, int capacity, ydst_action** out);
+int ydst_action_destroy(ydst_action* a);
+/* One ActionIdentify.update(detections): rows_host (k,6) int32 [x1,y1,x2,y2,track_id,class_id] (k may be 0: every orbit ages),
+ * timestamp = time.time() of the call (orbit.py:26).  triples_host receives *n_host rows (track_id, class_id, rule index) in the
+ * reference's order (cache insertion order, rules in list order); capacity k * n_rules.  Synchronises.                  */
+int ydst_action_update(ydst_action* a, const int32_t* rows_host, int k, double timestamp, int32_t* triples_host, int* n_host,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tracker: Tracker + Track + NearestNeighborDistanceMetric + the DeepSort.update output block.
  * Replaces deep_sort/sort/tracker.py:38-176, track.py:63-152, nn_matching.py:139-156,

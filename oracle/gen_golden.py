@@ -16,6 +16,8 @@ Golden files (small, committed):
                       image digests per frame
   reid.npz            Extractor features for boxes on one frame (crop + cv2.resize + Net)
   overlay.npz         LabelDrawer.draw_labels_by_trackers / draw_labels output (images and digests) on two synthetic frames
+  action.npz          ActionIdentify.update (action/) on a seeded (K,6) row sequence with patched time stamps: the emitted
+                      (track id, class id, rule) triples per frame, every rule firing, deletions and re-insertions included
   window.npz          ImageDetector.detect in sliding-window mode (win_size, overlap; batched tiles + merge-NMS) on a 700x1000
                       image, and soft_non_max_suppression(merge=True) on hand-built predictions that reach the k == n and
                       k == 1 branches of the merge block
@@ -410,11 +412,44 @@ def gen_overlay():
     print("  overlay fixture written (reference LabelDrawer on 2 frames x 3 modes)")
 
 
+from .action_ref import ACTION_RULES, action_sequence  # noqa: E402  (shared with the tests: no reference needed to rebuild the inputs)
+
+
+def gen_action():
+    """action.npz: the reference ActionIdentify.update (action/action_Identify.py:15-47) on action_sequence()."""
+    import time as _time
+    from action import actions as RA
+    from action.action_Identify import ActionIdentify as RefAI
+    frames, stamps = action_sequence()
+    rules = [getattr(RA, name)(cid, prm) for name, cid, prm in ACTION_RULES]
+    ai = RefAI(rules, max_age=6, max_size=4)
+    real = _time.time
+    out = {"n_frames": np.int32(len(frames)), "stamps": np.asarray(stamps, np.float64)}
+    total = 0
+    try:
+        for f, (rows, ts) in enumerate(zip(frames, stamps)):
+            _time.time = lambda ts=ts: ts
+            res = ai.update(rows if len(rows) else [])
+            names = [r.name for r in rules]
+            trip = np.asarray([(tid, cid, [i for i, r in enumerate(rules) if r.name == nm and r.class_id == cid][0]) for tid, cid, nm in res],
+                              np.int32).reshape(-1, 3)
+            out[f"rows_{f}"] = rows
+            out[f"actions_{f}"] = trip
+            total += len(trip)
+    finally:
+        _time.time = real
+    assert total > 40, total
+    kinds = sorted({int(t[2]) for f in range(len(frames)) for t in out[f"actions_{f}"]})
+    assert kinds == list(range(len(ACTION_RULES))), kinds       # every rule fires somewhere
+    np.savez_compressed(os.path.join(GOLD, "action.npz"), **out)
+    print(f"  action fixture written ({len(frames)} frames, {total} (track, class, rule) triples, rules seen {kinds})")
+
+
 def main():
     ref_shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_other_cfgs, gen_reid, gen_window, gen_overlay, gen_video):
+    for fn in (gen_kalman, gen_assoc, gen_tiny, gen_other_cfgs, gen_reid, gen_window, gen_overlay, gen_video, gen_action):
         print(fn.__name__)
         fn()
     print("golden vectors written to", GOLD)

@@ -16,12 +16,12 @@ DROPIN = os.path.join(ROOT, "dropin")
 
 @pytest.fixture
 def dropin_path():
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("yolo3", "deep_sort")}
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("yolo3", "deep_sort", "action")}
     sys.path.insert(0, DROPIN)
     yield
     sys.path.remove(DROPIN)
     for k in list(sys.modules):
-        if k.split(".")[0] in ("yolo3", "deep_sort"):
+        if k.split(".")[0] in ("yolo3", "deep_sort", "action"):
             del sys.modules[k]
     sys.modules.update(saved)
 
@@ -34,6 +34,9 @@ def test_reference_import_lines_resolve(dropin_path):
     from yolo3.detect.img_detect import ImageDetector
     from yolo3.utils.model_build import soft_non_max_suppression, resize_boxes, p1p2Toxywh
     from yolo3.utils.parse_config import parse_model_config
+    from action.action_Identify import ActionIdentify                  # video_deepsort.py:3-4
+    from action import actions as rules
+    assert ActionIdentify is Y.ActionIdentify and all(hasattr(rules, n) for n in ("TakeOff", "Landing", "Glide", "FastCrossing", "BreakInto"))
     assert Darknet is Y.Darknet and DeepSort is Y.DeepSort and VideoDetector is Y.VideoDetector and ImageDetector is Y.ImageDetector
     assert callable(build_tracker) and callable(soft_non_max_suppression) and callable(resize_boxes) and callable(p1p2Toxywh)
     defs = parse_model_config(os.path.join(ROOT, "config", "yolov3-tiny.cfg"))

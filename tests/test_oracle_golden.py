@@ -203,3 +203,21 @@ def test_video_detector_loop_vs_golden(tmp_path):
         result = cv2.cvtColor(img, cv2.COLOR_RGB2BGR)
         digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(result).tobytes()).digest(), np.uint8)
         np.testing.assert_array_equal(digest, g[f"image_sha256_{t}"], err_msg=f"yielded image of frame {t}")
+
+
+def test_action_identify_oracle_vs_reference_golden():
+    """oracle/action_ref.py against the triples the reference's own action/ package emitted (tests/golden/action.npz), and the
+    golden's inputs against the committed generator (so that the fixture can be rebuilt without the reference)."""
+    from oracle.action_ref import ACTION_RULES, ActionIdentifyRef, action_sequence
+    g = np.load(os.path.join(GOLDEN, "action.npz"))
+    frames, stamps = action_sequence()
+    assert len(frames) == int(g["n_frames"])
+    np.testing.assert_array_equal(np.asarray(stamps), g["stamps"])
+    ref = ActionIdentifyRef(ACTION_RULES, max_age=6, max_size=4)
+    fired = set()
+    for f, rows in enumerate(frames):
+        np.testing.assert_array_equal(rows, g[f"rows_{f}"])
+        got = ref.update(rows, stamps[f])
+        assert got == [tuple(int(v) for v in t) for t in g[f"actions_{f}"]], f
+        fired |= {r for _, _, r in got}
+    assert fired == set(range(len(ACTION_RULES)))

@@ -10,3 +10,4 @@ from .reid import Extractor  # noqa: F401
 from .deepsort import DeepSort  # noqa: F401
 from .pipeline import FramePipeline  # noqa: F401
 from .detect import ImageDetector, VideoDetector  # noqa: F401
+from .action import ActionIdentify  # noqa: F401

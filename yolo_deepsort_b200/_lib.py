@@ -64,6 +64,9 @@ SIGNATURES = {
     "ydst_appearance_cost": (_I, [_P, _P, _I, _P, _I, _P, _P, _P, ctypes.c_double, _P, _P]),
     "ydst_iou_cost": (_I, [_P, _P, _I, _P, _I, ctypes.c_double, _P, _P]),
     "ydst_lsap": (_I, [_P, _I, _I, _F, _P, _P, _P, _P]),
+    "ydst_action_create": (_I, [_I, _I, _P, _P, _P, _P, _I, _I, ctypes.POINTER(_P)]),
+    "ydst_action_destroy": (_I, [_P]),
+    "ydst_action_update": (_I, [_P, _P, _I, ctypes.c_double, _P, ctypes.POINTER(_I), _P]),
     "ydst_tracker_create": (_I, [ctypes.c_double, ctypes.c_double, _I, _I, _I, _I, _I, ctypes.POINTER(_P)]),
     "ydst_tracker_destroy": (_I, [_P]),
     "ydst_tracker_update": (_I, [_P, _P, _P, _P, _I, _P, ctypes.POINTER(_I), _P]),

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "conv_tc.cu", "layers.cu", "nms.cu", "assoc.cu", "cosine_tc.cu", "net.cu", "tracker.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "conv_tc.cu", "layers.cu", "nms.cu", "assoc.cu", "cosine_tc.cu", "net.cu", "tracker.cu", "action.cu")]
 OUT = os.path.join(HERE, "libydst.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",

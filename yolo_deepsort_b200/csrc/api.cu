@@ -8,6 +8,7 @@
 #include "cosine_tc.cuh"
 #include "net.cuh"
 #include "tracker.cuh"
+#include "action.cuh"
 
 namespace ydst {
 static thread_local std::string g_err;
@@ -418,6 +419,30 @@ int ydst_lsap(const float* cost_dev, int nr, int nc, float max_dist, int* rows_h
 }
 
 // ---------------- tracker ----------------
+// ---- ActionIdentify (csrc/action.cu) ----
+struct ydst_action { ydst::ActionIdentifyDev* impl; };
+int ydst_action_create(int max_age, int max_size, const int* kinds, const int* class_ids, const double* p0, const double* p1, int n_rules,
+                       int capacity, ydst_action** out) {
+    YDST_API_BEGIN
+    YDST_CHECK(out && (n_rules == 0 || (kinds && class_ids && p0 && p1)), "null argument");
+    auto* h = new ydst_action{nullptr};
+    try { h->impl = ydst::action_create(max_age, max_size, kinds, class_ids, p0, p1, n_rules, capacity); }
+    catch (...) { delete h; throw; }
+    *out = h;
+    YDST_API_END
+}
+int ydst_action_destroy(ydst_action* a) {
+    YDST_API_BEGIN
+    if (a) { ydst::action_destroy(a->impl); delete a; }
+    YDST_API_END
+}
+int ydst_action_update(ydst_action* a, const int32_t* rows_host, int k, double timestamp, int32_t* triples_host, int* n_host, void* stream) {
+    YDST_API_BEGIN
+    YDST_CHECK(a && a->impl && triples_host && n_host && (k == 0 || rows_host), "null argument");
+    *n_host = ydst::action_update(a->impl, rows_host, k, timestamp, triples_host, S(stream));
+    YDST_API_END
+}
+
 int ydst_tracker_create(double max_dist, double max_iou_distance, int max_age, int n_init, int nn_budget, int cap_tracks, int cap_dets,
                         ydst_tracker** out) {
     YDST_API_BEGIN
