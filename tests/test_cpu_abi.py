@@ -97,3 +97,26 @@ def test_planner_micro_batch_choices(cdll):
     # few waves with streamed weights stay on plain launches (two co-resident CTAs per SM)
     bn, ks, occ, ctas, _ = tiling(cdll, 8, 76, 76, 256, 128, 1)
     assert ctas == (8 * 78 * 78 + 127) // 128 * (128 // bn) and occ == 2
+
+
+def test_planner_round2_rules(cdll, monkeypatch):
+    """The measured rules of DESIGN.md 4.1 (9-12): persistent CTA pairs for 3x3 layers from two tiles per SM on, plain launches
+    below, and the knobs that switch both families off."""
+    # 3x3 128->256 @76x76 at micro-batch 8: 381 tiles -> 74 clusters of two persistent CTAs (148 CTAs), one CTA per SM
+    bn, ks, occ, ctas, _ = tiling(cdll, 8, 76, 76, 128, 256, 3)
+    assert (bn, ks, occ, ctas) == (256, 1, 1, 148)
+    # ReID layer4 at 368 crops: 348 tiles >= 2 x 148 -> persistent pairs as well
+    bn, ks, occ, ctas, _ = tiling(cdll, 368, 8, 4, 512, 512, 3)
+    assert (bn, ks, ctas) == (256, 1, 148)
+    # 38x38 256->512 (200 tiles: between one and two waves) and 19x19 512->1024 (112 tiles of 128 x 256): plain launches
+    bn, ks, occ, ctas, _ = tiling(cdll, 8, 38, 38, 256, 512, 3)
+    assert (bn, ks, ctas) == (256, 1, 200)
+    bn, ks, occ, ctas, _ = tiling(cdll, 8, 19, 19, 512, 1024, 3)
+    assert (bn, ks, ctas) == (128, 1, 28 * 8)                            # paired 128 x 128 tiles, two per SM
+    # knobs: no pairs, no persistent loop -> every layer is one tile per CTA again
+    monkeypatch.setenv("YDST_CTA2", "0")
+    monkeypatch.setenv("YDST_PERSISTENT", "0")
+    for shape in [(8, 76, 76, 128, 256, 3), (408, 64, 32, 64, 64, 3), (8, 304, 304, 64, 32, 1)]:
+        bn, ks, occ, ctas, _ = tiling(cdll, *shape)
+        N, H, W, cin, cout, k = shape
+        assert ctas == (N * (H + 2) * (W + 2) + 127) // 128 * ((max(cout, 64) + bn - 1) // bn) * ks
