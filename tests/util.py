@@ -58,37 +58,3 @@ def conv2d_ref(x_nhwc, w, stride, bn=None, bias=None, act=0, res=None, res_mode=
     if res_mode == 1:
         y = y + r
     return y.permute(0, 2, 3, 1).contiguous()
-
-
-def match_boxes(got, ref):
-    """Order-free pairing of two equally long box lists: returns perm with got[perm[i]] paired to ref[i] (minimum total
-    L-inf distance).  The detector's fp16 activations can swap the ORDER of two detections whose fp32 scores are
-    nearly tied; the pairing itself is unambiguous because distinct detections are many pixels apart."""
-    from scipy.optimize import linear_sum_assignment
-    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
-    assert got.shape == ref.shape
-    if len(ref) == 0:
-        return np.zeros(0, np.int64)
-    cost = np.abs(ref[:, None, :] - got[None, :, :]).max(-1)
-    r, c = linear_sum_assignment(cost)
-    perm = np.zeros(len(ref), np.int64)
-    perm[r] = c
-    return perm
-
-
-class IdBijection:
-    """Track ids are handed out in detection order (deep_sort/sort/tracker.py:160-161), so a swapped pair of
-    near-tied detections relabels two tracks.  The end-to-end tests therefore require the got<->ref track-id
-    relation to be ONE bijection that stays fixed over the whole clip (the stage-isolated tracker tests, fed
-    identical detections, require the ids themselves to be bit-exact)."""
-
-    def __init__(self):
-        self.fwd, self.bwd = {}, {}
-
-    def check(self, got_ids, ref_ids, where=""):
-        for g, r in zip(np.asarray(got_ids).tolist(), np.asarray(ref_ids).tolist()):
-            assert self.fwd.setdefault(r, g) == g and self.bwd.setdefault(g, r) == r, \
-                f"{where}: track id relation is not a fixed bijection (ref {r} -> got {g}, seen {self.fwd.get(r)} / {self.bwd.get(g)})"
-
-    def identity_fraction(self):
-        return float(np.mean([k == v for k, v in self.fwd.items()])) if self.fwd else 1.0
