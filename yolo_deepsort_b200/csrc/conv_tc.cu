@@ -1697,7 +1697,7 @@ ConvTiling conv_tc_choose_tiling(int m_tiles128, int cout16, int taps, int cin_b
                     const int fixed_p = a_st * a_stage + 6144;
                     int b_stages = std::min(std::min(8, pers ? 8 : total_b), (budget - fixed_p) / b_stage);
                     // weight-stationary persistent tiles: the N tile's whole weight slab fits and is fetched once per column block
-                    const bool resident = pers && !c2 && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
+                    const bool resident = pers && (!c2 || env_int("YDST_CTA2_RESIDENT", 1)) && total_b <= 16 && total_b * b_stage <= budget - fixed_p && m_tiles >= 2 * kSms / std::max(1, n_tiles) &&
                                           env_int("YDST_B_RESIDENT", 1);
                     if (resident) b_stages = total_b;
                     if (b_stages < (pers && !resident ? 2 : 1)) continue;
