@@ -594,21 +594,22 @@ __device__ __forceinline__ void epilogue_persistent(const ConvTcParams& p, const
             staged_tn = tn;
         }
         const int ab = it & 1;
-        {
-            const uint32_t bar = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
-            uint32_t spins = 0;
-            while (!mbar_try_wait(bar, par)) { __nanosleep(32); if (++spins > (1u << 26)) __trap(); }
-        }
-        tcgen05_fence_after();
-        if (tr && it < 16) p.trace[16 + it * 8 + 2] = (unsigned long long)clock64();
 #pragma unroll 1
         for (int h = 0; h < kMp; ++h) {                             // the 128-row accumulators of this tile, one after the other
+        // (the row's geometry first: it is ready by the time the accumulator is)
         const int p0 = (tm * kMp + h) * kBlockM;
         const long long pp = (long long)p0 + row;
-        const int rem = (int)(pp % HpWp);
+        const int rem = (int)((unsigned)pp % (unsigned)HpWp);          // (P_total < 2^31, checked by the planner: a 64-bit modulo costs ~100 instructions)
         const int y = rem / Wp, xx = rem - y * Wp;
         const bool valid = pp < p.P_total && (p.gemm || (y >= 1 && y <= p.Ho && xx >= 1 && xx <= p.Wo));
         const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;             // border pixels are stored as zeros (branch-free)
+        if (h == 0) {
+            const uint32_t bar = bar_tfull + 8u * ab, par = ((uint32_t)(it >> 1)) & 1u;
+            uint32_t spins = 0;
+            while (!mbar_try_wait(bar, par)) { __nanosleep(32); if (++spins > (1u << 26)) __trap(); }
+            tcgen05_fence_after();
+            if (tr && it < 16) p.trace[16 + it * 8 + 2] = (unsigned long long)clock64();
+        }
         const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * kMp + h) * bn);
 #pragma unroll 1
         for (int g = 0; g < ngroups; ++g, ++q) {
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         if (p.mode == 0) {
             const long long pp = (long long)p0 + row;
             const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
-            const int rem = (int)(pp % HpWp);
+            const int rem = (int)((unsigned)pp % (unsigned)HpWp);          // (P_total < 2^31, checked by the planner: a 64-bit modulo costs ~100 instructions)
             const int y = rem / Wp, x = rem - y * Wp;
             valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
             pix = pp;
@@ -999,7 +1000,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv_tc_pers_kernel(const __grid
             if (p.mode == 0) {
                 const long long pp = (long long)p0 + row;
                 const int Wp = p.Wo + 2, HpWp = (p.Ho + 2) * Wp;
-                const int rem = (int)(pp % HpWp);
+                const int rem = (int)((unsigned)pp % (unsigned)HpWp);          // (P_total < 2^31, checked by the planner: a 64-bit modulo costs ~100 instructions)
                 const int y = rem / Wp, x = rem - y * Wp;
                 valid = pp < p.P_total && y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo;
                 pix = pp;
@@ -1442,7 +1443,7 @@ __global__ void __launch_bounds__(kThreads2, kPers ? 1 : 2) conv_tc2_kernel(cons
             const uint32_t tmem_d = tmem_base + (uint32_t)((ab * mp + h) * p.block_n);
             constexpr uint32_t bar_rel = 0u;                       // (no second tile: nobody waits for the accumulator)
             const long long pp = (long long)p0 + row;
-            const int rem = (int)(pp % HpWp);
+            const int rem = (int)((unsigned)pp % (unsigned)HpWp);          // (P_total < 2^31, checked by the planner: a 64-bit modulo costs ~100 instructions)
             const int y = rem / Wp, x = rem - y * Wp;
             const bool valid = pp < p.P_total && (p.gemm || (y >= 1 && y <= p.Ho && x >= 1 && x <= p.Wo));
             if (p.ksplit == 1) {
@@ -1782,6 +1783,7 @@ void conv_tc_plan(ConvTcLaunch& L, const Act& in, const Act& out, const __half* 
     p.cout = (cout_real + 15) & ~15;
     YDST_CHECK(out_f32 != nullptr || out.C == cout_real, "output view has %d channels, conv produces %d", out.C, cout_real);
     p.N = out.N; p.Ho = out.H; p.Wo = out.W;
+    YDST_CHECK(out.pixels() < (1LL << 31) && in.pixels() < (1LL << 31), "conv_tc: more than 2^31 padded pixels per launch");
     p.in_Wp = in.W + 2;
     p.scale = scale; p.bias = bias; p.act = act;
     p.res_mode = res_mode;

@@ -489,6 +489,14 @@ __device__ __forceinline__ bool decode_idx(const Act& a, long long idx, int& n, 
     const int cg = a.C >> 3;
     const long long total = (long long)a.N * a.H * a.W * cg;
     if (idx >= total) return false;
+    if (total < (1LL << 31)) {                             // (every tensor of the path: 32-bit divisions cost ~20 instructions, 64-bit ones ~100 each)
+        const unsigned u = (unsigned)idx, t1 = u / (unsigned)cg, t2 = t1 / (unsigned)a.W, t3 = t2 / (unsigned)a.H;
+        c = (int)(u - t1 * (unsigned)cg) * 8;
+        x = (int)(t1 - t2 * (unsigned)a.W);
+        y = (int)(t2 - t3 * (unsigned)a.H);
+        n = (int)t3;
+        return true;
+    }
     c = (int)(idx % cg) * 8;
     long long t = idx / cg;
     x = (int)(t % a.W); t /= a.W;
